@@ -1,0 +1,170 @@
+"""ctypes binding of include/ema_b200.h (no compute here; see ema_b200/csrc)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libema_b200.so")
+
+
+class EmabError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libema_b200.so; there is no fallback if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise EmabError(f"{_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(ema_b200 has no CPU fallback)")
+        L = C.CDLL(_SO)
+        L.emab_last_error.restype = C.c_char_p
+        L.emab_last_kernel_ms.restype = C.c_double
+        L.emab_last_kernel_ms.argtypes = [C.c_void_p]
+        L.emab_last_launches.argtypes = [C.c_void_p]
+        L.emab_index_build_ms.restype = C.c_double
+        L.emab_index_build_ms.argtypes = [C.c_void_p]
+        L.emab_index_free.argtypes = [C.c_void_p]
+        L.emab_ctx_free.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise EmabError(f"libema_b200 error {rc}: {lib().emab_last_error().decode(errors='replace')}")
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _pack(seqs):
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs])
+    flat = np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]) if len(seqs) and off[-1] else np.zeros(1, np.uint8)
+    return np.ascontiguousarray(flat), off
+
+
+class Index:
+    """FM index + packed reference resident in one GPU's HBM (emab_index_load)."""
+
+    def __init__(self, prefix: str, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().emab_index_load(prefix.encode(), device, C.byref(self._h)))
+        info = np.zeros(12, dtype=np.int64)
+        _check(lib().emab_index_info(self._h, _p(info, C.c_int64)))
+        self.info = info
+        self.l_pac, self.n_seqs, self.primary, self.seq_len = (int(x) for x in info[:4])
+        self.contigs = []
+        for i in range(self.n_seqs):
+            off, ln, name = C.c_int64(), C.c_int32(), C.create_string_buffer(512)
+            _check(lib().emab_index_contig(self._h, i, C.byref(off), C.byref(ln), name, 512))
+            self.contigs.append((name.value.decode(), off.value, ln.value))
+
+    @property
+    def build_ms(self) -> float:
+        return lib().emab_index_build_ms(self._h)
+
+    def close(self):
+        if self._h:
+            lib().emab_index_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One worker (CUDA stream + scratch) — emab_ctx_create."""
+
+    def __init__(self, index: Index | None = None):
+        self._h = C.c_void_p()
+        self.index = index
+        _check(lib().emab_ctx_create(index._h if index else None, C.byref(self._h)))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return lib().emab_last_kernel_ms(self._h)
+
+    @property
+    def last_launches(self) -> int:
+        return lib().emab_last_launches(self._h)
+
+    def close(self):
+        if self._h:
+            lib().emab_ctx_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def extend_batch(ctx: Context, qs, ts, h0, w=100, end_bonus=5, zdrop=100):
+    """ksw_extend2 over a batch -> (out[n,6] = score,qle,tle,gtle,gscore,max_off ; cells)"""
+    q, qo = _pack(qs)
+    t, to = _pack(ts)
+    h0 = np.ascontiguousarray(h0, dtype=np.int32)
+    out = np.zeros((len(qs), 6), dtype=np.int32)
+    cells = C.c_int64(0)
+    _check(lib().emab_extend_batch(ctx._h, len(qs), _p(q, C.c_uint8), _p(qo, C.c_int64), _p(t, C.c_uint8), _p(to, C.c_int64),
+                                   _p(h0, C.c_int32), w, end_bonus, zdrop, _p(out, C.c_int32), C.byref(cells)))
+    return out, cells.value
+
+
+def global_batch(ctx: Context, qs, ts, ws, max_cigar=64):
+    """ksw_global2 over a batch -> (out[n,2] = score,n_cigar ; cigar[n,max_cigar] ; cells)"""
+    q, qo = _pack(qs)
+    t, to = _pack(ts)
+    ws = np.ascontiguousarray(ws, dtype=np.int32)
+    out = np.zeros((len(qs), 2), dtype=np.int32)
+    cig = np.zeros((len(qs), max_cigar), dtype=np.uint32)
+    cells = C.c_int64(0)
+    _check(lib().emab_global_batch(ctx._h, len(qs), _p(q, C.c_uint8), _p(qo, C.c_int64), _p(t, C.c_uint8), _p(to, C.c_int64),
+                                   _p(ws, C.c_int32), _p(out, C.c_int32), _p(cig, C.c_uint32), max_cigar, C.byref(cells)))
+    return out, cig, cells.value
+
+
+def local_batch(ctx: Context, qs, ts):
+    """ksw_align2 (mem_matesw flags) over a batch -> (out[n,7] = score,te,qe,score2,te2,tb,qb ; cells)"""
+    q, qo = _pack(qs)
+    t, to = _pack(ts)
+    out = np.zeros((len(qs), 7), dtype=np.int32)
+    cells = C.c_int64(0)
+    _check(lib().emab_local_batch(ctx._h, len(qs), _p(q, C.c_uint8), _p(qo, C.c_int64), _p(t, C.c_uint8), _p(to, C.c_int64),
+                                  _p(out, C.c_int32), C.byref(cells)))
+    return out, cells.value
+
+
+def smem_batch(ctx: Context, reads, max_intv=128):
+    """mem_collect_intv over a batch of nt4 reads -> (list of (n_i,4) int64 arrays ; block touches)"""
+    s, off = _pack(reads)
+    n = len(reads)
+    iv = np.zeros((n, max_intv, 4), dtype=np.int64)
+    cnt = np.zeros(n, dtype=np.int32)
+    touches = C.c_int64(0)
+    _check(lib().emab_smem_batch(ctx._h, n, _p(s, C.c_uint8), _p(off, C.c_int64), _p(iv, C.c_int64), _p(cnt, C.c_int32),
+                                 max_intv, C.byref(touches)))
+    return [iv[i, :cnt[i]] for i in range(n)], touches.value
+
+
+def sa_batch(ctx: Context, ks, mode=0):
+    """bwt_sa for SA indices ks (mode 0: dense SA, 1: LF walk over the sampled SA)"""
+    ks = np.ascontiguousarray(ks, dtype=np.int64)
+    out = np.zeros_like(ks)
+    _check(lib().emab_sa_batch(ctx._h, len(ks), _p(ks, C.c_int64), _p(out, C.c_int64), mode))
+    return out

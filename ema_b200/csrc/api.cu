@@ -1,0 +1,549 @@
+// C ABI of libema_b200.so (include/ema_b200.h): index residency, worker contexts and the
+// kernel-level batch entry points.  Pipeline entry points live in pipeline.cu.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../include/ema_b200.h"
+#include "runtime.cuh"
+#include "fmindex.cuh"
+#include "seed.cuh"
+#include "ksw_warp.cuh"
+
+thread_local char emab_errbuf[512] = "";
+
+extern "C" const char *emab_last_error(void) { return emab_errbuf; }
+extern "C" int emab_version(void) { return 100; }
+extern "C" int emab_device_count(int *n)
+{
+	CUDA_TRY(cudaGetDeviceCount(n));
+	return EMAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// index
+// ---------------------------------------------------------------------------------------------
+static int read_file(const std::string &path, std::vector<uint8_t> &out)
+{
+	FILE *f = fopen(path.c_str(), "rb");
+	if (!f) { snprintf(emab_errbuf, sizeof emab_errbuf, "cannot open %s", path.c_str()); return EMAB_ERR_IO; }
+	fseek(f, 0, SEEK_END);
+	long n = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	out.resize(n);
+	size_t got = n ? fread(out.data(), 1, n, f) : 0;
+	fclose(f);
+	if ((long)got != n) { snprintf(emab_errbuf, sizeof emab_errbuf, "short read on %s", path.c_str()); return EMAB_ERR_IO; }
+	return EMAB_OK;
+}
+
+// Dense SA: walk LF from every sampled slot until the next sampled slot, writing SA values on the
+// way.  The walks partition the text, so every SA slot is written exactly once (N LF steps total,
+// against ~31 N for looking every slot up with bwt_sa).  Values are those of bwa/bwt.c:86-96.
+template <class T>
+__global__ void k_build_dense_sa(DevIndex ix, T *dense, uint64_t n_sa)
+{
+	uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= n_sa) return;
+	Fm fm{ix, 0};
+	uint64_t k = m * (uint64_t)ix.sa_intv;
+	uint64_t s = m == 0 ? ix.seq_len : ix.sa_sampled[m];  // SA[0] is the empty suffix (bwa/bwt.c:76,83)
+	uint64_t mask = (uint64_t)ix.sa_intv - 1;
+	dense[k] = (T)s;
+	for (;;) {
+		k = bwt_invPsi(fm, k);
+		if ((k & mask) == 0) break;
+		--s;
+		dense[k] = (T)s;
+	}
+}
+
+extern "C" int emab_index_load(const char *prefix, int device, emab_index_t **out)
+{
+	*out = nullptr;
+	int ndev = 0;
+	CUDA_TRY(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) { snprintf(emab_errbuf, sizeof emab_errbuf, "no CUDA device %d", device); return EMAB_ERR_CUDA; }
+	CUDA_TRY(cudaSetDevice(device));
+	std::string pre(prefix);
+	std::vector<uint8_t> bwt, sa, pac;
+	int rc;
+	if ((rc = read_file(pre + ".bwt", bwt)) || (rc = read_file(pre + ".sa", sa)) || (rc = read_file(pre + ".pac", pac))) return rc;
+	if (bwt.size() < 40 || sa.size() < 56) { snprintf(emab_errbuf, sizeof emab_errbuf, "truncated index files"); return EMAB_ERR_IO; }
+	emab_index *ix = new emab_index();
+	ix->device = device;
+	const uint64_t *bw = (const uint64_t *)bwt.data();
+	ix->d.primary = bw[0];
+	ix->d.L2[0] = 0;
+	for (int i = 0; i < 4; ++i) ix->d.L2[i + 1] = bw[1 + i];
+	ix->d.seq_len = ix->d.L2[4];
+	ix->bwt_size_u32 = (bwt.size() - 40) >> 2;
+	ix->d.n_blocks = ix->bwt_size_u32 / 16;
+	const uint64_t *sw = (const uint64_t *)sa.data();
+	if (sw[0] != ix->d.primary || sw[6] != ix->d.seq_len) { snprintf(emab_errbuf, sizeof emab_errbuf, "SA-BWT inconsistency"); delete ix; return EMAB_ERR_IO; }
+	ix->d.sa_intv = (int)sw[5];
+	ix->n_sa = (ix->d.seq_len + ix->d.sa_intv) / ix->d.sa_intv;
+	if ((ix->d.sa_intv & (ix->d.sa_intv - 1)) || sa.size() < 56 + (ix->n_sa - 1) * 8) { snprintf(emab_errbuf, sizeof emab_errbuf, "bad .sa file"); delete ix; return EMAB_ERR_IO; }
+	{  // .ann (bwa/bntseq.c:109-137)
+		FILE *f = fopen((pre + ".ann").c_str(), "r");
+		if (!f) { snprintf(emab_errbuf, sizeof emab_errbuf, "cannot open %s.ann", prefix); delete ix; return EMAB_ERR_IO; }
+		long long xx; int n_seqs; unsigned seed;
+		char name[8192];
+		if (fscanf(f, "%lld%d%u", &xx, &n_seqs, &seed) != 3) { fclose(f); delete ix; snprintf(emab_errbuf, sizeof emab_errbuf, "bad .ann"); return EMAB_ERR_IO; }
+		ix->d.l_pac = xx; ix->d.n_seqs = n_seqs;
+		for (int i = 0; i < n_seqs; ++i) {
+			unsigned gi; int c, l, na;
+			if (fscanf(f, "%u%8191s", &gi, name) != 2) break;
+			while ((c = fgetc(f)) != '\n' && c != EOF) {}
+			if (fscanf(f, "%lld%d%d", &xx, &l, &na) != 3) break;
+			ix->names.push_back(name); ix->ann_offset.push_back(xx); ix->ann_len.push_back(l);
+		}
+		fclose(f);
+		if ((int)ix->names.size() != n_seqs) { delete ix; snprintf(emab_errbuf, sizeof emab_errbuf, "bad .ann"); return EMAB_ERR_IO; }
+	}
+	if ((int64_t)pac.size() < ix->d.l_pac / 4 + 1 || (uint64_t)ix->d.l_pac * 2 != ix->d.seq_len) { delete ix; snprintf(emab_errbuf, sizeof emab_errbuf, "bad .pac"); return EMAB_ERR_IO; }
+	// upload verbatim
+	size_t bwt_bytes = ix->bwt_size_u32 * 4, sas_bytes = ix->n_sa * 8;
+	CUDA_TRY(cudaMalloc(&ix->d_bwt, bwt_bytes + 64));
+	CUDA_TRY(cudaMemcpy(ix->d_bwt, bwt.data() + 40, bwt_bytes, cudaMemcpyHostToDevice));
+	std::vector<uint64_t> sas(ix->n_sa);
+	sas[0] = ~0ull;
+	memcpy(sas.data() + 1, sw + 7, (ix->n_sa - 1) * 8);
+	CUDA_TRY(cudaMalloc(&ix->d_sa_sampled, sas_bytes));
+	CUDA_TRY(cudaMemcpy(ix->d_sa_sampled, sas.data(), sas_bytes, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&ix->d_pac, pac.size() + 16));
+	CUDA_TRY(cudaMemcpy(ix->d_pac, pac.data(), pac.size(), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&ix->d_ann_off, ix->ann_offset.size() * 8));
+	CUDA_TRY(cudaMemcpy(ix->d_ann_off, ix->ann_offset.data(), ix->ann_offset.size() * 8, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&ix->d_ann_len, ix->ann_len.size() * 4));
+	CUDA_TRY(cudaMemcpy(ix->d_ann_len, ix->ann_len.data(), ix->ann_len.size() * 4, cudaMemcpyHostToDevice));
+	ix->d.bwt = (const uint4 *)ix->d_bwt;
+	ix->d.sa_sampled = (const uint64_t *)ix->d_sa_sampled;
+	ix->d.pac = (const uint8_t *)ix->d_pac;
+	ix->d.ann_offset = (const int64_t *)ix->d_ann_off;
+	ix->d.ann_len = (const int32_t *)ix->d_ann_len;
+	// dense SA
+	const bool small = ix->d.seq_len < 0xffffffffull;
+	size_t dense_bytes = (ix->d.seq_len + 1) * (small ? 4 : 8);
+	CUDA_TRY(cudaMalloc(&ix->d_sa_dense, dense_bytes));
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+	CUDA_TRY(cudaEventRecord(e0));
+	{
+		unsigned blocks = (unsigned)((ix->n_sa + 255) / 256);
+		if (small) k_build_dense_sa<uint32_t><<<blocks, 256>>>(ix->d, (uint32_t *)ix->d_sa_dense, ix->n_sa);
+		else k_build_dense_sa<uint64_t><<<blocks, 256>>>(ix->d, (uint64_t *)ix->d_sa_dense, ix->n_sa);
+	}
+	CUDA_TRY(cudaEventRecord(e1));
+	CUDA_TRY(cudaDeviceSynchronize());
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	ix->build_ms = ms;
+	if (small) ix->d.sa32 = (const uint32_t *)ix->d_sa_dense; else ix->d.sa64 = (const uint64_t *)ix->d_sa_dense;
+	ix->hbm_bytes = bwt_bytes + sas_bytes + pac.size() + dense_bytes;
+	*out = ix;
+	return EMAB_OK;
+}
+
+extern "C" void emab_index_free(emab_index_t *ix)
+{
+	if (!ix) return;
+	cudaSetDevice(ix->device);
+	cudaFree(ix->d_bwt); cudaFree(ix->d_sa_dense); cudaFree(ix->d_sa_sampled); cudaFree(ix->d_pac); cudaFree(ix->d_ann_off); cudaFree(ix->d_ann_len);
+	delete ix;
+}
+
+extern "C" int emab_index_info(const emab_index_t *ix, int64_t info[12])
+{
+	if (!ix) return EMAB_ERR_ARG;
+	info[0] = ix->d.l_pac; info[1] = ix->d.n_seqs; info[2] = (int64_t)ix->d.primary; info[3] = (int64_t)ix->d.seq_len;
+	for (int i = 0; i < 5; ++i) info[4 + i] = (int64_t)ix->d.L2[i];
+	info[9] = ix->d.sa_intv; info[10] = (int64_t)ix->n_sa; info[11] = (int64_t)ix->bwt_size_u32;
+	return EMAB_OK;
+}
+
+extern "C" int emab_index_contig(const emab_index_t *ix, int i, int64_t *offset, int32_t *len, char *name, int name_cap)
+{
+	if (!ix || i < 0 || i >= ix->d.n_seqs) return EMAB_ERR_ARG;
+	*offset = ix->ann_offset[i]; *len = ix->ann_len[i];
+	snprintf(name, name_cap, "%s", ix->names[i].c_str());
+	return EMAB_OK;
+}
+
+extern "C" double emab_index_build_ms(const emab_index_t *ix) { return ix ? ix->build_ms : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// contexts
+// ---------------------------------------------------------------------------------------------
+extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
+{
+	*out = nullptr;
+	int dev = ix ? ix->device : 0;
+	int ndev = 0;
+	CUDA_TRY(cudaGetDeviceCount(&ndev));
+	if (ndev <= 0) { snprintf(emab_errbuf, sizeof emab_errbuf, "no CUDA device"); return EMAB_ERR_CUDA; }
+	CUDA_TRY(cudaSetDevice(dev));
+	emab_ctx *c = new emab_ctx();
+	c->ix = ix;
+	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaEventCreate(&c->ev0));
+	CUDA_TRY(cudaEventCreate(&c->ev1));
+	CUDA_TRY(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+	c->n_sm = prop.multiProcessorCount;
+	*out = c;
+	return EMAB_OK;
+}
+
+extern "C" void emab_ctx_free(emab_ctx_t *c)
+{
+	if (!c) return;
+	for (auto &b : c->b) b.release();
+	cudaFree(c->d_counters);
+	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" double emab_last_kernel_ms(const emab_ctx_t *c) { return c ? c->last_ms : 0; }
+extern "C" int emab_last_launches(const emab_ctx_t *c) { return c ? c->last_launches : 0; }
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+static int upload(emab_ctx *c, DevBuf &b, const void *src, size_t bytes)
+{
+	TRY(b.ensure(bytes ? bytes : 1));
+	if (bytes) CUDA_TRY(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+	return EMAB_OK;
+}
+
+static int finish_timed(emab_ctx *c)
+{
+	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	float ms = 0;
+	CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+	c->last_ms = ms;
+	return EMAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Smith-Waterman batches: one warp per task, tasks handed out through an atomic counter so that
+// long and short tasks balance across the persistent grid (grid = SMs x resident blocks).
+// ---------------------------------------------------------------------------------------------
+#define SW_WARPS 8
+
+__device__ __forceinline__ int next_task(unsigned long long *counter, int lane)
+{
+	unsigned long long t = 0;
+	if (lane == 0) t = atomicAdd(counter, 1ull);
+	return (int)__shfl_sync(FULL_MASK, t, 0);
+}
+
+__global__ void __launch_bounds__(SW_WARPS * 32)
+k_extend_batch(int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff, const int32_t *h0,
+               int w, int end_bonus, int zdrop, int32_t *out, unsigned long long *counters)
+{
+	__shared__ WarpDP sm_all[SW_WARPS];
+	WarpDP &sm = sm_all[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31;
+	for (;;) {
+		int i = next_task(&counters[1], lane);
+		if (i >= n) break;
+		const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
+		const uint8_t *qp = q + qoff[i];
+		__syncwarp();
+		for (int j = lane; j < ql; j += 32) sm.q[j] = qp[j];
+		__syncwarp();
+		SeqFetch tf{t + toff[i], 1};
+		ExtResult r = warp_extend(sm, ql, tf, tl, w, end_bonus, zdrop, h0[i], &counters[0]);
+		if (lane == 0) {
+			int32_t *o = out + (size_t)i * 6;
+			o[0] = r.score; o[1] = r.qle; o[2] = r.tle; o[3] = r.gtle; o[4] = r.gscore; o[5] = r.max_off;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(SW_WARPS * 32)
+k_global_batch(int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff, const int32_t *w,
+               int32_t *out, uint32_t *cigar, int max_cigar, uint8_t *zbuf, size_t z_stride, uint32_t *tmpbuf, unsigned long long *counters)
+{
+	__shared__ WarpDP sm_all[SW_WARPS];
+	WarpDP &sm = sm_all[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31;
+	const int gw = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+	uint8_t *z = zbuf + (size_t)gw * z_stride;
+	uint32_t *tmp = tmpbuf + (size_t)gw * max_cigar;
+	for (;;) {
+		int i = next_task(&counters[1], lane);
+		if (i >= n) break;
+		const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
+		const uint8_t *qp = q + qoff[i];
+		__syncwarp();
+		for (int j = lane; j < ql; j += 32) sm.q[j] = qp[j];
+		__syncwarp();
+		SeqFetch tf{t + toff[i], 1};
+		int score = warp_global(sm, ql, tf, tl, w[i], z, &counters[0]);
+		__syncwarp();
+		int nc = global_backtrack(z, ql, tl, w[i], cigar + (size_t)i * max_cigar, max_cigar, tmp);
+		if (lane == 0) { out[i * 2] = score; out[i * 2 + 1] = nc; }
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(SW_WARPS * 32)
+k_local_batch(int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff, int32_t *out, unsigned long long *counters)
+{
+	__shared__ WarpDP sm_all[SW_WARPS];
+	WarpDP &sm = sm_all[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31;
+	for (;;) {
+		int i = next_task(&counters[1], lane);
+		if (i >= n) break;
+		const int ql = (int)(qoff[i + 1] - qoff[i]), tl = (int)(toff[i + 1] - toff[i]);
+		const uint8_t *qp = q + qoff[i];
+		__syncwarp();
+		for (int j = lane; j < ql; j += 32) sm.q[j] = qp[j];
+		__syncwarp();
+		SeqFetch tf{t + toff[i], 1};
+		LocResult r = warp_local(sm, ql, tf, tl, opt::min_seed_len * opt::a, ql * opt::a < 250, &counters[0]);
+		if (lane == 0) {
+			int32_t *o = out + (size_t)i * 7;
+			o[0] = r.score; o[1] = r.te; o[2] = r.qe; o[3] = r.score2; o[4] = r.te2; o[5] = r.tb; o[6] = r.qb;
+		}
+	}
+}
+
+static int check_lengths(int n, const int64_t *qoff, const int64_t *toff, int max_t)
+{
+	for (int i = 0; i < n; ++i) {
+		int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+		if (ql < 0 || tl < 0 || ql > EMAB_MAX_READ_LEN || (max_t && tl > max_t)) {
+			snprintf(emab_errbuf, sizeof emab_errbuf, "task %d: query length %lld (max %d) / target length %lld out of range", i, (long long)ql, EMAB_MAX_READ_LEN, (long long)tl);
+			return EMAB_ERR_ARG;
+		}
+	}
+	return EMAB_OK;
+}
+
+static int sw_grid(emab_ctx *c) { return c->n_sm * 4; }
+
+static int upload_sw_inputs(emab_ctx *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff)
+{
+	TRY(upload(c, c->b[0], q, (size_t)qoff[n]));
+	TRY(upload(c, c->b[1], qoff, (size_t)(n + 1) * 8));
+	TRY(upload(c, c->b[2], t, (size_t)toff[n]));
+	TRY(upload(c, c->b[3], toff, (size_t)(n + 1) * 8));
+	return EMAB_OK;
+}
+
+extern "C" int emab_extend_batch(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
+                                 const int32_t *h0, int w, int end_bonus, int zdrop, int32_t *out, int64_t *cells)
+{
+	if (!c || n < 0) return EMAB_ERR_ARG;
+	if (n == 0) { if (cells) *cells = 0; return EMAB_OK; }
+	TRY(check_lengths(n, qoff, toff, 0));
+	for (int i = 0; i < n; ++i) if (h0[i] <= 0) { snprintf(emab_errbuf, sizeof emab_errbuf, "task %d: h0 must be > 0 (bwa/ksw.c:421)", i); return EMAB_ERR_ARG; }
+	TRY(upload_sw_inputs(c, n, q, qoff, t, toff));
+	TRY(upload(c, c->b[4], h0, (size_t)n * 4));
+	TRY(c->b[5].ensure((size_t)n * 24));
+	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+	k_extend_batch<<<sw_grid(c), SW_WARPS * 32, 0, c->stream>>>(n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(), c->b[3].as<int64_t>(),
+	                                                             c->b[4].as<int32_t>(), w, end_bonus, zdrop, c->b[5].as<int32_t>(), c->d_counters);
+	c->last_launches = 1;
+	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(out, c->b[5].p, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
+	unsigned long long cnt[2];
+	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 16, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
+	if (cells) *cells = (int64_t)cnt[0];
+	return EMAB_OK;
+}
+
+extern "C" int emab_extend_resident_load(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff, const int32_t *h0)
+{
+	if (!c || n <= 0) return EMAB_ERR_ARG;
+	TRY(check_lengths(n, qoff, toff, 0));
+	TRY(upload_sw_inputs(c, n, q, qoff, t, toff));
+	TRY(upload(c, c->b[4], h0, (size_t)n * 4));
+	TRY(c->b[5].ensure((size_t)n * 24));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	c->res_n = n;
+	return EMAB_OK;
+}
+
+extern "C" int emab_extend_resident_run(emab_ctx_t *c, int w, int end_bonus, int zdrop, int reps, int32_t *out, int64_t *cells)
+{
+	if (!c || c->res_n <= 0 || reps <= 0) return EMAB_ERR_ARG;
+	const int n = c->res_n;
+	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+	for (int r = 0; r < reps; ++r) {
+		CUDA_TRY(cudaMemsetAsync(c->d_counters + 1, 0, 8, c->stream));
+		k_extend_batch<<<sw_grid(c), SW_WARPS * 32, 0, c->stream>>>(n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(), c->b[3].as<int64_t>(),
+		                                                             c->b[4].as<int32_t>(), w, end_bonus, zdrop, c->b[5].as<int32_t>(), c->d_counters);
+	}
+	c->last_launches = reps;
+	TRY(finish_timed(c));
+	if (out) CUDA_TRY(cudaMemcpy(out, c->b[5].p, (size_t)n * 24, cudaMemcpyDeviceToHost));
+	unsigned long long cnt = 0;
+	CUDA_TRY(cudaMemcpy(&cnt, c->d_counters, 8, cudaMemcpyDeviceToHost));
+	if (cells) *cells = (int64_t)(cnt / (unsigned long long)reps);
+	return EMAB_OK;
+}
+
+extern "C" int emab_global_batch(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
+                                 const int32_t *w, int32_t *out, uint32_t *cigar, int max_cigar, int64_t *cells)
+{
+	if (!c || n < 0 || max_cigar <= 0) return EMAB_ERR_ARG;
+	if (n == 0) { if (cells) *cells = 0; return EMAB_OK; }
+	TRY(check_lengths(n, qoff, toff, 0));
+	size_t z_stride = 1;
+	for (int i = 0; i < n; ++i) {
+		int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+		if (w[i] < 0) { snprintf(emab_errbuf, sizeof emab_errbuf, "task %d: negative band", i); return EMAB_ERR_ARG; }
+		int64_t ncol = ql < 2 * (int64_t)w[i] + 1 ? ql : 2 * (int64_t)w[i] + 1;
+		size_t need = (size_t)(ncol * tl) + 16;
+		if (need > z_stride) z_stride = need;
+	}
+	z_stride = (z_stride + 15) & ~(size_t)15;
+	const int grid = sw_grid(c), n_warps = grid * SW_WARPS;
+	TRY(upload_sw_inputs(c, n, q, qoff, t, toff));
+	TRY(upload(c, c->b[4], w, (size_t)n * 4));
+	TRY(c->b[5].ensure((size_t)n * 8));
+	TRY(c->b[6].ensure((size_t)n * max_cigar * 4));
+	TRY(c->b[7].ensure((size_t)n_warps * z_stride));
+	TRY(c->b[8].ensure((size_t)n_warps * max_cigar * 4));
+	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->b[6].p, 0, (size_t)n * max_cigar * 4, c->stream));
+	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+	k_global_batch<<<grid, SW_WARPS * 32, 0, c->stream>>>(n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(), c->b[3].as<int64_t>(),
+	                                                       c->b[4].as<int32_t>(), c->b[5].as<int32_t>(), c->b[6].as<uint32_t>(), max_cigar,
+	                                                       c->b[7].as<uint8_t>(), z_stride, c->b[8].as<uint32_t>(), c->d_counters);
+	c->last_launches = 1;
+	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(out, c->b[5].p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(cigar, c->b[6].p, (size_t)n * max_cigar * 4, cudaMemcpyDeviceToHost, c->stream));
+	unsigned long long cnt[2];
+	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 16, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
+	if (cells) *cells = (int64_t)cnt[0];
+	return EMAB_OK;
+}
+
+extern "C" int emab_local_batch(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
+                                int32_t *out, int64_t *cells)
+{
+	if (!c || n < 0) return EMAB_ERR_ARG;
+	if (n == 0) { if (cells) *cells = 0; return EMAB_OK; }
+	TRY(check_lengths(n, qoff, toff, KSW_MAX_TLEN));
+	TRY(upload_sw_inputs(c, n, q, qoff, t, toff));
+	TRY(c->b[5].ensure((size_t)n * 28));
+	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+	k_local_batch<<<sw_grid(c), SW_WARPS * 32, 0, c->stream>>>(n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(), c->b[3].as<int64_t>(),
+	                                                            c->b[5].as<int32_t>(), c->d_counters);
+	c->last_launches = 1;
+	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(out, c->b[5].p, (size_t)n * 28, cudaMemcpyDeviceToHost, c->stream));
+	unsigned long long cnt[2];
+	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 16, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
+	if (cells) *cells = (int64_t)cnt[0];
+	return EMAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FM index batches
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sa_batch(DevIndex ix, int n, const int64_t *k, int64_t *out, int mode)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	Fm fm{ix, 0};
+	out[i] = mode == 0 ? (int64_t)bwt_sa_dense(ix, (uint64_t)k[i]) : (int64_t)bwt_sa_walk(fm, (uint64_t)k[i]);
+}
+
+__global__ void __launch_bounds__(128)
+k_smem_batch(DevIndex ix, int n, const uint8_t *seq, const int64_t *off, Intv *intv, int32_t *n_intv, int max_intv,
+             Intv *scratch, int32_t *overflow, unsigned long long *counters)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned touches = 0;
+	if (r < n) {
+		Fm fm{ix, 0};
+		const int len = (int)(off[r + 1] - off[r]);
+		Intv *buf0 = scratch + (size_t)r * 2 * (EMAB_MAX_READ_LEN + 1);
+		int ovf = 0;
+		n_intv[r] = collect_intv(fm, len, seq + off[r], intv + (size_t)r * max_intv, max_intv, buf0, buf0 + EMAB_MAX_READ_LEN + 1, &ovf);
+		if (ovf) *overflow = 1;
+		touches = fm.touches;
+	}
+	// one atomic per warp
+	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(FULL_MASK, touches, d);
+	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(&counters[2], (unsigned long long)touches);
+}
+
+extern "C" int emab_sa_batch(emab_ctx_t *c, int n, const int64_t *k, int64_t *out, int mode)
+{
+	if (!c || !c->ix || n < 0) return EMAB_ERR_ARG;
+	if (n == 0) return EMAB_OK;
+	for (int i = 0; i < n; ++i) if (k[i] < 0 || (uint64_t)k[i] > c->ix->d.seq_len) { snprintf(emab_errbuf, sizeof emab_errbuf, "SA index out of range"); return EMAB_ERR_ARG; }
+	TRY(upload(c, c->b[0], k, (size_t)n * 8));
+	TRY(c->b[1].ensure((size_t)n * 8));
+	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+	k_sa_batch<<<(n + 255) / 256, 256, 0, c->stream>>>(c->ix->d, n, c->b[0].as<int64_t>(), c->b[1].as<int64_t>(), mode);
+	c->last_launches = 1;
+	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(out, c->b[1].p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
+	return EMAB_OK;
+}
+
+extern "C" int emab_smem_batch(emab_ctx_t *c, int n, const uint8_t *seq, const int64_t *off, int64_t *intervals, int32_t *n_intv,
+                               int max_intv, int64_t *touches)
+{
+	if (!c || !c->ix || n < 0 || max_intv <= 0) return EMAB_ERR_ARG;
+	if (n == 0) { if (touches) *touches = 0; return EMAB_OK; }
+	for (int i = 0; i < n; ++i) {
+		int64_t l = off[i + 1] - off[i];
+		if (l < 0 || l > EMAB_MAX_READ_LEN) { snprintf(emab_errbuf, sizeof emab_errbuf, "read %d: length %lld out of range (max %d)", i, (long long)l, EMAB_MAX_READ_LEN); return EMAB_ERR_ARG; }
+	}
+	TRY(upload(c, c->b[0], seq, (size_t)off[n]));
+	TRY(upload(c, c->b[1], off, (size_t)(n + 1) * 8));
+	TRY(c->b[2].ensure((size_t)n * max_intv * sizeof(Intv)));
+	TRY(c->b[3].ensure((size_t)n * 4 + 4));
+	TRY(c->b[4].ensure((size_t)n * 2 * (EMAB_MAX_READ_LEN + 1) * sizeof(Intv)));
+	int32_t *d_ovf = c->b[3].as<int32_t>() + n;
+	CUDA_TRY(cudaMemsetAsync(d_ovf, 0, 4, c->stream));
+	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+	k_smem_batch<<<(n + 127) / 128, 128, 0, c->stream>>>(c->ix->d, n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(),
+	                                                       max_intv, c->b[4].as<Intv>(), d_ovf, c->d_counters);
+	c->last_launches = 1;
+	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(intervals, c->b[2].p, (size_t)n * max_intv * sizeof(Intv), cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(n_intv, c->b[3].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+	int32_t ovf = 0;
+	unsigned long long cnt[3];
+	CUDA_TRY(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 24, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	CUDA_TRY(cudaGetLastError());
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_ms = ms;
+	if (touches) *touches = (int64_t)cnt[2];
+	if (ovf) { snprintf(emab_errbuf, sizeof emab_errbuf, "a read produced more than %d SA intervals", max_intv); return EMAB_ERR_OVERFLOW; }
+	return EMAB_OK;
+}

@@ -122,21 +122,28 @@ struct Aln {  // what append_alignments keeps of mem_aln_t / SingleReadAlignment
 };
 
 // ---------------------------------------------------------------------------------------------
-// small device helpers
+// small helpers.  EMAB_HD functions are thread-scalar and also compile for the host, where
+// tests/hostsim drives them for GPU-less unit tests of the control logic (never a product path).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
-__device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
-__device__ __forceinline__ int64_t lmax(int64_t a, int64_t b) { return a > b ? a : b; }
-__device__ __forceinline__ int64_t lmin(int64_t a, int64_t b) { return a < b ? a : b; }
+#define EMAB_HD __host__ __device__ inline
+#ifdef __CUDA_ARCH__
+#define emab_popc(x) __popc(x)
+#else
+#define emab_popc(x) __builtin_popcount(x)
+#endif
+EMAB_HD int imax(int a, int b) { return a > b ? a : b; }
+EMAB_HD int imin(int a, int b) { return a < b ? a : b; }
+EMAB_HD int64_t lmax(int64_t a, int64_t b) { return a > b ? a : b; }
+EMAB_HD int64_t lmin(int64_t a, int64_t b) { return a < b ? a : b; }
 
-__device__ __forceinline__ int64_t bns_depos(int64_t l_pac, int64_t pos, int *is_rev)
+EMAB_HD int64_t bns_depos(int64_t l_pac, int64_t pos, int *is_rev)
 {  // bwa/bntseq.h:87-90
 	*is_rev = pos >= l_pac;
 	return *is_rev ? (l_pac << 1) - 1 - pos : pos;
 }
 
 // base of the forward-reverse reference at coordinate p in [0, 2*l_pac)  (bwa/bntseq.c:403-424)
-__device__ __forceinline__ int ref_base(const DevIndex &ix, int64_t p)
+EMAB_HD int ref_base(const DevIndex &ix, int64_t p)
 {
 	if (p >= ix.l_pac) {
 		int64_t f = (ix.l_pac << 1) - 1 - p;
@@ -145,7 +152,7 @@ __device__ __forceinline__ int ref_base(const DevIndex &ix, int64_t p)
 	return (ix.pac[p >> 2] >> ((~p & 3) << 1)) & 3;
 }
 
-__device__ inline int bns_pos2rid(const DevIndex &ix, int64_t pos_f)
+EMAB_HD int bns_pos2rid(const DevIndex &ix, int64_t pos_f)
 {  // bwa/bntseq.c:354-368 (same bisection so that out-of-range behaviour is identical)
 	if (pos_f >= ix.l_pac) return -1;
 	int left = 0, mid = 0, right = ix.n_seqs;
@@ -160,7 +167,7 @@ __device__ inline int bns_pos2rid(const DevIndex &ix, int64_t pos_f)
 	return mid;
 }
 
-__device__ inline int bns_intv2rid(const DevIndex &ix, int64_t rb, int64_t re)
+EMAB_HD int bns_intv2rid(const DevIndex &ix, int64_t rb, int64_t re)
 {  // bwa/bntseq.c:370-378
 	if (rb < ix.l_pac && re > ix.l_pac) return -2;
 	int is_rev;
@@ -171,7 +178,7 @@ __device__ inline int bns_intv2rid(const DevIndex &ix, int64_t rb, int64_t re)
 
 // bns_fetch_seq's clamping (bwa/bntseq.c:426-451) without materialising the sequence: the DP
 // kernels read bases straight from the packed reference.
-__device__ inline void bns_clamp(const DevIndex &ix, int64_t *beg, int64_t mid, int64_t *end, int *rid)
+EMAB_HD void bns_clamp(const DevIndex &ix, int64_t *beg, int64_t mid, int64_t *end, int *rid)
 {
 	int is_rev;
 	*rid = bns_pos2rid(ix, bns_depos(ix.l_pac, mid, &is_rev));
@@ -187,7 +194,7 @@ __device__ inline void bns_clamp(const DevIndex &ix, int64_t *beg, int64_t mid, 
 }
 
 // substitution score of bwa_fill_scmat(1, 4) (bwa/bwa.c:136-146): 1 / -4, and -1 against N
-__device__ __forceinline__ int sc_mat(int t, int q)
+EMAB_HD int sc_mat(int t, int q)
 {
 	return (t > 3 || q > 3) ? -1 : (t == q ? opt::a : -opt::b);
 }

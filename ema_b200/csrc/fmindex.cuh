@@ -5,42 +5,52 @@
 
 // One 64-byte Occ block = 4 x 128-bit loads.  ld.global.nc keeps the (read-only) index on the
 // non-coherent path; blocks are 64-byte aligned so each load is one fully used 32-byte sector pair.
-__device__ __forceinline__ uint4 ldg128(const uint4 *p)
+EMAB_HD uint4 ldg128(const uint4 *p)
 {
+#ifdef __CUDA_ARCH__
 	uint4 r;
 	asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
 	return r;
+#else
+	return *p;
+#endif
 }
+
+struct Fm {  // per-thread view of the index + instrumentation (64-byte block loads)
+	const DevIndex &ix;
+	unsigned touches;
+};
 
 struct OccBlock {
 	uint4 c0, c1;  // cumulative counts of A,C / G,T before the block (4 x u64)
 	uint4 b0, b1;  // 8 x u32, 16 symbols each, symbol i at bits ((~i)&15)<<1
 };
 
-__device__ __forceinline__ OccBlock load_block(const DevIndex &ix, uint64_t blk)
+EMAB_HD OccBlock load_block(Fm &fm, uint64_t blk)
 {
-	const uint4 *p = ix.bwt + (blk << 2);
+	const uint4 *p = fm.ix.bwt + (blk << 2);
+	++fm.touches;
 	OccBlock o;
 	o.c0 = ldg128(p); o.c1 = ldg128(p + 1); o.b0 = ldg128(p + 2); o.b1 = ldg128(p + 3);
 	return o;
 }
 
 // counts of C,G,T (and all symbols) among the first n (0..16) symbols of word w
-__device__ __forceinline__ void word_counts(uint32_t w, int n, uint32_t &nc, uint32_t &ng, uint32_t &nt)
+EMAB_HD void word_counts(uint32_t w, int n, uint32_t &nc, uint32_t &ng, uint32_t &nt)
 {
 	n = n < 0 ? 0 : (n > 16 ? 16 : n);
 	uint32_t mask = ~(uint32_t)(0xffffffffull >> (n << 1));  // top n symbols (MSB first)
 	w &= mask;
 	uint32_t hi = (w >> 1) & 0x55555555u, lo = w & 0x55555555u;
-	uint32_t t = __popc(hi & lo);
+	uint32_t t = emab_popc(hi & lo);
 	nt += t;
-	ng += __popc(hi) - t;
-	nc += __popc(lo) - t;
+	ng += emab_popc(hi) - t;
+	nc += emab_popc(lo) - t;
 }
 
 // Occ of all four bases in B[0..k] inclusive, k already adjusted for the primary and != -1.
 // `idx` = k & 127 within block `o`.
-__device__ __forceinline__ void block_occ4(const OccBlock &o, int idx, uint64_t cnt[4])
+EMAB_HD void block_occ4(const OccBlock &o, int idx, uint64_t cnt[4])
 {
 	uint32_t nc = 0, ng = 0, nt = 0;
 	int n = idx + 1;  // symbols to count
@@ -61,23 +71,23 @@ __device__ __forceinline__ void block_occ4(const OccBlock &o, int idx, uint64_t 
 
 // bwt_2occ4(k, l): two positions, one block load when they share a block (bwa/bwt.c:189-220).
 // *touches counts 64-byte block loads (the roofline unit of SURVEY.md §8d).
-__device__ __forceinline__ void bwt_2occ4(const DevIndex &ix, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t cl[4])
+EMAB_HD void bwt_2occ4(Fm &fm, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t cl[4])
 {
 	const uint64_t NEG1 = ~0ull;
-	uint64_t _k = k - (k >= ix.primary && k != NEG1), _l = l - (l >= ix.primary && l != NEG1);
+	uint64_t _k = k - (k >= fm.ix.primary && k != NEG1), _l = l - (l >= fm.ix.primary && l != NEG1);
 	if (k == NEG1) { ck[0] = ck[1] = ck[2] = ck[3] = 0; }
 	if (l == NEG1) { cl[0] = cl[1] = cl[2] = cl[3] = 0; }
 	if (k != NEG1 && l != NEG1 && (_k >> 7) == (_l >> 7)) {
-		OccBlock o = load_block(ix, _k >> 7);
+		OccBlock o = load_block(fm, _k >> 7);
 		block_occ4(o, (int)(_k & 127), ck);
 		block_occ4(o, (int)(_l & 127), cl);
 		return;
 	}
-	if (k != NEG1) { OccBlock o = load_block(ix, _k >> 7); block_occ4(o, (int)(_k & 127), ck); }
-	if (l != NEG1) { OccBlock o = load_block(ix, _l >> 7); block_occ4(o, (int)(_l & 127), cl); }
+	if (k != NEG1) { OccBlock o = load_block(fm, _k >> 7); block_occ4(o, (int)(_k & 127), ck); }
+	if (l != NEG1) { OccBlock o = load_block(fm, _l >> 7); block_occ4(o, (int)(_l & 127), cl); }
 }
 
-__device__ __forceinline__ void bwt_set_intv(const DevIndex &ix, int c, Intv &ik)
+EMAB_HD void bwt_set_intv(const DevIndex &ix, int c, Intv &ik)
 {  // bwa/bwt.h:82
 	ik.x0 = ix.L2[c] + 1;
 	ik.x2 = ix.L2[c + 1] - ix.L2[c];
@@ -87,19 +97,19 @@ __device__ __forceinline__ void bwt_set_intv(const DevIndex &ix, int c, Intv &ik
 
 // bwt_extend (bwa/bwt.c:262-275).  x[] is indexed as {x0,x1,x2}; is_back selects which coordinate
 // is the one being walked.  ok[c].info is left untouched (callers set it).
-__device__ __forceinline__ void bwt_extend(const DevIndex &ix, const Intv &ik, Intv ok[4], int is_back)
+EMAB_HD void bwt_extend(Fm &fm, const Intv &ik, Intv ok[4], int is_back)
 {
 	uint64_t tk[4], tl[4];
 	uint64_t xa = is_back ? ik.x0 : ik.x1;  // x[!is_back]
 	uint64_t xb = is_back ? ik.x1 : ik.x0;  // x[is_back]
-	bwt_2occ4(ix, xa - 1, xa - 1 + ik.x2, tk, tl);
+	bwt_2occ4(fm, xa - 1, xa - 1 + ik.x2, tk, tl);
 	uint64_t na[4], nb[4], ns[4];
 #pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		na[i] = ix.L2[i] + 1 + tk[i];
+		na[i] = fm.ix.L2[i] + 1 + tk[i];
 		ns[i] = tl[i] - tk[i];
 	}
-	nb[3] = xb + (xa <= ix.primary && xa + ik.x2 - 1 >= ix.primary);
+	nb[3] = xb + (xa <= fm.ix.primary && xa + ik.x2 - 1 >= fm.ix.primary);
 	nb[2] = nb[3] + ns[3];
 	nb[1] = nb[2] + ns[2];
 	nb[0] = nb[1] + ns[1];
@@ -112,10 +122,10 @@ __device__ __forceinline__ void bwt_extend(const DevIndex &ix, const Intv &ik, I
 }
 
 // Only the interval for base c (what every caller on the path consumes).
-__device__ __forceinline__ Intv bwt_extend1(const DevIndex &ix, const Intv &ik, int c, int is_back)
+EMAB_HD Intv bwt_extend1(Fm &fm, const Intv &ik, int c, int is_back)
 {
 	Intv ok[4];
-	bwt_extend(ix, ik, ok, is_back);
+	bwt_extend(fm, ik, ok, is_back);
 	Intv r = ok[0];
 	if (c == 1) r = ok[1];
 	if (c == 2) r = ok[2];
@@ -125,7 +135,7 @@ __device__ __forceinline__ Intv bwt_extend1(const DevIndex &ix, const Intv &ik, 
 
 // bwt_sa through the dense suffix array: identical values to bwa/bwt.c:86-96 with no LF walk
 // (bwt_sa is a pure function of the index; SURVEY.md §7 hard part 6).
-__device__ __forceinline__ uint64_t bwt_sa_dense(const DevIndex &ix, uint64_t k)
+EMAB_HD uint64_t bwt_sa_dense(const DevIndex &ix, uint64_t k)
 {
 	if (ix.sa32) {
 		uint32_t v = ix.sa32[k];
@@ -135,11 +145,11 @@ __device__ __forceinline__ uint64_t bwt_sa_dense(const DevIndex &ix, uint64_t k)
 }
 
 // bwt_invPsi (bwa/bwt.c:53-59): LF-mapping step, used by the dense-SA builder and the walking bwt_sa.
-__device__ __forceinline__ uint64_t bwt_invPsi(const DevIndex &ix, uint64_t k)
+EMAB_HD uint64_t bwt_invPsi(Fm &fm, uint64_t k)
 {
-	if (k == ix.primary) return 0;
-	uint64_t x = k - (k > ix.primary);
-	OccBlock o = load_block(ix, x >> 7);
+	if (k == fm.ix.primary) return 0;
+	uint64_t x = k - (k > fm.ix.primary);
+	OccBlock o = load_block(fm, x >> 7);
 	int idx = (int)(x & 127);
 	uint32_t w;
 	{
@@ -157,14 +167,14 @@ __device__ __forceinline__ uint64_t bwt_invPsi(const DevIndex &ix, uint64_t k)
 	if (c == 1) occ = cnt[1];
 	if (c == 2) occ = cnt[2];
 	if (c == 3) occ = cnt[3];
-	return ix.L2[c] + occ;
+	return fm.ix.L2[c] + occ;
 }
 
 // bwt_sa by walking to a sampled slot (bwa/bwt.c:86-96); kept for parity tests and as the
 // builder's cross-check.
-__device__ __forceinline__ uint64_t bwt_sa_walk(const DevIndex &ix, uint64_t k)
+EMAB_HD uint64_t bwt_sa_walk(Fm &fm, uint64_t k)
 {
-	uint64_t sa = 0, mask = (uint64_t)ix.sa_intv - 1;
-	while (k & mask) { ++sa; k = bwt_invPsi(ix, k); }
-	return sa + ix.sa_sampled[k / ix.sa_intv];
+	uint64_t sa = 0, mask = (uint64_t)fm.ix.sa_intv - 1;
+	while (k & mask) { ++sa; k = bwt_invPsi(fm, k); }
+	return sa + fm.ix.sa_sampled[k / fm.ix.sa_intv];
 }

@@ -1,0 +1,54 @@
+// Host-side runtime objects behind the C ABI: the HBM-resident index and the per-worker context.
+#pragma once
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+struct DevBuf {  // grow-only device buffer
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes)
+	{
+		if (bytes <= cap) return EMAB_OK;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) {
+			snprintf(emab_errbuf, sizeof emab_errbuf, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+			p = nullptr;
+			return EMAB_ERR_NOMEM;
+		}
+		cap = want;
+		return EMAB_OK;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <class T> T *as() const { return (T *)p; }
+};
+
+struct emab_index {
+	int device = 0;
+	DevIndex d{};            // device pointers + scalars (passed to kernels by value)
+	// owned device allocations
+	void *d_bwt = nullptr, *d_sa_dense = nullptr, *d_sa_sampled = nullptr, *d_pac = nullptr, *d_ann_off = nullptr, *d_ann_len = nullptr;
+	// host mirrors
+	std::vector<std::string> names;
+	std::vector<int64_t> ann_offset;
+	std::vector<int32_t> ann_len;
+	uint64_t n_sa = 0, bwt_size_u32 = 0;
+	double build_ms = 0;
+	size_t hbm_bytes = 0;
+};
+
+struct emab_ctx {
+	emab_index *ix = nullptr;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	double last_ms = 0;
+	int last_launches = 0;
+	DevBuf b[24];            // scratch slots, meaning assigned by each entry point
+	unsigned long long *d_counters = nullptr;  // 8 x u64 instrumentation counters
+	int n_sm = 148;
+	// resident SW microbench inputs
+	int res_n = 0;
+};

@@ -12,7 +12,7 @@ struct SeedScratch {  // per read: two interval lists of (len+1) entries for bwt
 	Intv *a;          // [n_slots][2][EMAB_MAX_READ_LEN + 1]
 };
 
-__device__ __forceinline__ void reverse_intvs(Intv *p, int n)
+EMAB_HD void reverse_intvs(Intv *p, int n)
 {
 	for (int j = 0; j < n >> 1; ++j) {
 		Intv t = p[n - 1 - j];
@@ -24,7 +24,7 @@ __device__ __forceinline__ void reverse_intvs(Intv *p, int n)
 // bwt_smem1a with max_intv = 0 (the only form on the path, bwa/bwt.c:353-356).
 // Appends to mem[*n_mem..]; returns the next x.  Entries shorter than min_seed_len are dropped by
 // the caller (bwa/bwamem.c:150-155,165-167) — done here so the output stays compact.
-__device__ inline int smem1(const DevIndex &ix, int len, const uint8_t *q, int x, uint64_t min_intv,
+EMAB_HD int smem1(Fm &fm, int len, const uint8_t *q, int x, uint64_t min_intv,
                             Intv *mem, int *n_mem, int mem_cap, Intv *buf0, Intv *buf1, int *overflow)
 {
 	if (q[x] > 3) return x + 1;
@@ -32,13 +32,13 @@ __device__ inline int smem1(const DevIndex &ix, int len, const uint8_t *q, int x
 	Intv *prev = buf0, *curr = buf1;
 	int n_prev, n_curr = 0;
 	Intv ik;
-	bwt_set_intv(ix, q[x], ik);
+	bwt_set_intv(fm.ix, q[x], ik);
 	ik.info = x + 1;
 	int i;
 	for (i = x + 1; i < len; ++i) {  // forward search
 		if (q[i] < 4) {
 			int c = 3 - q[i];
-			Intv ok = bwt_extend1(ix, ik, c, 0);
+			Intv ok = bwt_extend1(fm, ik, c, 0);
 			if (ok.x2 != ik.x2) {
 				curr[n_curr++] = ik;
 				if (ok.x2 < min_intv) break;
@@ -68,7 +68,7 @@ __device__ inline int smem1(const DevIndex &ix, int len, const uint8_t *q, int x
 			Intv p = prev[j];
 			Intv ok;
 			ok.x2 = 0;
-			if (c >= 0) ok = bwt_extend1(ix, p, c, 1);
+			if (c >= 0) ok = bwt_extend1(fm, p, c, 1);
 			if (c < 0 || ok.x2 < min_intv) {
 				if (n_curr == 0) {
 					if (!have_last || (uint64_t)(i + 1) < last_start) {
@@ -103,16 +103,16 @@ __device__ inline int smem1(const DevIndex &ix, int len, const uint8_t *q, int x
 }
 
 // bwt_seed_strategy1 (bwa/bwt.c:358-379)
-__device__ inline int seed_strategy1(const DevIndex &ix, int len, const uint8_t *q, int x, int min_len, uint64_t max_intv, Intv *out)
+EMAB_HD int seed_strategy1(Fm &fm, int len, const uint8_t *q, int x, int min_len, uint64_t max_intv, Intv *out)
 {
 	out->x0 = out->x1 = out->x2 = out->info = 0;
 	if (q[x] > 3) return x + 1;
 	Intv ik;
-	bwt_set_intv(ix, q[x], ik);
+	bwt_set_intv(fm.ix, q[x], ik);
 	for (int i = x + 1; i < len; ++i) {
 		if (q[i] < 4) {
 			int c = 3 - q[i];
-			Intv ok = bwt_extend1(ix, ik, c, 0);
+			Intv ok = bwt_extend1(fm, ik, c, 0);
 			if (ok.x2 < max_intv && i - x >= min_len) {
 				*out = ok;
 				out->info = (uint64_t)x << 32 | (uint64_t)(i + 1);
@@ -125,12 +125,12 @@ __device__ inline int seed_strategy1(const DevIndex &ix, int len, const uint8_t 
 }
 
 // mem_collect_intv for one read.  Returns the number of intervals (sorted by info).
-__device__ inline int collect_intv(const DevIndex &ix, int len, const uint8_t *seq, Intv *mem, int mem_cap,
+EMAB_HD int collect_intv(Fm &fm, int len, const uint8_t *seq, Intv *mem, int mem_cap,
                                    Intv *buf0, Intv *buf1, int *overflow)
 {
 	int n = 0, x = 0;
 	while (x < len) {  // pass 1: all SMEMs
-		if (seq[x] < 4) x = smem1(ix, len, seq, x, 1, mem, &n, mem_cap, buf0, buf1, overflow);
+		if (seq[x] < 4) x = smem1(fm, len, seq, x, 1, mem, &n, mem_cap, buf0, buf1, overflow);
 		else ++x;
 	}
 	int old_n = n;
@@ -138,13 +138,13 @@ __device__ inline int collect_intv(const DevIndex &ix, int len, const uint8_t *s
 		Intv p = mem[k];
 		int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
 		if (end - start < opt::split_len || p.x2 > (uint64_t)opt::split_width) continue;
-		smem1(ix, len, seq, (start + end) >> 1, p.x2 + 1, mem, &n, mem_cap, buf0, buf1, overflow);
+		smem1(fm, len, seq, (start + end) >> 1, p.x2 + 1, mem, &n, mem_cap, buf0, buf1, overflow);
 	}
 	x = 0;
 	while (x < len) {  // pass 3: LAST-like
 		if (seq[x] < 4) {
 			Intv m;
-			x = seed_strategy1(ix, len, seq, x, opt::min_seed_len, opt::max_mem_intv, &m);
+			x = seed_strategy1(fm, len, seq, x, opt::min_seed_len, opt::max_mem_intv, &m);
 			if (m.x2 > 0) {
 				if (n < mem_cap) mem[n++] = m; else *overflow = 1;
 			}

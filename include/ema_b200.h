@@ -1,0 +1,90 @@
+/*
+ * ema_b200.h — the C ABI of libema_b200.so: a B200-native (sm_100a CUDA) implementation of the
+ * `ema align` hot path, exported as the drop-in for the reference's BWA bridge
+ * (reference: include/bwabridge.h:19-22,92-106 as used from src/align.c:986-1061).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns EMAB_OK (0) or a negative error code,
+ *     and never calls exit() (the reference bridge asserts / exits: src/bwabridge.c:81-84);
+ *     emab_last_error() returns a message for the calling thread.
+ *   - all buffers passed in are HOST buffers owned by the caller; host<->device copies happen
+ *     inside the call.  Output buffers are caller-allocated with the stated capacities.
+ *   - sequences are nt4 codes (A,C,G,T,other -> 0,1,2,3,4 : bwa/bntseq.c nst_nt4_table) unless a
+ *     function says ASCII.
+ *   - there is no CPU implementation behind any entry point: without a CUDA device every compute
+ *     call fails with EMAB_ERR_CUDA.
+ */
+#ifndef EMA_B200_H
+#define EMA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMAB_OK 0
+#define EMAB_ERR_IO (-1)
+#define EMAB_ERR_CUDA (-2)
+#define EMAB_ERR_ARG (-3)
+#define EMAB_ERR_OVERFLOW (-4)
+#define EMAB_ERR_NOMEM (-5)
+
+typedef struct emab_index emab_index_t; /* FM index + packed reference resident in one GPU's HBM */
+typedef struct emab_ctx emab_ctx_t;     /* one worker: a CUDA stream + its device scratch */
+
+const char *emab_last_error(void);
+int emab_version(void);
+int emab_device_count(int *n);
+
+/* ---- index: replaces load_reference / bwa_idx_load (src/bwabridge.c:76-96, bwa/bwa.c:271-316).
+ * Reads <prefix>.bwt/.sa/.pac/.ann/.amb as written by `bwa index`, uploads them to `device` and
+ * builds the dense suffix array there.  info[12] = l_pac, n_seqs, primary, seq_len, L2[0..4],
+ * sa_intv, n_sa, bwt_size(u32) — the same fields bwt_t/bntseq_t expose. */
+int emab_index_load(const char *prefix, int device, emab_index_t **out);
+void emab_index_free(emab_index_t *ix);
+int emab_index_info(const emab_index_t *ix, int64_t info[12]);
+int emab_index_contig(const emab_index_t *ix, int i, int64_t *offset, int32_t *len, char *name, int name_cap);
+double emab_index_build_ms(const emab_index_t *ix); /* device time spent densifying the SA */
+
+int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out);  /* ix may be NULL for the sequence-only SW calls */
+void emab_ctx_free(emab_ctx_t *ctx);
+/* device time (ms, CUDA events on the ctx stream) of the kernels launched by the last call, and
+ * the number of kernel launches it made */
+double emab_last_kernel_ms(const emab_ctx_t *ctx);
+int emab_last_launches(const emab_ctx_t *ctx);
+
+/* ---- Smith-Waterman batches (sequence-only; one warp per task) -------------------------------
+ * q/t are concatenated nt4 strings with n+1 int64 offsets.  Scoring is BWA-MEM's default
+ * (a=1,b=4,o=6,e=1 both ways: bwa/bwamem.c:79-81).  *cells (optional) receives the number of DP
+ * cells visited (the roofline unit of SURVEY.md §8d).
+ *
+ * emab_extend_batch  = ksw_extend2 (bwa/ksw.c:416) ; out[6n] = score,qle,tle,gtle,gscore,max_off
+ * emab_global_batch  = ksw_global2 (bwa/ksw.c:540) ; out[2n] = score,n_cigar ; cigar[n*max_cigar]
+ * emab_local_batch   = ksw_align2 with KSW_XSUBO|KSW_XSTART|19 (+KSW_XBYTE when qlen<250), the
+ *                      mem_matesw call (bwa/bwamem_pair.c:176-177) ; out[7n] = score,te,qe,score2,te2,tb,qb
+ */
+int emab_extend_batch(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
+                      const int32_t *h0, int w, int end_bonus, int zdrop, int32_t *out, int64_t *cells);
+int emab_global_batch(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
+                      const int32_t *w, int32_t *out, uint32_t *cigar, int max_cigar, int64_t *cells);
+int emab_local_batch(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
+                     int32_t *out, int64_t *cells);
+
+/* device-resident variant used by bench.py for the kernel-only number: uploads once, then
+ * emab_extend_resident_run launches the kernel `reps` times on resident inputs. */
+int emab_extend_resident_load(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff, const int32_t *h0);
+int emab_extend_resident_run(emab_ctx_t *ctx, int w, int end_bonus, int zdrop, int reps, int32_t *out, int64_t *cells);
+
+/* ---- FM index --------------------------------------------------------------------------------
+ * emab_sa_batch      = bwt_sa (bwa/bwt.c:86) for n SA indices; mode 0 = dense SA, 1 = LF walk
+ * emab_smem_batch    = mem_collect_intv (bwa/bwamem.c:140) for n reads: intervals[n*max_intv*4]
+ *                      (x0,x1,x2,info), n_intv[n]; *touches = 64-byte Occ-block loads issued
+ */
+int emab_sa_batch(emab_ctx_t *ctx, int n, const int64_t *k, int64_t *out, int mode);
+int emab_smem_batch(emab_ctx_t *ctx, int n, const uint8_t *seq, const int64_t *off, int64_t *intervals, int32_t *n_intv,
+                    int max_intv, int64_t *touches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

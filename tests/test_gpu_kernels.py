@@ -1,0 +1,129 @@
+"""GPU parity tests (-m gpu): the CUDA kernels, called through the C ABI (include/ema_b200.h),
+against the oracle on the same seeded inputs and against the committed golden vectors.
+Bar: bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import _p
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def unpack(flat, off):
+    return [flat[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+@pytest.fixture(scope="module")
+def emab():
+    import ema_b200
+    return ema_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(emab):
+    return emab.Context()
+
+
+@pytest.fixture(scope="module")
+def tiny(emab):
+    ix = emab.Index(os.path.join(G, "tiny_rep", "ref.fa"))
+    return ix, emab.Context(ix)
+
+
+def test_extend_golden(emab, ctx):
+    g = np.load(os.path.join(G, "sw_golden.npz"))
+    out, cells = emab.extend_batch(ctx, unpack(g["q"], g["qo"]), unpack(g["t"], g["to"]), g["h0"])
+    bad = np.nonzero((out != g["ext"]).any(axis=1))[0]
+    assert len(bad) == 0, f"{len(bad)} mismatches, first {bad[:5]}: {out[bad[:3]]} vs {g['ext'][bad[:3]]}"
+    assert ctx.last_launches == 1 and ctx.last_kernel_ms > 0
+
+
+@pytest.mark.parametrize("params", [(100, 5, 100), (200, 5, 100), (7, 0, 0), (100, 5, 15)])
+def test_extend_vs_oracle(emab, ctx, port_lib, params):
+    w, eb, zd = params
+    qs, ts, h0 = helpers.random_extend_tasks(4000, 100 + w, max_q=256)
+    a, cells_gpu = emab.extend_batch(ctx, qs, ts, h0, w, eb, zd)
+    b, cells_cpu = helpers.sw_extend(port_lib, "orc", qs, ts, h0, w, eb, zd)
+    bad = np.nonzero((a != b).any(axis=1))[0]
+    assert len(bad) == 0, f"{len(bad)} mismatches, first {bad[:5]}: {a[bad[:3]]} vs {b[bad[:3]]}"
+    assert cells_gpu == cells_cpu, "the kernel must visit exactly the reference's DP cells"
+
+
+def test_extend_edge_cases(emab, ctx, port_lib):
+    qs = [np.array([0], np.uint8), np.array([0, 1, 2, 3] * 8, np.uint8), np.full(256, 2, np.uint8), np.full(40, 4, np.uint8),
+          np.array([1] * 33, np.uint8), np.array([1] * 32, np.uint8), np.array([1] * 31, np.uint8)]
+    ts = [np.array([0], np.uint8), np.array([0, 1, 2, 3] * 100, np.uint8), np.full(700, 2, np.uint8), np.full(50, 4, np.uint8),
+          np.array([1] * 64, np.uint8), np.array([1] * 400, np.uint8), np.array([3], np.uint8)]
+    h0 = np.array([1, 19, 150, 30, 5, 7, 9], np.int32)
+    a, _ = emab.extend_batch(ctx, qs, ts, h0)
+    b, _ = helpers.sw_extend(port_lib, "orc", qs, ts, h0)
+    assert np.array_equal(a, b)
+    out, cells = emab.extend_batch(ctx, [], [], np.zeros(0, np.int32))
+    assert out.shape == (0, 6) and cells == 0
+    with pytest.raises(emab.EmabError):
+        emab.extend_batch(ctx, [np.zeros(300, np.uint8)], [np.zeros(10, np.uint8)], [5])
+
+
+def test_global_golden_and_oracle(emab, ctx, port_lib):
+    g = np.load(os.path.join(G, "sw_golden.npz"))
+    out, cig, _ = emab.global_batch(ctx, unpack(g["q"], g["qo"]), unpack(g["t"], g["to"]), g["ws"], max_cigar=512)
+    assert np.array_equal(out, g["glo"])
+    assert np.array_equal(cig, g["gcig"])
+    qs, ts, _ = helpers.random_extend_tasks(3000, 77, max_q=256)
+    ws = np.array([max(int(w), abs(len(q) - len(t)) + 3) for w, q, t in
+                   zip(np.random.default_rng(3).integers(0, 120, size=len(qs)), qs, ts)], dtype=np.int32)
+    a, ca, cg = emab.global_batch(ctx, qs, ts, ws, max_cigar=600)
+    b, cb, cc = helpers.sw_global(port_lib, "orc", qs, ts, ws, max_cigar=600)
+    assert np.array_equal(a, b) and np.array_equal(ca, cb) and cg == cc
+
+
+def test_local_golden_and_oracle(emab, ctx, port_lib):
+    g = np.load(os.path.join(G, "sw_golden.npz"))
+    out, _ = emab.local_batch(ctx, unpack(g["lq"], g["lqo"]), unpack(g["lt"], g["lto"]))
+    bad = np.nonzero((out != g["loc"]).any(axis=1))[0]
+    assert len(bad) == 0, f"{len(bad)} mismatches, first {bad[:5]}: {out[bad[:3]]} vs {g['loc'][bad[:3]]}"
+    qs, ts, _ = helpers.random_extend_tasks(3000, 78, max_q=256)
+    lq = [q for q in qs if len(q) >= 2]
+    lt = [np.concatenate([t, q[::-1], t[: len(t) // 2]])[:1000] for q, t in zip(qs, ts) if len(q) >= 2]
+    a, _ = emab.local_batch(ctx, lq, lt)
+    b, _ = helpers.sw_local(port_lib, "orc", lq, lt)
+    bad = np.nonzero((a != b).any(axis=1))[0]
+    assert len(bad) == 0, f"{len(bad)} mismatches, first {bad[:5]}: {a[bad[:3]]} vs {b[bad[:3]]}"
+
+
+def test_index_and_sa(emab, tiny):
+    ix, c = tiny
+    g = np.load(os.path.join(G, "fm_golden.npz"))
+    assert np.array_equal(ix.info, g["info"])
+    assert np.array_equal(emab.sa_batch(c, g["ks"], mode=0), g["sa"]), "dense SA must reproduce bwt_sa"
+    assert np.array_equal(emab.sa_batch(c, g["ks"], mode=1), g["sa"]), "LF-walk bwt_sa"
+    allk = np.arange(0, ix.seq_len + 1, dtype=np.int64)
+    assert np.array_equal(emab.sa_batch(c, allk, mode=0), emab.sa_batch(c, allk, mode=1)), "every SA slot"
+    sa = emab.sa_batch(c, allk[1:], mode=0)
+    assert np.array_equal(np.sort(sa), np.arange(ix.seq_len)), "SA[1..] is a permutation of the text positions"
+
+
+def test_smem_golden_and_oracle(emab, tiny, port_lib):
+    ix, c = tiny
+    g = np.load(os.path.join(G, "fm_golden.npz"))
+    reads = unpack(g["reads"], g["roff"])
+    ivs, touches = emab.smem_batch(c, reads)
+    pos = 0
+    for i, (iv, n) in enumerate(zip(ivs, g["n_intv"])):
+        assert len(iv) == n and np.array_equal(iv, g["intv"][pos:pos + n]), f"read {i}"
+        pos += n
+    pix = port_lib.orc_index_load(os.path.join(G, "tiny_rep", "ref.fa").encode())
+    port_lib.orc_touches(C.c_void_p(pix), 1)
+    for s in reads:
+        s = np.ascontiguousarray(s)
+        ob = np.zeros((256, 4), np.int64)
+        port_lib.orc_collect_intv_flat(C.c_void_p(pix), len(s), _p(s, C.c_uint8), _p(ob, C.c_int64), 256)
+    assert touches == port_lib.orc_touches(C.c_void_p(pix), 1), "64-byte Occ block touches must equal the reference's"
+    # edge cases: empty read, all-N read, read shorter than a seed
+    ivs, _ = emab.smem_batch(c, [np.zeros(0, np.uint8), np.full(50, 4, np.uint8), reads[0][:10]])
+    assert [len(x) for x in ivs] == [0, 0, 0]
