@@ -168,3 +168,32 @@ def sa_batch(ctx: Context, ks, mode=0):
     out = np.zeros_like(ks)
     _check(lib().emab_sa_batch(ctx._h, len(ks), _p(ks, C.c_int64), _p(out, C.c_int64), mode))
     return out
+
+
+ALN_DTYPE = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("NM", "<i4"), ("n_cigar", "<i4"), ("score", "<i4"),
+                      ("mapq", "<i4"), ("score_mapq", "<i4"), ("clip", "<i4"), ("clip_edit_dist", "<i4"), ("keep", "<i4"),
+                      ("em_score", "<f8"), ("cigar", "<u4", (64,))])
+
+
+class Stats(C.Structure):
+    _fields_ = [("extend_cells", C.c_int64), ("global_cells", C.c_int64), ("local_cells", C.c_int64), ("occ_touches", C.c_int64),
+                ("n_occ", C.c_int64), ("n_regs", C.c_int64), ("kernel_ms", C.c_double), ("launches", C.c_int32), ("pad", C.c_int32)]
+
+
+def align_pairs(ctx: Context, reads, stage=3, want_regs=False, aln_cap=None):
+    """emab_align_pairs over nt4 reads laid out pair0/mate1, pair0/mate2, pair1/mate1, ...
+    Returns dict(n_regs[2n], alns (structured array, all regions incl. keep==0), regs (A,18) or None, stats)."""
+    assert len(reads) % 2 == 0
+    s, off = _pack(reads)
+    R = len(reads)
+    cap = aln_cap if aln_cap is not None else max(1024, 16 * R)
+    n_regs = np.zeros(R, dtype=np.int32)
+    alns = np.zeros(cap, dtype=ALN_DTYPE)
+    regs = np.zeros((cap, 18), dtype=np.int64) if want_regs else None
+    n_alns = C.c_int64(0)
+    st = Stats()
+    _check(lib().emab_align_pairs(ctx._h, R // 2, _p(s, C.c_uint8), _p(off, C.c_int64), stage, _p(n_regs, C.c_int32),
+                                  alns.ctypes.data_as(C.c_void_p), cap, C.byref(n_alns),
+                                  _p(regs, C.c_int64) if want_regs else None, C.byref(st)))
+    A = n_alns.value
+    return dict(n_regs=n_regs, alns=alns[:A], regs=regs[:A] if want_regs else None, stats=st)

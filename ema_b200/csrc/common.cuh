@@ -106,6 +106,9 @@ struct Reg {  // mem_alnreg_t (bwa/bwamem.h:92-110)
 	float frac_rep;
 };
 
+struct ExtResult { int score, qle, tle, gtle, gscore, max_off; };  // ksw_extend2 outputs
+struct LocResult { int score, te, qe, score2, te2, tb, qb; };     // kswr_t (bwa/ksw.h:14-19)
+
 struct Aln {  // what append_alignments keeps of mem_aln_t / SingleReadAlignment / SAMRecord (src/align.c:915-956)
 	int64_t pos;       // 0-based leftmost position on the contig
 	int32_t rid;

@@ -30,8 +30,6 @@ struct WarpDP {  // per-warp shared-memory working set
 	uint8_t q[KSW_QPAD + 2];
 };
 
-struct ExtResult { int score, qle, tle, gtle, gscore, max_off; };
-struct LocResult { int score, te, qe, score2, te2, tb, qb; };
 
 // target fetchers: operator()(i) returns base i of the target in DP order
 struct SeqFetch {  // explicit byte string (batch API / tests)
@@ -348,19 +346,18 @@ __device__ PassResult warp_local_pass(WarpDP &sm, int qlen, int qpad, const TF &
 		__syncwarp();
 		const int k = (r.score + opt::a - 1) / opt::a, lo = te - k, hi = te + k;
 		const int nrow = i < KSW_MAX_TLEN ? i : KSW_MAX_TLEN;
-		int run_row = -1, run_val = -1, prev = -2;
-		for (int a = 0; a <= nrow; ++a) {
-			int v = a < nrow ? sm.rowmax[a] : -1;
-			bool in = v >= minsc;
-			if (in && prev + 1 == a && run_val >= 0) {          // extend the open run
-				if (run_val < v) { run_val = v; run_row = a; }
-			} else {
+		// NB "consecutive" is judged against the row stored in the last entry, which is the row of that
+		// entry's maximum, not the previous row (b[n_b-1] + 1 != i, bwa/ksw.c:216).
+		int run_row = -2, run_val = -1;
+		for (int a = 0; a < nrow; ++a) {
+			const int v = sm.rowmax[a];
+			if (v < minsc) continue;
+			if (run_val < 0 || run_row + 1 != a) {
 				if (run_val >= 0 && (run_row < lo || run_row > hi) && run_val > r.score2) { r.score2 = run_val; r.te2 = run_row; }
-				run_val = -1;
-				if (in) { run_val = v; run_row = a; }
-			}
-			if (in) prev = a;
+				run_val = v; run_row = a;
+			} else if (run_val < v) { run_val = v; run_row = a; }
 		}
+		if (run_val >= 0 && (run_row < lo || run_row > hi) && run_val > r.score2) { r.score2 = run_val; r.te2 = run_row; }
 	}
 	return r;
 }

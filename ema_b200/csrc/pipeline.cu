@@ -1,0 +1,352 @@
+// The per-bucket device pipeline behind emab_align_pairs: the batched replacement of
+// bwa_mem_mate_sw + bwa_smith_waterman + append_alignments (src/bwabridge.c:204-311,
+// src/align.c:986-1061).  One bucket (or any batch of read pairs) is one call:
+//
+//   k_seed      thread / read   mem_collect_intv                      -> SA intervals, #occurrences
+//   (scan)                      exclusive sum of #occurrences          -> per-read pool offsets
+//   k_chain     thread / read   mem_chain + mem_chain_flt (dense SA)   -> chains + seeds
+//   k_align1    warp   / read   mem_chain2aln + mem_sort_dedup_patch   -> regions
+//   k_rescue    warp   / pair   mem_matesw both ways                   -> regions (+ rescued)
+//   (scan)                      exclusive sum of #regions              -> candidate offsets
+//   k_finalize  warp   / pair   mem_reg2aln + append_alignments        -> candidate alignments
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cub/device/device_scan.cuh>
+#include "../../include/ema_b200.h"
+#include "runtime.cuh"
+#include "seed.cuh"
+#include "chain.cuh"
+#include "ksw_warp.cuh"
+#include "align.cuh"
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+#define PL_WARPS 8
+#define RESCUE_ROOM 51  // mem_matesw can add one region per anchor, at most max_matesw = 50 anchors
+
+static_assert(sizeof(emab_aln_t) == sizeof(Aln), "public and device candidate records must have one layout");
+
+// ---------------------------------------------------------------------------------------------
+// device DP policy: the warp-cooperative kernels of ksw_warp.cuh
+// ---------------------------------------------------------------------------------------------
+struct WarpPolicy {
+	const DevIndex &ix;
+	WarpDP &sm;
+	unsigned long long *counters;  // [0] extend cells, [3] global cells, [4] local cells
+	uint8_t *z;                    // this warp's backtrack scratch
+	size_t z_cap;
+	uint32_t *tmp;                 // this warp's cigar scratch [EMAB_MAX_CIGAR]
+	int *err;
+
+	__device__ ExtResult extend(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, int end_bonus, int h0)
+	{
+		const int lane = threadIdx.x & 31;
+		__syncwarp();
+		for (int j = lane; j < qlen; j += 32) sm.q[j] = query[q0 + j * qstep];
+		__syncwarp();
+		RefFetch tf{&ix, t0, tstep};
+		ExtResult r = warp_extend(sm, qlen, tf, tlen, w, end_bonus, opt::zdrop, h0, &counters[0]);
+		__syncwarp();
+		return r;
+	}
+	__device__ int global(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, uint32_t *cigar, int *n_cigar)
+	{
+		const int lane = threadIdx.x & 31;
+		__syncwarp();
+		for (int j = lane; j < qlen; j += 32) sm.q[j] = query[q0 + j * qstep];
+		__syncwarp();
+		RefFetch tf{&ix, t0, tstep};
+		const int ncol = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+		bool bt = cigar != nullptr;
+		if (bt && (size_t)ncol * tlen > z_cap) { *err = 1; bt = false; }
+		int score = warp_global(sm, qlen, tf, tlen, w, bt ? z : nullptr, &counters[3]);
+		__syncwarp();
+		if (cigar) *n_cigar = bt ? global_backtrack(z, qlen, tlen, w, cigar, EMAB_MAX_CIGAR, tmp) : 0;
+		__syncwarp();
+		return score;
+	}
+	// query = reverse complement of ms (bwa/bwamem_pair.c:150-153), target = ref[rb, rb+tlen)
+	__device__ LocResult local(const uint8_t *ms, int l_ms, int64_t rb, int tlen)
+	{
+		const int lane = threadIdx.x & 31;
+		__syncwarp();
+		for (int j = lane; j < l_ms; j += 32) { int c = ms[j]; sm.q[l_ms - 1 - j] = c < 4 ? 3 - c : 4; }
+		__syncwarp();
+		RefFetch tf{&ix, rb, 1};
+		LocResult r;
+		if (tlen > KSW_MAX_TLEN) { *err = 2; r.score = 0; r.te = r.qe = r.score2 = r.te2 = r.tb = r.qb = -1; return r; }
+		r = warp_local(sm, l_ms, tf, tlen, opt::min_seed_len * opt::a, l_ms * opt::a < 250, &counters[4]);
+		__syncwarp();
+		return r;
+	}
+};
+
+__device__ __forceinline__ int next_item(unsigned long long *counter, int lane)
+{
+	unsigned long long t = 0;
+	if (lane == 0) t = atomicAdd(counter, 1ull);
+	return (int)__shfl_sync(FULL_MASK, t, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_seed(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, Intv *intv, int32_t *n_intv, Intv *scratch,
+       int32_t *occ_cnt, int *err, unsigned long long *counters)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned touches = 0;
+	if (r < n_reads) {
+		Fm fm{ix, 0};
+		const int len = (int)(off[r + 1] - off[r]);
+		Intv *buf0 = scratch + (size_t)r * 2 * (EMAB_MAX_READ_LEN + 1);
+		Intv *mine = intv + (size_t)r * EMAB_MAX_INTV;
+		int ovf = 0;
+		const int n = collect_intv(fm, len, seq + off[r], mine, EMAB_MAX_INTV, buf0, buf0 + EMAB_MAX_READ_LEN + 1, &ovf);
+		if (ovf) *err = 3;
+		n_intv[r] = n;
+		int occ = 0;
+		if (len >= opt::min_seed_len)
+			for (int i = 0; i < n; ++i) occ += intv_occ_count(mine[i].x2);
+		occ_cnt[r] = occ;
+		touches = fm.touches;
+	}
+	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(FULL_MASK, touches, d);
+	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(&counters[2], (unsigned long long)touches);
+}
+
+struct Pools {  // device pools sized by the total number of SA occurrences T and the number of reads R
+	Seed *w_seeds; Chain *w_chains; BNode *w_nodes; int32_t *w_ord;   // chaining work space
+	Seed *seeds; Chain *chains;                                       // surviving chains + seeds
+	uint64_t *srt;                                                    // mem_chain2aln's per-chain sort keys
+	Reg *regs;                                                        // [T + RESCUE_ROOM * R]
+	int32_t *n_chains, *n_regs;
+};
+
+__global__ void __launch_bounds__(128)
+k_chain(DevIndex ix, int n_reads, const int64_t *off, const Intv *intv, const int32_t *n_intv, const int32_t *occ_off, Pools p)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int o = occ_off[r], cap = occ_off[r + 1] - o;
+	ChainWork wk;
+	wk.seeds = p.w_seeds + o;
+	wk.chains = p.w_chains + o;
+	wk.nodes = p.w_nodes + (o / 3 + 2 * (size_t)r);
+	wk.ord = p.w_ord + 3 * (size_t)o;
+	p.n_chains[r] = chain_read(ix, (int)(off[r + 1] - off[r]), intv + (size_t)r * EMAB_MAX_INTV, n_intv[r], wk, cap, p.chains + o, p.seeds + o);
+}
+
+__global__ void __launch_bounds__(PL_WARPS * 32)
+k_align1(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p,
+         uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
+{
+	__shared__ WarpDP sm_all[PL_WARPS];
+	const int lane = threadIdx.x & 31, gw = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
+	WarpPolicy dp{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err};
+	for (;;) {
+		const int r = next_item(&counters[5], lane);
+		if (r >= n_reads) break;
+		const int o = occ_off[r];
+		Reg *regs = p.regs + (o + (size_t)RESCUE_ROOM * r);
+		const int n = align1_from_chains(ix, dp, (int)(off[r + 1] - off[r]), seq + off[r], p.chains + o, p.n_chains[r], p.seeds + o, p.srt + o, regs);
+		p.n_regs[r] = n;
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(PL_WARPS * 32)
+k_rescue(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p,
+         uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
+{
+	__shared__ WarpDP sm_all[PL_WARPS];
+	const int lane = threadIdx.x & 31, gw = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
+	WarpPolicy dp{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err};
+	for (;;) {
+		const int pr = next_item(&counters[6], lane);
+		if (pr >= n_pairs) break;
+		const int r1 = 2 * pr, r2 = r1 + 1;
+		Reg *g1 = p.regs + (occ_off[r1] + (size_t)RESCUE_ROOM * r1), *g2 = p.regs + (occ_off[r2] + (size_t)RESCUE_ROOM * r2);
+		int n1 = p.n_regs[r1], n2 = p.n_regs[r2];
+		mate_sw_pair(ix, dp, (int)(off[r1 + 1] - off[r1]), seq + off[r1], (int)(off[r2 + 1] - off[r2]), seq + off[r2], g1, &n1, g2, &n2);
+		p.n_regs[r1] = n1; p.n_regs[r2] = n2;
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(PL_WARPS * 32)
+k_finalize(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p, const int32_t *aln_off,
+           Aln *alns, const ScoreConsts *sc, uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
+{
+	__shared__ WarpDP sm_all[PL_WARPS];
+	const int lane = threadIdx.x & 31, gw = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
+	WarpPolicy dp{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err};
+	for (;;) {
+		const int pr = next_item(&counters[7], lane);
+		if (pr >= n_pairs) break;
+		int best_dist = -1;
+		for (int m = 0; m < 2; ++m) {
+			const int r = 2 * pr + m;
+			const Reg *regs = p.regs + (occ_off[r] + (size_t)RESCUE_ROOM * r);
+			append_candidates(ix, dp, *sc, (int)(off[r + 1] - off[r]), seq + off[r], regs, p.n_regs[r], alns + aln_off[r], &best_dist);
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void k_export_regs(int n_reads, const int32_t *occ_off, const int32_t *aln_off, Pools p, int64_t *out)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const Reg *regs = p.regs + (occ_off[r] + (size_t)RESCUE_ROOM * r);
+	for (int i = 0; i < p.n_regs[r]; ++i) {
+		const Reg &g = regs[i];
+		int64_t *o = out + (size_t)(aln_off[r] + i) * 18;
+		o[0] = g.rb; o[1] = g.re; o[2] = g.qb; o[3] = g.qe; o[4] = g.rid; o[5] = g.score; o[6] = g.truesc; o[7] = g.sub; o[8] = g.csub;
+		o[9] = g.sub_n; o[10] = g.w; o[11] = g.seedcov; o[12] = g.secondary; o[13] = g.seedlen0; o[14] = g.n_comp; o[15] = 0;
+		o[16] = __float_as_uint(g.frac_rep); o[17] = 0;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static void fill_consts(ScoreConsts &sc, double eps)
+{  // src/align.c:858-864 with glibc's log/log10; bwa/bwamem.c:107 for the (int)log(50) = 3 factor
+	sc.log_match = log(1 - eps); sc.log_mismatch = log(eps); sc.log_indel = log(0.0001); sc.log_clip = log(0.03);
+	sc.log10_mismatch = log10(eps); sc.log10_indel = log10(0.0001); sc.log10_clip = log10(0.03);
+	const int fac = (int)log(50.0f);
+	for (int l = 0; l < 1024; ++l) sc.mapq_len_coef[l] = l < 50 ? 1. : fac / log((double)l);
+}
+
+static int upload(emab_ctx *c, DevBuf &b, const void *src, size_t bytes)
+{
+	TRY(b.ensure(bytes ? bytes : 1));
+	if (bytes) CUDA_TRY(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+	return EMAB_OK;
+}
+
+extern "C" int emab_set_error_rate(emab_ctx_t *c, double eps)
+{
+	if (!c || !(eps > 0 && eps < 1)) return EMAB_ERR_ARG;
+	ScoreConsts sc;
+	fill_consts(sc, eps);
+	TRY(c->b[23].ensure(sizeof sc));
+	CUDA_TRY(cudaMemcpy(c->b[23].p, &sc, sizeof sc, cudaMemcpyHostToDevice));
+	c->consts_ready = true;
+	return EMAB_OK;
+}
+
+extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, const int64_t *off, int stage,
+                                int32_t *n_regs_out, emab_aln_t *alns_out, int64_t aln_cap, int64_t *n_alns, int64_t *regs_dbg,
+                                emab_stats_t *stats)
+{
+	if (!c || !c->ix || n_pairs < 0 || stage < 1 || stage > 3) return EMAB_ERR_ARG;
+	const int R = 2 * n_pairs;
+	if (n_alns) *n_alns = 0;
+	if (stats) memset(stats, 0, sizeof *stats);
+	if (R == 0) return EMAB_OK;
+	for (int i = 0; i < R; ++i) {
+		int64_t l = off[i + 1] - off[i];
+		if (l < 0 || l > EMAB_MAX_READ_LEN) { snprintf(emab_errbuf, sizeof emab_errbuf, "read %d: length %lld out of range (max %d)", i, (long long)l, EMAB_MAX_READ_LEN); return EMAB_ERR_ARG; }
+	}
+	if (!c->consts_ready) TRY(emab_set_error_rate(c, 0.001));
+	const DevIndex &ix = c->ix->d;
+	cudaStream_t st = c->stream;
+	// slots: 0 seq, 1 off, 2 intv, 3 n_intv, 4 smem scratch, 5 occ_cnt/off, 6 cub temp, 7.. pools
+	TRY(upload(c, c->b[0], seq, (size_t)off[R]));
+	TRY(upload(c, c->b[1], off, (size_t)(R + 1) * 8));
+	TRY(c->b[2].ensure((size_t)R * EMAB_MAX_INTV * sizeof(Intv)));
+	TRY(c->b[3].ensure((size_t)R * 4));
+	TRY(c->b[4].ensure((size_t)R * 2 * (EMAB_MAX_READ_LEN + 1) * sizeof(Intv)));
+	TRY(c->b[5].ensure((size_t)(R + 1) * 4 * 2));
+	int32_t *d_occ_cnt = c->b[5].as<int32_t>(), *d_occ_off = d_occ_cnt + (R + 1);
+	TRY(c->b[22].ensure(16));
+	int *d_err = c->b[22].as<int>();
+	CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
+	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, st));
+	CUDA_TRY(cudaMemsetAsync(d_occ_cnt, 0, (size_t)(R + 1) * 4, st));
+	int launches = 0;
+	CUDA_TRY(cudaEventRecord(c->ev0, st));
+	k_seed<<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(),
+	                                        c->b[4].as<Intv>(), d_occ_cnt, d_err, c->d_counters);
+	++launches;
+	size_t tmp_bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_occ_cnt, d_occ_off, R + 1, st);
+	TRY(c->b[6].ensure(tmp_bytes + 16));
+	cub::DeviceScan::ExclusiveSum(c->b[6].p, tmp_bytes, d_occ_cnt, d_occ_off, R + 1, st);
+	++launches;
+	int32_t T = 0;
+	CUDA_TRY(cudaMemcpyAsync(&T, d_occ_off + R, 4, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	if (T < 0) { snprintf(emab_errbuf, sizeof emab_errbuf, "seed occurrence count overflow"); return EMAB_ERR_OVERFLOW; }
+	const size_t Tn = (size_t)T + 1, NR = (size_t)T + (size_t)RESCUE_ROOM * R + 1;
+	Pools p;
+	TRY(c->b[7].ensure(Tn * sizeof(Seed)));   p.w_seeds = c->b[7].as<Seed>();
+	TRY(c->b[8].ensure(Tn * sizeof(Chain)));  p.w_chains = c->b[8].as<Chain>();
+	TRY(c->b[9].ensure((Tn / 3 + 2 * (size_t)R + 4) * sizeof(BNode)));  p.w_nodes = c->b[9].as<BNode>();
+	TRY(c->b[10].ensure(3 * Tn * 4));         p.w_ord = c->b[10].as<int32_t>();
+	TRY(c->b[11].ensure(Tn * sizeof(Seed)));  p.seeds = c->b[11].as<Seed>();
+	TRY(c->b[12].ensure(Tn * sizeof(Chain))); p.chains = c->b[12].as<Chain>();
+	TRY(c->b[13].ensure(Tn * 8));             p.srt = c->b[13].as<uint64_t>();
+	TRY(c->b[14].ensure(NR * sizeof(Reg)));   p.regs = c->b[14].as<Reg>();
+	TRY(c->b[15].ensure((size_t)(R + 1) * 4 * 3));
+	p.n_chains = c->b[15].as<int32_t>(); p.n_regs = p.n_chains + (R + 1);
+	int32_t *d_aln_off = p.n_regs + (R + 1);
+	CUDA_TRY(cudaMemsetAsync(p.n_chains, 0, (size_t)(R + 1) * 4 * 3, st));
+	const int grid = c->n_sm * 4, n_warps = grid * PL_WARPS;
+	const size_t z_cap = (size_t)EMAB_MAX_READ_LEN * 1024;
+	TRY(c->b[16].ensure((size_t)n_warps * z_cap));
+	TRY(c->b[17].ensure((size_t)n_warps * EMAB_MAX_CIGAR * 4));
+	k_chain<<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(), d_occ_off, p);
+	k_align1<<<grid, PL_WARPS * 32, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
+	                                          c->b[17].as<uint32_t>(), d_err, c->d_counters);
+	launches += 2;
+	if (stage >= 2) {
+		k_rescue<<<grid, PL_WARPS * 32, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
+		                                          c->b[17].as<uint32_t>(), d_err, c->d_counters);
+		++launches;
+	}
+	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, p.n_regs, d_aln_off, R + 1, st);
+	TRY(c->b[6].ensure(tmp_bytes + 16));
+	cub::DeviceScan::ExclusiveSum(c->b[6].p, tmp_bytes, p.n_regs, d_aln_off, R + 1, st);
+	++launches;
+	int32_t A = 0;
+	CUDA_TRY(cudaMemcpyAsync(&A, d_aln_off + R, 4, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
+	if (n_alns) *n_alns = A;
+	if (A > aln_cap) { snprintf(emab_errbuf, sizeof emab_errbuf, "%d candidate regions exceed the caller's capacity %lld", A, (long long)aln_cap); return EMAB_ERR_OVERFLOW; }
+	if (stage >= 3) {
+		TRY(c->b[18].ensure(((size_t)A + 1) * sizeof(Aln)));
+		k_finalize<<<grid, PL_WARPS * 32, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, d_aln_off, c->b[18].as<Aln>(),
+		                                            c->b[23].as<ScoreConsts>(), c->b[16].as<uint8_t>(), z_cap, c->b[17].as<uint32_t>(), d_err, c->d_counters);
+		++launches;
+	}
+	CUDA_TRY(cudaEventRecord(c->ev1, st));
+	if (regs_dbg) {
+		TRY(c->b[19].ensure(((size_t)A + 1) * 18 * 8));
+		k_export_regs<<<(R + 127) / 128, 128, 0, st>>>(R, d_occ_off, d_aln_off, p, c->b[19].as<int64_t>());
+		CUDA_TRY(cudaMemcpyAsync(regs_dbg, c->b[19].p, (size_t)A * 18 * 8, cudaMemcpyDeviceToHost, st));
+	}
+	if (n_regs_out) CUDA_TRY(cudaMemcpyAsync(n_regs_out, p.n_regs, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+	if (stage >= 3 && alns_out && A) CUDA_TRY(cudaMemcpyAsync(alns_out, c->b[18].p, (size_t)A * sizeof(Aln), cudaMemcpyDeviceToHost, st));
+	int h_err[4] = {0, 0, 0, 0};
+	unsigned long long cnt[8];
+	CUDA_TRY(cudaMemcpyAsync(h_err, d_err, 16, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
+	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+	c->last_ms = ms; c->last_launches = launches;
+	if (stats) {
+		stats->extend_cells = (int64_t)cnt[0]; stats->occ_touches = (int64_t)cnt[2]; stats->global_cells = (int64_t)cnt[3];
+		stats->local_cells = (int64_t)cnt[4]; stats->n_occ = T; stats->n_regs = A; stats->kernel_ms = ms; stats->launches = launches;
+	}
+	if (h_err[0]) {
+		snprintf(emab_errbuf, sizeof emab_errbuf, "device pipeline error %d (1: backtrack scratch too small, 2: rescue window too long, 3: too many SA intervals)", h_err[0]);
+		return EMAB_ERR_OVERFLOW;
+	}
+	return EMAB_OK;
+}

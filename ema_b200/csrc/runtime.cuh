@@ -51,4 +51,5 @@ struct emab_ctx {
 	int n_sm = 148;
 	// resident SW microbench inputs
 	int res_n = 0;
+	bool consts_ready = false;
 };

@@ -84,6 +84,50 @@ int emab_sa_batch(emab_ctx_t *ctx, int n, const int64_t *k, int64_t *out, int mo
 int emab_smem_batch(emab_ctx_t *ctx, int n, const uint8_t *seq, const int64_t *off, int64_t *intervals, int32_t *n_intv,
                     int max_intv, int64_t *touches);
 
+/* ---- the pipeline: batched bwa_mem_mate_sw + bwa_smith_waterman + append_alignments ----------
+ * (src/bwabridge.c:204-311, src/align.c:986-1061).  Reads are nt4, concatenated as
+ * pair0/mate1, pair0/mate2, pair1/mate1, ... with 2*n_pairs+1 offsets.
+ *
+ * For every read the call returns its candidate regions IN THE ORDER the reference's
+ * append_alignments visits them (region order of bwa_mem_mate_sw).  n_regs[r] regions of read r
+ * start at alns[sum(n_regs[0..r))].  A record with keep == 0 was dropped by the reference's clip /
+ * edit-distance filters (src/align.c:1017-1024) and must be ignored; the others carry exactly the
+ * fields alignment_to_sam_rec stores in a SAMRecord (src/align.c:915-956).
+ *
+ * stage: 1 = stop after mem_align1_core, 2 = stop after mate rescue (regions only, via regs_dbg),
+ *        3 = full.  regs_dbg (optional) receives 18 int64 per region: rb,re,qb,qe,rid,score,truesc,
+ *        sub,csub,sub_n,w,seedcov,secondary,seedlen0,n_comp,is_alt,frac_rep(float bits),secondary_all.
+ */
+typedef struct {
+	int64_t pos;            /* 0-based leftmost reference position on contig rid */
+	int32_t rid;
+	int32_t is_rev;
+	int32_t NM;
+	int32_t n_cigar;
+	int32_t score;          /* SW score of the region (mem_alnreg_t.score) */
+	int32_t mapq;           /* mem_approx_mapq_se_insist (src/align.c:959-984) */
+	int32_t score_mapq;     /* src/align.c:909-912 */
+	int32_t clip;
+	int32_t clip_edit_dist;
+	int32_t keep;
+	double em_score;        /* src/align.c:904-907 */
+	uint32_t cigar[64];     /* BAM encoding len<<4|op, op 0..3 = M,I,D,S */
+} emab_aln_t;
+
+typedef struct {
+	int64_t extend_cells, global_cells, local_cells;  /* DP cells visited */
+	int64_t occ_touches;                              /* 64-byte Occ block loads */
+	int64_t n_occ, n_regs;
+	double kernel_ms;                                 /* device time, first kernel to last */
+	int32_t launches;
+	int32_t pad;
+} emab_stats_t;
+
+int emab_set_error_rate(emab_ctx_t *ctx, double eps);  /* platform error_rate (src/techs.c:71-127); default 0.001 */
+int emab_align_pairs(emab_ctx_t *ctx, int n_pairs, const uint8_t *seq, const int64_t *off, int stage,
+                     int32_t *n_regs, emab_aln_t *alns, int64_t aln_cap, int64_t *n_alns, int64_t *regs_dbg,
+                     emab_stats_t *stats);
+
 #ifdef __cplusplus
 }
 #endif

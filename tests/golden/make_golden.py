@@ -7,6 +7,8 @@ Outputs
   tiny_rep/ref.sam                                  `ema align -s ... -p 10x -t 1` output of the reference
   sw_golden.npz     ksw_extend2 / ksw_global2 / ksw_align2 inputs + reference outputs
   fm_golden.npz     mem_collect_intv intervals and bwt_sa values of the reference on tiny_rep reads
+  cand_golden.npz   per pair of the tiny_rep bucket (file order): the candidate SAMRecords append_alignments builds
+                    (chrom,pos,rev,mate,mapq,score_mapq,clip,clip_edit_dist,NM,n_cigar,unique ; EM score ; CIGAR)
 """
 import ctypes as C
 import os
@@ -76,6 +78,22 @@ def main():
     rf, ro = helpers.pack(reads)
     np.savez_compressed(os.path.join(HERE, "fm_golden.npz"), reads=rf, roff=ro, intv=np.concatenate(ivs), n_intv=np.array(cnt),
                         ks=ks, sa=sa, info=info)
+    # candidate alignments per pair exactly as append_alignments (src/align.c:986) produces them
+    R.ref_ema_init.argtypes = [C.c_char_p, C.c_char_p]
+    assert R.ref_ema_init(os.path.join(dst, "ref.fa").encode(), b"10x") == 0
+    ints_all, sc_all, cg_all, cnt = [], [], [], []
+    for ln in open(os.path.join(dst, "ema-bin-000.10x")).read().split("\n"):
+        if not ln:
+            continue
+        f = ln.split(" ")
+        ints = np.zeros((4096, 11), np.int64)
+        sc = np.zeros(4096, np.float64)
+        cg = np.zeros((4096, 64), np.uint32)
+        n = R.ref_ema_candidates(f[1][1:].encode(), f[2].encode(), f[3].encode(), f[4].encode(), f[5].encode(),
+                                 _p(ints, C.c_int64), _p(sc, C.c_double), _p(cg, C.c_uint32), 64, 4096)
+        ints_all.append(ints[:n].copy()); sc_all.append(sc[:n].copy()); cg_all.append(cg[:n].copy()); cnt.append(n)
+    np.savez_compressed(os.path.join(HERE, "cand_golden.npz"), ints=np.concatenate(ints_all), score=np.concatenate(sc_all),
+                        cigar=np.concatenate(cg_all), n=np.array(cnt))
     print("golden vectors written to", HERE)
 
 

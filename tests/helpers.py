@@ -180,3 +180,59 @@ def random_extend_tasks(n, seed, max_q=200, n_frac=0.02):
         ts.append(np.asarray(t, dtype=np.uint8))
         h0.append(int(rng.integers(1, 160)))
     return qs, ts, np.array(h0, dtype=np.int32)
+
+
+# ---- bucket files and candidate records ------------------------------------------------------------
+def read_bucket(path, limit=None):
+    """Lines of a preprocessed bucket -> list of (bc, name, read1, qual1, read2, qual2) strings."""
+    out = []
+    with open(path) as f:
+        for ln in f:
+            ln = ln.rstrip("\n")
+            if ln:
+                out.append(tuple(ln.split(" ")))
+            if limit and len(out) >= limit:
+                break
+    return out
+
+
+def cands_from_alns(alns, n1, n2, base=0):
+    """emab_aln_t records of one pair (mate-1 regions then mate-2 regions) -> the tuples the reference's
+    append_alignments would have kept: (chrom,pos1,rev,mate,mapq,score_mapq,clip,clip_edit_dist,NM,n_cigar,score,cigar)"""
+    out = []
+    for k in range(n1 + n2):
+        x = alns[base + k]
+        if x["keep"]:
+            out.append((int(x["rid"]), int(x["pos"]) + 1, int(x["is_rev"]), 0 if k < n1 else 1, int(x["mapq"]), int(x["score_mapq"]),
+                        int(x["clip"]), int(x["clip_edit_dist"]), int(x["NM"]), int(x["n_cigar"]), float(x["em_score"]),
+                        tuple(int(c) for c in x["cigar"][:x["n_cigar"]])))
+    return out
+
+
+def cands_from_golden(g):
+    """tests/golden/cand_golden.npz -> per-pair lists of the same tuples"""
+    out, pos = [], 0
+    for n in g["n"]:
+        cur = []
+        for i, s, c in zip(g["ints"][pos:pos + n], g["score"][pos:pos + n], g["cigar"][pos:pos + n]):
+            cur.append((int(i[0]), int(i[1]), int(i[2]), int(i[3]), int(i[4]), int(i[5]), int(i[6]), int(i[7]), int(i[8]), int(i[9]),
+                        float(s), tuple(int(x) for x in c[:i[9]])))
+        out.append(cur)
+        pos += n
+    return out
+
+
+_hs = None
+
+
+def hostsim():
+    """tests/hostsim/libhostsim.so: the scalar device logic compiled for the host (test tooling)."""
+    global _hs
+    if _hs is None:
+        d = os.path.join(ROOT, "tests", "hostsim")
+        subprocess.run(["make", "-s", "-C", d], check=True)
+        L = C.CDLL(os.path.join(d, "libhostsim.so"))
+        L.hs_index_load.restype = C.c_void_p
+        L.hs_index_load.argtypes = [C.c_char_p]
+        _hs = L
+    return _hs

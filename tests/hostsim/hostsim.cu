@@ -1,0 +1,220 @@
+// tests/hostsim/hostsim.cu — TEST TOOLING ONLY, never loaded by the ema_b200 package.
+//
+// Compiles the thread-scalar (__host__ __device__) control logic of ema_b200/csrc — seeding,
+// chaining, chain filtering, mem_chain2aln's seed-extension scheduling, de-duplication, mate rescue,
+// mem_reg2aln and the append_alignments filters — for the HOST, so that it can be unit-tested against
+// the reference on machines without a GPU.  The DP steps, which on the device are the
+// warp-cooperative kernels of ksw_warp.cuh, are supplied here by the oracle's scalar routines
+// (oracle/oracle_ksw.c): this file therefore checks the control flow around the kernels, while
+// tests/test_gpu_*.py check the kernels themselves and the assembled pipeline on the B200.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../ema_b200/csrc/seed.cuh"
+#include "../../ema_b200/csrc/chain.cuh"
+#include "../../ema_b200/csrc/align.cuh"
+#include "../../oracle/oracle.h"
+#define RESCUE_ROOM_HS 51
+
+thread_local char emab_errbuf[512] = "";
+
+struct HostIndex {
+	orc_index_t *o;
+	DevIndex d;
+	std::vector<uint4> bwt_aligned;  // uint4 loads need 16-byte alignment; the file image is at +40
+	std::vector<uint32_t> sa32;
+	std::vector<uint64_t> sa64;
+};
+
+struct HostDP {  // scalar stand-in for WarpPolicy (pipeline.cu)
+	const DevIndex &ix;
+	int8_t mat[25];
+	explicit HostDP(const DevIndex &i) : ix(i) { orc_fill_scmat(1, 4, mat); }
+	ExtResult extend(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, int end_bonus, int h0)
+	{
+		std::vector<uint8_t> q(qlen + 1), t(tlen + 1);
+		for (int j = 0; j < qlen; ++j) q[j] = query[q0 + j * qstep];
+		for (int i = 0; i < tlen; ++i) t[i] = (uint8_t)ref_base(ix, t0 + (int64_t)i * tstep);
+		ExtResult r;
+		r.score = orc_ksw_extend2(qlen, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, w, end_bonus, opt::zdrop, h0, &r.qle, &r.tle, &r.gtle, &r.gscore, &r.max_off, 0);
+		return r;
+	}
+	int global(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, uint32_t *cigar, int *n_cigar)
+	{
+		std::vector<uint8_t> q(qlen + 1), t(tlen + 1);
+		for (int j = 0; j < qlen; ++j) q[j] = query[q0 + j * qstep];
+		for (int i = 0; i < tlen; ++i) t[i] = (uint8_t)ref_base(ix, t0 + (int64_t)i * tstep);
+		return orc_ksw_global2(qlen, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, w, cigar ? n_cigar : 0, cigar, EMAB_MAX_CIGAR, 0);
+	}
+	LocResult local(const uint8_t *ms, int l_ms, int64_t rb, int tlen)
+	{
+		std::vector<uint8_t> q(l_ms + 1), t(tlen + 1);
+		for (int j = 0; j < l_ms; ++j) q[l_ms - 1 - j] = ms[j] < 4 ? 3 - ms[j] : 4;
+		for (int i = 0; i < tlen; ++i) t[i] = (uint8_t)ref_base(ix, rb + i);
+		int out[7];
+		orc_ksw_align2(l_ms, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, 19, l_ms * opt::a < 250, out, 0);
+		LocResult r{out[0], out[1], out[2], out[3], out[4], out[5], out[6]};
+		return r;
+	}
+};
+
+static void flatten(const Reg &g, int64_t *o)
+{
+	union { float f; uint32_t u; } fr; fr.f = g.frac_rep;
+	o[0] = g.rb; o[1] = g.re; o[2] = g.qb; o[3] = g.qe; o[4] = g.rid; o[5] = g.score; o[6] = g.truesc; o[7] = g.sub; o[8] = g.csub;
+	o[9] = g.sub_n; o[10] = g.w; o[11] = g.seedcov; o[12] = g.secondary; o[13] = g.seedlen0; o[14] = g.n_comp; o[15] = 0; o[16] = fr.u; o[17] = 0;
+}
+
+extern "C" {
+
+void *hs_index_load(const char *prefix)
+{
+	orc_index_t *o = orc_index_load(prefix);
+	if (!o) return 0;
+	HostIndex *h = new HostIndex();
+	h->o = o;
+	DevIndex &d = h->d;
+	memset(&d, 0, sizeof d);
+	h->bwt_aligned.resize(o->bwt_size / 4 + 4);
+	memcpy(h->bwt_aligned.data(), o->bwt, o->bwt_size * 4);
+	d.bwt = h->bwt_aligned.data(); d.n_blocks = o->bwt_size / 16; d.primary = o->primary; d.seq_len = o->seq_len;
+	for (int i = 0; i < 5; ++i) d.L2[i] = o->L2[i];
+	d.sa_sampled = o->sa; d.sa_intv = o->sa_intv; d.pac = o->pac; d.l_pac = o->l_pac; d.n_seqs = o->n_seqs;
+	d.ann_offset = o->ann_offset; d.ann_len = o->ann_len;
+	// dense SA, same walk as k_build_dense_sa (api.cu)
+	h->sa32.assign(d.seq_len + 1, 0);
+	Fm fm{d, 0};
+	uint64_t mask = (uint64_t)d.sa_intv - 1;
+	for (uint64_t m = 0; m < o->n_sa; ++m) {
+		uint64_t k = m * d.sa_intv, s = m == 0 ? d.seq_len : o->sa[m];
+		h->sa32[k] = (uint32_t)s;
+		for (;;) {
+			k = bwt_invPsi(fm, k);
+			if ((k & mask) == 0) break;
+			--s;
+			h->sa32[k] = (uint32_t)s;
+		}
+	}
+	d.sa32 = h->sa32.data();
+	return h;
+}
+
+int hs_collect_intv(void *h_, int len, const uint8_t *seq, int64_t *out, int max)
+{
+	HostIndex *h = (HostIndex *)h_;
+	std::vector<Intv> mem(EMAB_MAX_INTV), b0(EMAB_MAX_READ_LEN + 1), b1(EMAB_MAX_READ_LEN + 1);
+	Fm fm{h->d, 0};
+	int ovf = 0;
+	int n = collect_intv(fm, len, seq, mem.data(), EMAB_MAX_INTV, b0.data(), b1.data(), &ovf);
+	for (int i = 0; i < n && i < max; ++i) { out[i*4] = mem[i].x0; out[i*4+1] = mem[i].x1; out[i*4+2] = mem[i].x2; out[i*4+3] = mem[i].info; }
+	return ovf ? -1 : n;
+}
+
+struct ReadWork {
+	std::vector<Intv> intv, b0, b1;
+	std::vector<Seed> w_seeds, seeds;
+	std::vector<Chain> w_chains, chains;
+	std::vector<BNode> nodes;
+	std::vector<int32_t> ord;
+	std::vector<uint64_t> srt;
+	std::vector<Reg> regs;
+	int n_chains = 0, n_regs = 0, cap = 0;
+};
+
+static int do_chain(HostIndex *h, int len, const uint8_t *seq, ReadWork &w)
+{
+	w.intv.resize(EMAB_MAX_INTV); w.b0.resize(EMAB_MAX_READ_LEN + 1); w.b1.resize(EMAB_MAX_READ_LEN + 1);
+	Fm fm{h->d, 0};
+	int ovf = 0;
+	int n = collect_intv(fm, len, seq, w.intv.data(), EMAB_MAX_INTV, w.b0.data(), w.b1.data(), &ovf);
+	int cap = 0;
+	if (len >= opt::min_seed_len) for (int i = 0; i < n; ++i) cap += intv_occ_count(w.intv[i].x2);
+	w.cap = cap;
+	w.w_seeds.resize(cap + 1); w.seeds.resize(cap + 1); w.w_chains.resize(cap + 1); w.chains.resize(cap + 1);
+	w.nodes.resize(cap / 3 + 3); w.ord.resize(3 * cap + 3); w.srt.resize(cap + 1); w.regs.resize(cap + RESCUE_ROOM_HS + 1);
+	ChainWork wk{w.w_seeds.data(), w.w_chains.data(), w.nodes.data(), w.ord.data()};
+	w.n_chains = chain_read(h->d, len, w.intv.data(), n, wk, cap, w.chains.data(), w.seeds.data());
+	return w.n_chains;
+}
+
+// chains after mem_chain_flt: pos,rid,n,w,kept,first,frac_rep_bits,seed_off ; seeds: rbeg,qbeg,len,score
+int hs_chain(void *h_, int len, const uint8_t *seq, int64_t *chains, int maxc, int64_t *seeds, int maxs, int *n_seeds_out)
+{
+	HostIndex *h = (HostIndex *)h_;
+	ReadWork w;
+	int n = do_chain(h, len, seq, w), ns = 0;
+	for (int i = 0; i < n; ++i) {
+		const Chain &c = w.chains[i];
+		union { float f; uint32_t u; } fr; fr.f = c.frac_rep;
+		if (i < maxc) { chains[i*8] = c.pos; chains[i*8+1] = c.rid; chains[i*8+2] = c.n; chains[i*8+3] = c.w; chains[i*8+4] = c.kept; chains[i*8+5] = c.first; chains[i*8+6] = fr.u; chains[i*8+7] = ns; }
+		for (int j = 0; j < c.n; ++j, ++ns)
+			if (ns < maxs) { const Seed &s = w.seeds[c.seed_beg + j]; seeds[ns*4] = s.rbeg; seeds[ns*4+1] = s.qbeg; seeds[ns*4+2] = s.len; seeds[ns*4+3] = s.score; }
+	}
+	*n_seeds_out = ns;
+	return n;
+}
+
+static int do_align1(HostIndex *h, int len, const uint8_t *seq, ReadWork &w, bool dedup)
+{
+	do_chain(h, len, seq, w);
+	HostDP dp(h->d);
+	if (dedup) w.n_regs = align1_from_chains(h->d, dp, len, seq, w.chains.data(), w.n_chains, w.seeds.data(), w.srt.data(), w.regs.data());
+	else {
+		int n = 0;
+		for (int i = 0; i < w.n_chains; ++i) chain2aln(h->d, dp, len, seq, w.chains[i], w.seeds.data() + w.chains[i].seed_beg, w.srt.data(), w.regs.data(), &n);
+		w.n_regs = n;
+	}
+	return w.n_regs;
+}
+
+int hs_align1(void *h_, int len, const uint8_t *seq, int64_t *regs, int max, int dedup)
+{
+	ReadWork w;
+	int n = do_align1((HostIndex *)h_, len, seq, w, dedup != 0);
+	for (int i = 0; i < n && i < max; ++i) flatten(w.regs[i], regs + (size_t)i * 18);
+	return n;
+}
+
+int hs_pair(void *h_, int l1, const uint8_t *s1, int l2, const uint8_t *s2, int64_t *regs1, int *n1, int64_t *regs2, int *n2, int max)
+{
+	HostIndex *h = (HostIndex *)h_;
+	ReadWork w1, w2;
+	do_align1(h, l1, s1, w1, true);
+	do_align1(h, l2, s2, w2, true);
+	HostDP dp(h->d);
+	mate_sw_pair(h->d, dp, l1, s1, l2, s2, w1.regs.data(), &w1.n_regs, w2.regs.data(), &w2.n_regs);
+	*n1 = w1.n_regs; *n2 = w2.n_regs;
+	for (int i = 0; i < w1.n_regs && i < max; ++i) flatten(w1.regs[i], regs1 + (size_t)i * 18);
+	for (int i = 0; i < w2.n_regs && i < max; ++i) flatten(w2.regs[i], regs2 + (size_t)i * 18);
+	return 0;
+}
+
+// full per-pair path: candidates as emab_aln_t-compatible records (sizeof(Aln) bytes each), mate 1 then mate 2
+int hs_candidates(void *h_, double eps, int l1, const uint8_t *s1, int l2, const uint8_t *s2, void *alns, int *n1, int *n2, int max)
+{
+	HostIndex *h = (HostIndex *)h_;
+	ReadWork w1, w2;
+	do_align1(h, l1, s1, w1, true);
+	do_align1(h, l2, s2, w2, true);
+	HostDP dp(h->d);
+	mate_sw_pair(h->d, dp, l1, s1, l2, s2, w1.regs.data(), &w1.n_regs, w2.regs.data(), &w2.n_regs);
+	static ScoreConsts sc;
+	sc.log_match = log(1 - eps); sc.log_mismatch = log(eps); sc.log_indel = log(0.0001); sc.log_clip = log(0.03);
+	sc.log10_mismatch = log10(eps); sc.log10_indel = log10(0.0001); sc.log10_clip = log10(0.03);
+	const int fac = (int)log(50.0f);
+	for (int l = 0; l < 1024; ++l) sc.mapq_len_coef[l] = l < 50 ? 1. : fac / log((double)l);
+	*n1 = w1.n_regs; *n2 = w2.n_regs;
+	if (w1.n_regs + w2.n_regs > max) return -1;
+	Aln *out = (Aln *)alns;
+	memset(out, 0, sizeof(Aln) * (w1.n_regs + w2.n_regs));
+	int best_dist = -1;
+	append_candidates(h->d, dp, sc, l1, s1, w1.regs.data(), w1.n_regs, out, &best_dist);
+	append_candidates(h->d, dp, sc, l2, s2, w2.regs.data(), w2.n_regs, out + w1.n_regs, &best_dist);
+	return 0;
+}
+
+int hs_sizeof_aln(void) { return (int)sizeof(Aln); }
+
+}  // extern "C"

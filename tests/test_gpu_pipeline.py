@@ -1,0 +1,125 @@
+"""GPU parity tests (-m gpu) of the assembled device pipeline (emab_align_pairs, through the C ABI):
+candidate alignments — positions, strands, CIGARs, NM, MAPQ inputs and the EM log-likelihood
+score — must be bit-exact against the reference's append_alignments (golden vectors, and the
+compiled reference where oracle/_ref exists)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import _p
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def emab():
+    import ema_b200
+    return ema_b200
+
+
+def pipeline_candidates(emab, ctx, lines):
+    reads = []
+    for f in lines:
+        reads += [helpers.nt4(f[2]), helpers.nt4(f[4])]
+    res = emab.align_pairs(ctx, reads)
+    off = np.zeros(len(reads) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(res["n_regs"])
+    out = []
+    for i in range(len(lines)):
+        n1, n2 = int(res["n_regs"][2 * i]), int(res["n_regs"][2 * i + 1])
+        out.append(helpers.cands_from_alns(res["alns"], n1, n2, int(off[2 * i])))
+    return out, res
+
+
+def test_candidates_golden(emab):
+    ix = emab.Index(os.path.join(G, "tiny_rep", "ref.fa"))
+    ctx = emab.Context(ix)
+    want = helpers.cands_from_golden(np.load(os.path.join(G, "cand_golden.npz")))
+    lines = helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x"))
+    got, res = pipeline_candidates(emab, ctx, lines)
+    bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert not bad, f"{len(bad)} of {len(want)} pairs differ; first {lines[bad[0]][1]}: {got[bad[0]]} vs {want[bad[0]]}"
+    st = res["stats"]
+    assert st.launches >= 7 and st.kernel_ms > 0 and st.occ_touches > 0
+    # determinism: a second run returns identical bytes
+    got2, _ = pipeline_candidates(emab, ctx, lines)
+    assert got2 == got
+
+
+def test_stage_regions_vs_hostsim(emab):
+    """regions after mem_align1_core (stage 1) and after mate rescue (stage 2) against the host build of
+    the same control logic driven by the oracle's scalar DP (itself pinned to the reference)."""
+    hs = helpers.hostsim()
+    pre = os.path.join(G, "tiny_rep", "ref.fa")
+    ix = emab.Index(pre)
+    ctx = emab.Context(ix)
+    hi = C.c_void_p(hs.hs_index_load(pre.encode()))
+    lines = helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x"))
+    reads = []
+    for f in lines:
+        reads += [helpers.nt4(f[2]), helpers.nt4(f[4])]
+    for stage in (1, 2):
+        res = emab.align_pairs(ctx, reads, stage=stage, want_regs=True)
+        off = np.zeros(len(reads) + 1, dtype=np.int64)
+        off[1:] = np.cumsum(res["n_regs"])
+        for i in range(len(lines)):
+            s1, s2 = reads[2 * i], reads[2 * i + 1]
+            if stage == 1:
+                for k, s in ((2 * i, s1), (2 * i + 1, s2)):
+                    rg = np.zeros((4096, 18), np.int64)
+                    n = hs.hs_align1(hi, len(s), _p(s, C.c_uint8), _p(rg, C.c_int64), 4096, 1)
+                    assert np.array_equal(res["regs"][off[k]:off[k + 1]], rg[:n]), (stage, lines[i][1])
+            else:
+                a1 = np.zeros((4096, 18), np.int64)
+                a2 = np.zeros((4096, 18), np.int64)
+                n1, n2 = C.c_int(), C.c_int()
+                hs.hs_pair(hi, len(s1), _p(s1, C.c_uint8), len(s2), _p(s2, C.c_uint8), _p(a1, C.c_int64), C.byref(n1), _p(a2, C.c_int64), C.byref(n2), 4096)
+                assert np.array_equal(res["regs"][off[2 * i]:off[2 * i + 1]], a1[:n1.value]), (stage, lines[i][1])
+                assert np.array_equal(res["regs"][off[2 * i + 1]:off[2 * i + 2]], a2[:n2.value]), (stage, lines[i][1])
+
+
+def test_candidates_vs_reference_c1(emab, ref_lib):
+    """BASELINE config 1 with planted repeats + indels: 10k pairs against the compiled reference."""
+    from tools import synth
+    if not os.path.exists(helpers.ref_bin("bwa")):
+        pytest.skip("oracle/_ref/bwa missing")
+    p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    ix = emab.Index(p["fasta"])
+    ctx = emab.Context(ix)
+    lines = helpers.read_bucket(p["bucket"], 3000)
+    got, res = pipeline_candidates(emab, ctx, lines)
+    ref_lib.ref_ema_init.argtypes = [C.c_char_p, C.c_char_p]
+    assert ref_lib.ref_ema_init(p["fasta"].encode(), b"10x") == 0
+    bad = 0
+    for f, g in zip(lines, got):
+        ints = np.zeros((4096, 11), np.int64)
+        sc = np.zeros(4096, np.float64)
+        cg = np.zeros((4096, 64), np.uint32)
+        n = ref_lib.ref_ema_candidates(f[1][1:].encode(), f[2].encode(), f[3].encode(), f[4].encode(), f[5].encode(),
+                                       _p(ints, C.c_int64), _p(sc, C.c_double), _p(cg, C.c_uint32), 64, 4096)
+        want = [(int(i[0]), int(i[1]), int(i[2]), int(i[3]), int(i[4]), int(i[5]), int(i[6]), int(i[7]), int(i[8]), int(i[9]), float(s),
+                 tuple(int(c) for c in c_[:i[9]])) for i, s, c_ in zip(ints[:n], sc[:n], cg[:n])]
+        if g != want:
+            bad += 1
+            if bad == 1:
+                first = (f[1], g, want)
+    assert bad == 0, f"{bad} pairs differ, first: {first}"
+
+
+def test_edge_cases(emab):
+    ix = emab.Index(os.path.join(G, "tiny_rep", "ref.fa"))
+    ctx = emab.Context(ix)
+    res = emab.align_pairs(ctx, [])
+    assert len(res["alns"]) == 0
+    lines = helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x"), 4)
+    r = helpers.nt4(lines[0][2])
+    # all-N mate, too-short mate, ragged lengths in one batch
+    reads = [r, np.full(150, 4, np.uint8), r[:15], helpers.nt4(lines[1][4]), helpers.nt4(lines[2][2])[:60], helpers.nt4(lines[2][4])]
+    res = emab.align_pairs(ctx, reads)
+    assert res["n_regs"][1] == 0 and res["n_regs"][2] == 0 and res["n_regs"][0] >= 1
+    with pytest.raises(emab.EmabError):
+        emab.align_pairs(ctx, [np.zeros(400, np.uint8), r])

@@ -1,0 +1,97 @@
+"""CPU tests (-m "not gpu") of the HOST-SIDE/control logic of the product: the thread-scalar
+(__host__ __device__) code of ema_b200/csrc — seeding, chaining, filtering, extension scheduling,
+de-duplication, mate rescue, CIGAR generation, candidate filters — compiled for the host by
+tests/hostsim (DP steps supplied by the oracle), checked against golden vectors of the reference
+and, where oracle/_ref is built, against the reference itself stage by stage."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import _p
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+ALN = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("NM", "<i4"), ("n_cigar", "<i4"), ("score", "<i4"),
+                ("mapq", "<i4"), ("score_mapq", "<i4"), ("clip", "<i4"), ("clip_edit_dist", "<i4"), ("keep", "<i4"),
+                ("em_score", "<f8"), ("cigar", "<u4", (64,))])
+
+
+@pytest.fixture(scope="module")
+def hs():
+    helpers.build_port()
+    return helpers.hostsim()
+
+
+def hs_candidates(H, hi, s1, s2):
+    al = np.zeros(8192, ALN)
+    n1, n2 = C.c_int(), C.c_int()
+    rc = H.hs_candidates(hi, C.c_double(0.001), len(s1), _p(s1, C.c_uint8), len(s2), _p(s2, C.c_uint8),
+                         al.ctypes.data_as(C.c_void_p), C.byref(n1), C.byref(n2), 8192)
+    assert rc == 0
+    return helpers.cands_from_alns(al, n1.value, n2.value)
+
+
+def test_layout(hs):
+    assert hs.hs_sizeof_aln() == ALN.itemsize
+
+
+def test_candidates_golden(hs):
+    hi = C.c_void_p(hs.hs_index_load(os.path.join(G, "tiny_rep", "ref.fa").encode()))
+    want = helpers.cands_from_golden(np.load(os.path.join(G, "cand_golden.npz")))
+    lines = helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x"))
+    assert len(lines) == len(want)
+    n_multi = 0
+    for f, w in zip(lines, want):
+        got = hs_candidates(hs, hi, helpers.nt4(f[2]), helpers.nt4(f[4]))
+        assert got == w, f[1]
+        n_multi += len(w) > 2
+    assert n_multi > 5, "fixture must contain multi-mapped pairs"
+
+
+def test_seeding_golden(hs):
+    g = np.load(os.path.join(G, "fm_golden.npz"))
+    hi = C.c_void_p(hs.hs_index_load(os.path.join(G, "tiny_rep", "ref.fa").encode()))
+    pos = 0
+    for i, n in enumerate(g["n_intv"]):
+        s = np.ascontiguousarray(g["reads"][g["roff"][i]:g["roff"][i + 1]])
+        ob = np.zeros((256, 4), np.int64)
+        nb = hs.hs_collect_intv(hi, len(s), _p(s, C.c_uint8), _p(ob, C.c_int64), 256)
+        assert nb == n and np.array_equal(ob[:nb], g["intv"][pos:pos + n])
+        pos += n
+
+
+def _regs(lib, fn, idx, s, *extra):
+    rg = np.zeros((4096, 18), np.int64)
+    n = getattr(lib, fn)(idx, len(s), _p(s, C.c_uint8), _p(rg, C.c_int64), 4096, *extra)
+    return rg[:n]
+
+
+def _chains(lib, fn, idx, s, *flt):
+    ch = np.zeros((4096, 8), np.int64)
+    sd = np.zeros((65536, 4), np.int64)
+    ns = C.c_int(0)
+    n = getattr(lib, fn)(idx, len(s), _p(s, C.c_uint8), *flt, _p(ch, C.c_int64), 4096, _p(sd, C.c_int64), 65536, C.byref(ns))
+    return ch[:n], sd[:ns.value]
+
+
+@pytest.mark.parametrize("cfg,limit", [("tiny_rep", 480), ("c1_rep", 700)])
+def test_stages_vs_reference(hs, ref_lib, cfg, limit):
+    """chains after mem_chain_flt, regions after mem_chain2aln, after mem_sort_dedup_patch, after
+    mate rescue, and the final candidates: all bit-exact against the compiled reference."""
+    from tools import synth
+    p = synth.build_config(cfg, helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    pre = p["fasta"].encode()
+    hi = C.c_void_p(hs.hs_index_load(pre))
+    ri = C.c_void_p(ref_lib.ref_idx_load(pre))
+    rng = np.random.default_rng(5)
+    for f in helpers.read_bucket(p["bucket"], limit):
+        reads = [helpers.nt4(f[2]), helpers.nt4(f[4])]
+        if rng.random() < 0.05:
+            reads[0][rng.integers(0, len(reads[0]))] = 4
+        for s in reads:
+            a, b = _chains(hs, "hs_chain", hi, s), _chains(ref_lib, "ref_chain", ri, s, 1)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), ("chain", f[1])
+            assert np.array_equal(_regs(hs, "hs_align1", hi, s, 0), _regs(ref_lib, "ref_chain2aln", ri, s)), ("chain2aln", f[1])
+            assert np.array_equal(_regs(hs, "hs_align1", hi, s, 1), _regs(ref_lib, "ref_align1", ri, s)), ("align1", f[1])
