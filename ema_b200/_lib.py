@@ -33,6 +33,10 @@ def lib():
         L.emab_index_build_ms.argtypes = [C.c_void_p]
         L.emab_index_free.argtypes = [C.c_void_p]
         L.emab_ctx_free.argtypes = [C.c_void_p]
+        L.emab_session_close.argtypes = [C.c_void_p]
+        L.emab_free.argtypes = [C.c_void_p]
+        L.emab_align_bucket.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.emab_align_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -197,3 +201,62 @@ def align_pairs(ctx: Context, reads, stage=3, want_regs=False, aln_cap=None):
                                   _p(regs, C.c_int64) if want_regs else None, C.byref(st)))
     A = n_alns.value
     return dict(n_regs=n_regs, alns=alns[:A], regs=regs[:A] if want_regs else None, stats=st)
+
+
+class RunStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("parse_ms", "encode_ms", "align_ms", "kernel_ms", "cloud_ms", "flatten_ms", "em_ms",
+                                          "em_kernel_ms", "format_ms", "total_ms")] + \
+               [(n, C.c_int64) for n in ("n_pairs", "n_barcodes", "n_cands", "n_clouds", "sam_bytes", "extend_cells", "global_cells",
+                                         "local_cells", "occ_touches")] + [("launches", C.c_int32), ("pad", C.c_int32)]
+
+
+class Session:
+    """The operator the reference's main() calls (find_clouds_and_align and friends) on one GPU:
+    emab_session_open / emab_sam_header / emab_align_bucket / emab_align_fastq."""
+
+    def __init__(self, ref_path: str, platform: str = "10x", device: int = 0, rg: str | None = None, bx_index: str | None = None,
+                 apply_opt: bool = False, threads: int = 1):
+        self._h = C.c_void_p()
+        _check(lib().emab_session_open(ref_path.encode(), platform.encode(), device, C.byref(self._h)))
+        _check(lib().emab_session_config(self._h, rg.encode() if rg else None, bx_index.encode() if bx_index else None,
+                                         int(apply_opt), threads))
+
+    def header(self, argv) -> bytes:
+        arr = (C.c_char_p * len(argv))(*[a.encode() for a in argv])
+        text, n = C.c_void_p(), C.c_uint64()
+        _check(lib().emab_sam_header(self._h, len(argv), arr, C.byref(text), C.byref(n)))
+        out = C.string_at(text, n.value)
+        lib().emab_free(text)
+        return out
+
+    def _take(self, text, n) -> bytes:
+        out = C.string_at(text, n.value)
+        lib().emab_free(text)
+        return out
+
+    def align_bucket(self, data: bytes) -> bytes:
+        text, n = C.c_void_p(), C.c_uint64()
+        _check(lib().emab_align_bucket(self._h, data, len(data), C.byref(text), C.byref(n)))
+        return self._take(text, n)
+
+    def align_fastq(self, d1: bytes, d2: bytes | None = None) -> bytes:
+        text, n = C.c_void_p(), C.c_uint64()
+        _check(lib().emab_align_fastq(self._h, d1, len(d1), d2, len(d2) if d2 else 0, C.byref(text), C.byref(n)))
+        return self._take(text, n)
+
+    @property
+    def stats(self) -> RunStats:
+        st = RunStats()
+        _check(lib().emab_session_stats(self._h, C.byref(st)))
+        return st
+
+    def close(self):
+        if self._h:
+            lib().emab_session_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

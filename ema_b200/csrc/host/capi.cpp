@@ -1,0 +1,98 @@
+// C ABI of the host side (include/ema_b200.h, "the operator the reference's main() calls").
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include "ema_host.hpp"
+
+extern thread_local char emab_errbuf[512];
+
+struct emab_session { emab::Session *s; };
+
+static int fail(int rc, const std::string &msg)
+{
+	snprintf(emab_errbuf, sizeof emab_errbuf, "%s", msg.c_str());
+	return rc;
+}
+
+static int give(const std::string &text, char **out, uint64_t *len)
+{
+	char *p = (char *)malloc(text.size() + 1);
+	if (!p) return fail(EMAB_ERR_NOMEM, "out of memory");
+	memcpy(p, text.data(), text.size());
+	p[text.size()] = 0;
+	*out = p; *len = text.size();
+	return EMAB_OK;
+}
+
+extern "C" {
+
+int emab_session_open(const char *ref_path, const char *platform, int device, emab_session_t **out)
+{
+	*out = nullptr;
+	if (!ref_path || !platform) return fail(EMAB_ERR_ARG, "null argument");
+	emab::Session *s = nullptr;
+	std::string err;
+	int rc = emab::session_open(ref_path, platform, device, &s, &err);
+	if (rc) return fail(rc, err);
+	*out = new emab_session{s};
+	return EMAB_OK;
+}
+
+void emab_session_close(emab_session_t *h)
+{
+	if (!h) return;
+	emab::session_close(h->s);
+	delete h;
+}
+
+int emab_session_config(emab_session_t *h, const char *rg, const char *bx_index, int apply_opt, int n_threads)
+{
+	if (!h) return fail(EMAB_ERR_ARG, "null session");
+	if (rg) {  // validate_read_group (src/main.c:73-76)
+		std::string r(rg);
+		if (r.rfind("@RG\t", 0) != 0 || r.find("\tID:") == std::string::npos) return fail(EMAB_ERR_ARG, "error: malformed read group: '" + r + "'");
+		h->s->rg = r;
+	}
+	if (bx_index) h->s->bx_index = bx_index;
+	h->s->apply_opt = apply_opt;
+	h->s->n_threads = n_threads > 0 ? n_threads : 1;
+	return EMAB_OK;
+}
+
+int emab_sam_header(emab_session_t *h, int argc, const char *const *argv, char **text, uint64_t *len)
+{
+	if (!h) return fail(EMAB_ERR_ARG, "null session");
+	std::string o;
+	emab::sam_header(h->s, argc, argv, &o);
+	return give(o, text, len);
+}
+
+int emab_align_bucket(emab_session_t *h, const char *data, uint64_t len, char **sam, uint64_t *sam_len)
+{
+	if (!h || (!data && len)) return fail(EMAB_ERR_ARG, "null argument");
+	std::string o;
+	int rc = emab::align_special_fastq(h->s, data, (size_t)len, &o);
+	if (rc) return fail(rc, h->s->err);
+	return give(o, sam, sam_len);
+}
+
+int emab_align_fastq(emab_session_t *h, const char *d1, uint64_t l1, const char *d2, uint64_t l2, char **sam, uint64_t *sam_len)
+{
+	if (!h || (!d1 && l1)) return fail(EMAB_ERR_ARG, "null argument");
+	std::string o;
+	int rc = emab::align_fastq(h->s, d1, (size_t)l1, d2, (size_t)l2, &o);
+	if (rc) return fail(rc, h->s->err);
+	return give(o, sam, sam_len);
+}
+
+int emab_session_stats(const emab_session_t *h, emab_run_stats_t *out)
+{
+	if (!h || !out) return EMAB_ERR_ARG;
+	*out = h->s->last;
+	return EMAB_OK;
+}
+
+emab_ctx_t *emab_session_ctx(emab_session_t *h) { return h ? h->s->ctx : nullptr; }
+void emab_free(void *p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,993 @@
+// Host side of `ema align`: everything the reference does around its BWA bridge, restated around the
+// device pipeline so that the SAM bytes are the reference's.
+//
+//   session_open          <- main()'s set-up for `align` + bwa_init + read_fai   (src/main.c:316-369, src/align.c:180-186)
+//   sam_header            <- write_sam_header                                    (src/align.c:193-212)
+//   align_special_fastq   <- find_clouds_and_align over a preprocessed bucket    (src/align.c:214-630, 759-843)
+//   align_fastq           <- the same over barcode-sorted FASTQ(s)               (src/align.c:637-744)
+//   Barcode::build_clouds <- the cloud sweep + SAMDict bookkeeping               (src/align.c:354-408, src/samdict.c:76-157)
+//   Barcode::choose       <- find_best_record, duplicate marking                 (src/samdict.c:166-243, src/align.c:545-585)
+//   print_sam_record      <- print_sam_record                                    (src/samrecord.c:104-284)
+//   mark_optimal          <- mark_optimal_alignments_in_cloud (-d)               (src/split.c:38-338)
+//
+// One bucket is one device batch: every pair of the bucket goes through emab_align_pairs in one
+// call, the EM of every barcode through emab_em_batch in one call.  Barcodes are independent
+// (SURVEY.md §8e), so cloud building and SAM formatting run on an OpenMP team and are stitched back
+// in barcode order, which is the reference's `-t 1` order (MI cloud ids included).
+#include "ema_host.hpp"
+#include <omp.h>
+#include <algorithm>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string_view>
+#include <unordered_map>
+
+namespace emab {
+
+// ---------------------------------------------------------------------------------------------
+// platforms (src/techs.c:71-127)
+// ---------------------------------------------------------------------------------------------
+static const Platform g_platforms[] = {
+    {"haplotag", BC_HAPLOTAG, 0, 12, 50000, 0.001, 4, {0.6, 0.05, 0.2, 0.01}},
+    {"10x", BC_10X, 0, 16, 50000, 0.001, 4, {0.6, 0.05, 0.2, 0.01}},
+    {"tru", BC_TRUSEQ, 1, 0, 15000, 0.001, 4, {0.6, 0.05, 0.2, 0.01}},
+    {"cpt", BC_CPTSEQ, 1, 0, 3500, 0.01, 9, {0.6, 0.01, 0.15, 0.001, 0.05, 0.001, 0.02, 0.001, 0.01}},
+    {"dbs", BC_10X, 0, 20, 50000, 0.001, 4, {0.6, 0.05, 0.2, 0.01}},
+    {"tellseq", BC_TELLSEQ, 0, 18, 50000, 0.001, 4, {0.6, 0.05, 0.2, 0.01}},
+};
+
+const Platform *platform_by_name(const char *name)
+{
+	for (const Platform &p : g_platforms)
+		if (strcmp(name, p.name) == 0) return &p;
+	return nullptr;
+}
+
+static double now_ms()
+{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+// barcodes (src/util.c:41-95)
+// ---------------------------------------------------------------------------------------------
+static bool encode_bc_default(const char *bc, int bc_len, uint64_t *out)
+{
+	uint64_t v = 0;
+	for (int i = bc_len - 1; i >= 0; --i) {
+		v <<= 2;
+		switch (bc[i]) {
+		case 'A': case 'a': break;
+		case 'C': case 'c': v |= 1; break;
+		case 'G': case 'g': v |= 2; break;
+		case 'T': case 't': v |= 3; break;
+		default: return false;  // the reference asserts here
+		}
+	}
+	*out = v;
+	return true;
+}
+
+static uint64_t encode_bc_haplotag(const char *s)
+{  // AxxCxxBxxDxx -> a<<24 | c<<16 | b<<8 | d   (src/util.c:66-73)
+	auto two = [](const char *p) { return (uint32_t)(10 * (p[0] - '0') + (p[1] - '0')); };
+	uint32_t a = two(s + 1), b = two(s + 7), c = two(s + 4), d = two(s + 10);
+	return (uint64_t)((a << 24) | (c << 16) | (b << 8) | d);
+}
+
+static bool encode_bc(const Session *s, const char *bc, size_t avail, uint64_t *out)
+{
+	if (s->is_haplotag) {
+		if (avail < 12) return false;
+		*out = encode_bc_haplotag(bc);
+		return true;
+	}
+	if ((int)avail < s->bc_len) return false;
+	return encode_bc_default(bc, s->bc_len, out);
+}
+
+static void decode_bc(const Session *s, uint64_t bc, std::string *out)
+{
+	if (s->is_haplotag) {
+		char buf[32];
+		snprintf(buf, sizeof buf, "A%02uC%02uB%02uD%02u", (unsigned)((bc >> 24) & 127), (unsigned)((bc >> 16) & 127), (unsigned)((bc >> 8) & 127), (unsigned)(bc & 127));
+		out->append(buf, std::min<size_t>(strlen(buf), (size_t)s->bc_len));  // bc_str has BC_LEN+1 bytes, zero-filled (src/samrecord.c:237-238)
+		return;
+	}
+	for (int i = 0; i < s->bc_len; ++i) { out->push_back("ACGT"[bc & 3]); bc >>= 2; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// session
+// ---------------------------------------------------------------------------------------------
+int session_open(const char *ref_path, const char *platform, int device, Session **out, std::string *err)
+{
+	*out = nullptr;
+	const Platform *tech = platform_by_name(platform);
+	if (!tech) { *err = std::string("error: invalid platform name: '") + platform + "'"; return EMAB_ERR_ARG; }
+	Session *s = new Session();
+	s->tech = tech;
+	s->bc_len = (int)tech->bc_len;
+	s->is_haplotag = strcmp(tech->name, "haplotag") == 0;
+	{  // read_fai: first whitespace-delimited token of every line of <ref>.fai (src/main.c:57-71)
+		std::string fai = std::string(ref_path) + ".fai";
+		FILE *f = fopen(fai.c_str(), "r");
+		if (!f) { *err = "error: file " + fai + " could not be opened"; delete s; return EMAB_ERR_IO; }
+		char line[256];  // MAX_CHROM_NAME_LEN
+		while (fgets(line, sizeof line, f)) {
+			size_t j = 0;
+			while (line[j] && !isspace((unsigned char)line[j])) ++j;
+			s->fai_names.emplace_back(line, j);
+		}
+		fclose(f);
+	}
+	int rc = emab_index_load(ref_path, device, &s->ix);
+	if (rc) { *err = std::string("error: could not load reference at ") + ref_path + ": " + emab_last_error(); delete s; return rc; }
+	rc = emab_ctx_create(s->ix, &s->ctx);
+	if (rc) { *err = emab_last_error(); emab_index_free(s->ix); delete s; return rc; }
+	emab_set_error_rate(s->ctx, tech->error_rate);
+	int64_t info[12];
+	emab_index_info(s->ix, info);
+	for (int i = 0; i < (int)info[1]; ++i) {
+		int64_t off; int32_t len; char name[1024];
+		emab_index_contig(s->ix, i, &off, &len, name, sizeof name);
+		s->sq_names.push_back(name);
+		s->sq_len.push_back(len);
+		// chrom_index: first .fai entry that starts with the contig name (src/main.c:41-55; a prefix match)
+		int found = -1;
+		size_t l = strlen(name);
+		for (size_t k = 0; k < s->fai_names.size(); ++k)
+			if (strncmp(name, s->fai_names[k].c_str(), l) == 0) { found = (int)k; break; }
+		if (found < 0) { *err = std::string("error: contig ") + name + " is not in the .fai"; session_close(s); return EMAB_ERR_ARG; }
+		s->rid2chrom.push_back(found);
+	}
+	*out = s;
+	return EMAB_OK;
+}
+
+void session_close(Session *s)
+{
+	if (!s) return;
+	emab_ctx_free(s->ctx);
+	emab_index_free(s->ix);
+	delete s;
+}
+
+void sam_header(const Session *s, int argc, const char *const *argv, std::string *out)
+{  // src/align.c:193-212
+	char buf[2048];
+	out->append("@HD\tVN:1.3\tSO:unsorted\n");
+	for (size_t i = 0; i < s->sq_names.size(); ++i) {
+		snprintf(buf, sizeof buf, "@SQ\tSN:%s\tLN:%d\n", s->sq_names[i].c_str(), s->sq_len[i]);
+		out->append(buf);
+	}
+	if (s->has_rg) { out->append(s->rg); out->push_back('\n'); }
+	out->append("@PG\tID:ema\tPN:ema\tVN:0.6.2\tCL:");
+	for (int i = 0; i < argc; ++i) { if (i) out->push_back(' '); out->append(argv[i]); }
+	out->push_back('\n');
+}
+
+// ---------------------------------------------------------------------------------------------
+// records
+// ---------------------------------------------------------------------------------------------
+struct Pair {  // one FASTQ pair (two FASTQRecords sharing an id in the bucket format)
+	uint64_t bc;
+	std::string_view id1, id2;   // without the leading '@'
+	std::string_view read[2], qual[2];
+};
+
+struct Rec {  // SAMRecord (include/samrecord.h:22-58), fields on the path only
+	uint32_t chrom, pos;
+	std::string_view ident;
+	double score;
+	int mapq, score_mapq, clip, clip_edit_dist;
+	uint8_t mate, rev, duplicate, unique, active, visited;
+	int pair;                 // index of the pair inside its barcode
+	const emab_aln_t *aln;
+	double gamma;
+	int cloud;                // index into Barcode::clouds
+	int selected_mate;        // record index or -1
+	int alt;                  // record index of the XA alternative or -1
+};
+
+struct Cloud { double exp_cov = 0, weight = 0; int parent = -1, child = -1, id = 0; bool bad = false; };
+
+struct Entry {  // SAMDictEnt (include/samdict.h:15-28)
+	int key;                       // record index
+	int mate = -1;                 // entry index
+	std::vector<int> cand_rec, cand_cloud;
+	std::vector<double> gamma;
+	bool visited = false;
+};
+
+struct KeyHash {
+	size_t operator()(const std::pair<std::string_view, int> &k) const { return std::hash<std::string_view>()(k.first) * 2 + k.second; }
+};
+
+static inline bool is_pair(const Rec &a, const Rec &b)
+{  // src/align.c:27-40
+	if (a.rev == b.rev || a.chrom != b.chrom) return false;
+	const Rec &r1 = b.rev ? b : a, &r2 = b.rev ? a : b;
+	const int64_t d = (int64_t)r1.pos - (int64_t)r2.pos;
+	return -35 <= d && d <= 750;
+}
+
+struct Barcode {
+	uint64_t bc = 0;
+	int first_pair = 0, n_pairs = 0;       // range in the bucket's (barcode-sorted) pair list
+	std::vector<Rec> recs;                 // after sort: (chrom&0xff, pos, ident) order
+	std::vector<Cloud> clouds;
+	std::vector<Entry> entries;            // insertion order; the reference walks them newest first
+	std::unordered_map<std::pair<std::string_view, int>, int, KeyHash> dict;
+	std::vector<int> final_;               // records_final
+	std::string sam;
+
+	int find(const Rec &k) const
+	{
+		auto it = dict.find({k.ident, (int)k.mate});
+		return it == dict.end() ? -1 : it->second;
+	}
+	int dict_add(int ri, int cloud, bool force, bool many_clouds);
+	void dict_del(int ri) { int e = find(recs[ri]); if (e >= 0) { entries[e].cand_rec.pop_back(); entries[e].cand_cloud.pop_back(); } }
+	void build_clouds(const Session *s, const std::vector<Pair> &pairs);
+	void choose(const Session *s);
+};
+
+// sam_dict_add (src/samdict.c:76-147)
+int Barcode::dict_add(int ri, int v, bool force, bool many_clouds)
+{
+	const Rec &k = recs[ri];
+	int ei = find(k);
+	if (ei >= 0) {
+		Entry &e = entries[ei];
+		const size_t n = e.cand_rec.size();
+		if (n < 5000) {  // MAX_CANDIDATES
+			if (n > 0) {
+				int parent = e.cand_cloud[n - 1];
+				if (parent == v && !force) return 1;
+				if (!many_clouds) {  // link the two clouds' sets (src/samdict.c:91-112)
+					int root1 = parent; while (clouds[root1].parent >= 0) root1 = clouds[root1].parent;
+					int root2 = v; while (clouds[root2].parent >= 0) root2 = clouds[root2].parent;
+					if (root1 != root2) {
+						int leaf = parent; while (clouds[leaf].child >= 0) leaf = clouds[leaf].child;
+						clouds[root2].parent = leaf;
+						clouds[leaf].child = root2;
+					}
+				}
+			}
+			e.cand_cloud.push_back(v);
+			e.cand_rec.push_back(ri);
+		}
+		return 0;
+	}
+	Entry e;
+	e.key = ri;
+	e.cand_rec.push_back(ri);
+	e.cand_cloud.push_back(v);
+	ei = (int)entries.size();
+	auto it = dict.find({k.ident, 1 - (int)k.mate});  // find_mate_for_key
+	if (it != dict.end()) { e.mate = it->second; entries[it->second].mate = ei; }
+	entries.push_back(std::move(e));
+	dict.emplace(std::make_pair(k.ident, (int)k.mate), ei);
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// -d: mark_optimal_alignments_in_cloud (src/split.c:38-338).  Uses libc rand() seeded from time()
+// exactly like the reference (one process-wide stream consumed in barcode order), so its output is
+// only reproducible against the reference when both run under the same pinned clock.
+// ---------------------------------------------------------------------------------------------
+static double log_density_prob(const Platform *tech, unsigned density)
+{  // src/split.c:15-35
+	const size_t size = tech->n_density_probs;
+	if (density < size) return log(tech->density_probs[density]);
+	return log(tech->density_probs[size - 1]) - (density - size + 1) * log(2.0);
+}
+
+static void mark_optimal(const Session *s, std::vector<Rec> &R, std::vector<int> recs)
+{
+	static int rand_init = 0;
+	if (!rand_init) { time_t t; srand((unsigned)time(&t)); rand_init = 1; }
+	const int BIN_SIZE = 1000, MAX_BINS = 1000, SCORE_SCALE = 20, MAX_NO_MOVE = 500, ITERS = 50000;
+	const size_t BUF_SIZE = 50000;
+	size_t n = recs.size();
+	if (n >= BUF_SIZE || n <= 5) return;
+	auto eq = [&](int a, int b) { return R[a].mate == R[b].mate && R[a].ident == R[b].ident; };
+	auto eq_mate = [&](int a, int b) { return R[a].mate != R[b].mate && R[a].ident == R[b].ident; };
+	std::vector<int> clean;
+	for (size_t i = 0; i < n;) {  // drop alignments too far from the read's lowest edit distance
+		size_t j = i + 1;
+		while (j < n && eq(recs[j], recs[i])) ++j;
+		const size_t m = j - i;
+		if (m > 1) {
+			size_t best = 0;
+			for (size_t k = 0; k < m; ++k) if (R[recs[i + k]].clip_edit_dist < R[recs[i + best]].clip_edit_dist) best = k;
+			const int cutoff = R[recs[i + best]].clip_edit_dist + 5;  // SPLIT_EXTRA_SEARCH_DEPTH
+			for (size_t k = 0; k < m; ++k) {
+				if (R[recs[i + k]].clip_edit_dist <= cutoff) clean.push_back(recs[i + k]);
+				else R[recs[i + k]].active = 0;
+			}
+		} else clean.push_back(recs[i]);
+		i = j;
+	}
+	recs.swap(clean);
+	n = recs.size();
+	struct MM { size_t idx; int n, mate_umap, mate_mmap, active; };
+	std::vector<size_t> umaps;
+	std::vector<MM> mmaps;
+	double log_config_prob = 0;
+	uint32_t lo = 0xffffffffu, hi = 0;
+	auto bounds = [&](int r) { if (R[r].pos < lo) lo = R[r].pos; if (R[r].pos > hi) hi = R[r].pos; };
+	for (size_t i = 0; i < n;) {
+		bounds(recs[i]);
+		size_t j = i + 1;
+		while (j < n && eq(recs[j], recs[i])) { bounds(recs[j]); ++j; }
+		const size_t m = j - i;
+		if (m > 1) {
+			size_t max_score = 0;
+			for (size_t k = 0; k < m; ++k) if (R[recs[i + k]].score > R[recs[i + max_score]].score) max_score = k;
+			int mate_umap = -1, mate_mmap = -1;
+			for (size_t k = 0; k < umaps.size(); ++k) if (eq_mate(recs[i], recs[umaps[k]])) { mate_umap = (int)k; break; }
+			if (mate_umap < 0)
+				for (size_t k = 0; k < mmaps.size(); ++k)
+					if (eq_mate(recs[i], recs[mmaps[k].idx])) { mate_mmap = (int)k; mmaps[k].mate_mmap = (int)mmaps.size(); break; }
+			mmaps.push_back({i, (int)m, mate_umap, mate_mmap, (int)max_score});
+			log_config_prob += R[recs[i + max_score]].score / SCORE_SCALE;
+		} else {
+			for (size_t k = 0; k < mmaps.size(); ++k) if (eq_mate(recs[i], recs[mmaps[k].idx])) { mmaps[k].mate_umap = (int)umaps.size(); break; }
+			umaps.push_back(i);
+			log_config_prob += R[recs[i]].score / SCORE_SCALE;
+		}
+		i = j;
+	}
+	const size_t n_bins = (hi - lo) / BIN_SIZE + 1;
+	if (n_bins >= (size_t)MAX_BINS || n <= 5 || mmaps.empty()) return;
+	std::vector<unsigned short> bins(MAX_BINS, 0);
+	auto bin_of = [&](uint32_t pos) { return (size_t)((pos - lo) / BIN_SIZE); };
+	for (size_t i = 0; i < n; ++i) R[recs[i]].active = 0;
+	for (size_t u : umaps) ++bins[bin_of(R[recs[u]].pos)];
+	for (const MM &m : mmaps) ++bins[bin_of(R[recs[m.idx + m.active]].pos)];
+	for (size_t i = 0; i < n_bins; ++i) log_config_prob += log_density_prob(s->tech, bins[i]);
+	int no_move = 0;
+	for (size_t k = 0; k < (size_t)ITERS; ++k) {  // simulated annealing (src/split.c:225-325)
+		const double t = pow(10.0, 0.0 - ((0.0 - (-12.0)) * k) / ITERS);
+		size_t r = rand() % mmaps.size();
+		size_t r_old = mmaps[r].active;
+		size_t r_new = rand() % (mmaps[r].n - 1);
+		if (r_new >= r_old) ++r_new;
+		const Rec *active_mate = nullptr;
+		size_t mate_r = 0;
+		int mate_is_mmap = 0;
+		if (mmaps[r].mate_umap >= 0) { mate_r = mmaps[r].mate_umap; active_mate = &R[recs[umaps[mate_r]]]; }
+		else if (mmaps[r].mate_mmap >= 0) { mate_r = mmaps[r].mate_mmap; active_mate = &R[recs[mmaps[mate_r].idx + mmaps[mate_r].active]]; mate_is_mmap = 1; }
+		const Rec &rec_old = R[recs[mmaps[r].idx + r_old]], &rec_new = R[recs[mmaps[r].idx + r_new]];
+		double density_change = 0.0, score_change = 0.0;
+		int force_move = 0, mate_new_active = -1;
+		size_t mate_old_bin = 0, mate_new_bin = 0;
+		const int old_paired = active_mate && is_pair(rec_old, *active_mate);
+		const int new_paired = active_mate && is_pair(rec_new, *active_mate);
+		if (!old_paired && new_paired) force_move = 1;
+		else if (old_paired && !new_paired && mate_is_mmap) {
+			for (int i = 0; i < mmaps[mate_r].n; ++i) {
+				const Rec &mate_new = R[recs[mmaps[mate_r].idx + i]];
+				if (is_pair(rec_new, mate_new)) {
+					mate_new_active = i;
+					mate_old_bin = bin_of(active_mate->pos);
+					mate_new_bin = bin_of(mate_new.pos);
+					score_change += (mate_new.score - active_mate->score) / SCORE_SCALE;
+					break;
+				}
+			}
+		}
+		const size_t old_bin = bin_of(rec_old.pos), new_bin = bin_of(rec_new.pos);
+		const int p1 = (mate_new_active >= 0 && old_bin == mate_old_bin) ? 2 : 1;
+		const int p2 = (mate_new_active >= 0 && new_bin == mate_new_bin) ? 2 : 1;
+		density_change += (log_density_prob(s->tech, bins[old_bin] - p1) - log_density_prob(s->tech, bins[old_bin])) +
+		                  (log_density_prob(s->tech, bins[new_bin] + p2) - log_density_prob(s->tech, bins[new_bin]));
+		if (p1 == 1 && mate_new_active >= 0) density_change += log_density_prob(s->tech, bins[mate_old_bin] - 1) - log_density_prob(s->tech, bins[mate_old_bin]);
+		if (p2 == 1 && mate_new_active >= 0) density_change += log_density_prob(s->tech, bins[mate_new_bin] + 1) - log_density_prob(s->tech, bins[mate_new_bin]);
+		score_change += (rec_new.score - rec_old.score) / SCORE_SCALE;
+		const double prob_change = density_change + score_change;
+		if (force_move || prob_change > 0 || exp(prob_change / t) >= ((double)rand()) / RAND_MAX) {
+			log_config_prob += prob_change;
+			mmaps[r].active = (int)r_new;
+			bins[old_bin] -= 1; bins[new_bin] += 1;
+			if (mate_new_active >= 0) { mmaps[mate_r].active = mate_new_active; bins[mate_old_bin] -= 1; bins[mate_new_bin] += 1; }
+		} else ++no_move;
+		if (no_move >= MAX_NO_MOVE) break;
+	}
+	for (size_t u : umaps) R[recs[u]].active = 1;
+	for (const MM &m : mmaps) R[recs[m.idx + m.active]].active = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// clouds (src/align.c:354-408)
+// ---------------------------------------------------------------------------------------------
+void Barcode::build_clouds(const Session *s, const std::vector<Pair> &pairs)
+{
+	(void)pairs;
+	// qsort(records, record_cmp): (bc, chrom & 0xff, pos, ident); glibc's merge sort is stable
+	std::stable_sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) {
+		const uint8_t ca = (uint8_t)a.chrom, cb = (uint8_t)b.chrom;
+		if (ca != cb) return ca < cb;
+		if (a.pos != b.pos) return a.pos < b.pos;
+		return a.ident.compare(b.ident) < 0;
+	});
+	const bool many = s->tech->many_clouds != 0;
+	const size_t n = recs.size();
+	dict.reserve(2 * (size_t)n_pairs + 8);
+	size_t i = 0;
+	while (i < n) {
+		const int c = (int)clouds.size();
+		clouds.emplace_back();
+		dict_add((int)i, c, false, many);
+		size_t r = i, cov = 1;
+		bool collision = false;
+		while (r + 1 < n && recs[r + 1].chrom == recs[r].chrom && recs[r + 1].pos - recs[r].pos <= s->tech->dist_thresh) {
+			++r;
+			if (!collision && dict_add((int)r, c, false, many)) {
+				collision = true;
+				for (size_t k = 0; k < cov; ++k) dict_del((int)(i + k));
+			}
+			++cov;
+		}
+		if (collision) {  // a read with two alignments in one cloud: the cloud is "bad"
+			clouds[c].bad = true;
+			std::vector<int> split(cov);
+			for (size_t k = 0; k < cov; ++k) split[k] = (int)(i + k);
+			std::stable_sort(split.begin(), split.end(), [&](int a, int b) {  // name_cmp (src/align.c:71-82)
+				int cmp = recs[a].ident.compare(recs[b].ident);
+				if (cmp != 0) return cmp < 0;
+				return recs[a].mate < recs[b].mate;
+			});
+			if (s->apply_opt) mark_optimal(s, recs, split);
+			for (size_t k = 0; k < cov; ++k) dict_add(split[k], c, true, many);
+		}
+		i = r + 1;
+	}
+}
+
+// find_best_record (src/samdict.c:166-243)
+static int find_best(Barcode &b, Entry &e)
+{
+	size_t best = 0;
+	double best_gamma = -1.0;
+	const size_t n = e.cand_rec.size();
+	for (size_t i = 0; i < n; ++i) {
+		if (!b.recs[e.cand_rec[i]].active) continue;
+		if (e.gamma[i] > best_gamma) { best = i; best_gamma = e.gamma[i]; }
+	}
+	Rec &chosen = b.recs[e.cand_rec[best]];
+	chosen.alt = -1;
+	chosen.gamma = best_gamma;
+	chosen.cloud = e.cand_cloud[best];
+	if (best_gamma <= 0.9) {  // SECONDARY_ALIGN_THRESH
+		size_t second = 0;
+		double second_gamma = -1.0;
+		for (size_t i = 0; i < n; ++i) {
+			if (!b.recs[e.cand_rec[i]].active) continue;
+			if (i != best && e.gamma[i] > second_gamma) { second = i; second_gamma = e.gamma[i]; }
+		}
+		if (second_gamma > 0) chosen.alt = e.cand_rec[second];
+	}
+	return e.cand_rec[best];
+}
+
+void Barcode::choose(const Session *s)
+{
+	final_.clear();
+	for (int ei = (int)entries.size() - 1; ei >= 0; --ei) {  // sd->head order
+		Entry &e = entries[ei];
+		if (e.visited) continue;
+		const int best = find_best(*this, e);
+		int best_mate = -1;
+		if (e.mate >= 0) best_mate = find_best(*this, entries[e.mate]);
+		final_.push_back(best);
+		recs[best].selected_mate = best_mate;
+		if (best_mate >= 0) { final_.push_back(best_mate); recs[best_mate].selected_mate = best; }
+		e.visited = true;
+		if (e.mate >= 0) { entries[e.mate].visited = true; entries[e.mate].mate = -1; }
+	}
+	if (!s->tech->many_clouds) {  // duplicates: dup_cmp (src/align.c:85-123), glibc qsort is stable
+		auto key = [&](int r, uint32_t k[6]) {
+			const Rec &x = recs[r];
+			k[0] = x.mate; k[1] = x.rev; k[2] = x.chrom; k[3] = x.pos;
+			k[4] = x.selected_mate >= 0 ? recs[x.selected_mate].chrom : 0xffffffffu;
+			k[5] = x.selected_mate >= 0 ? recs[x.selected_mate].pos : 0xffffffffu;
+		};
+		auto cmp = [&](int a, int b) {
+			uint32_t ka[6], kb[6];
+			key(a, ka); key(b, kb);
+			for (int i = 0; i < 6; ++i) if (ka[i] != kb[i]) return ka[i] < kb[i] ? -1 : 1;
+			return 0;
+		};
+		std::stable_sort(final_.begin(), final_.end(), [&](int a, int b) { return cmp(a, b) < 0; });
+		for (size_t i = 0; i < final_.size();) {
+			size_t j = i + 1;
+			while (j < final_.size() && cmp(final_[i], final_[j]) == 0) { recs[final_[j]].duplicate = 1; ++j; }
+			i = j;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// SAM text (src/samrecord.c:104-284)
+// ---------------------------------------------------------------------------------------------
+static inline int get_rlen(const emab_aln_t *a)
+{
+	int l = 0;
+	for (int k = 0; k < a->n_cigar; ++k) { int op = a->cigar[k] & 0xf; if (op == 0 || op == 2) l += a->cigar[k] >> 4; }
+	return l;
+}
+
+static inline void put_int(std::string *o, long long v)
+{
+	char buf[24];
+	int n = 0;
+	bool neg = v < 0;
+	unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
+	do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+	if (neg) o->push_back('-');
+	while (n) o->push_back(buf[--n]);
+}
+
+static inline void put_cigar(std::string *o, const emab_aln_t *a)
+{
+	for (int i = 0; i < a->n_cigar; ++i) { put_int(o, a->cigar[i] >> 4); o->push_back("MIDSS"[a->cigar[i] & 0xf]); }
+}
+
+static inline char rc(char c)
+{
+	switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; }
+}
+
+static void print_sam_record(const Session *s, const Barcode &b, const std::vector<Pair> &pairs, int ri, int mi, int cloud_base, std::string *o)
+{
+	const Rec *rec = ri >= 0 ? &b.recs[ri] : nullptr, *mate = mi >= 0 ? &b.recs[mi] : nullptr;
+	int flag = 1;
+	std::string_view ident, read, qual;
+	const char *chrom = "*";
+	uint32_t pos = 0;
+	int mapq = 0;
+	if (rec) {
+		const Pair &p = pairs[b.first_pair + rec->pair];
+		ident = rec->ident;
+		chrom = s->fai_names[rec->chrom].c_str();
+		pos = rec->pos;
+		read = p.read[rec->mate]; qual = p.qual[rec->mate];
+		const double gamma = rec->gamma;
+		const int gamma_mapq = (gamma <= 0.999999) ? (int)(-10 * log10(1 - gamma)) : 60;
+		mapq = std::min(gamma_mapq, rec->score_mapq);
+		mapq = std::min(mapq, rec->mapq);
+		mapq = std::max(mapq, 0);
+		mapq = std::min(mapq, 60);
+		if (rec->rev) flag |= 16;
+		if (rec->duplicate) flag |= 1024;
+		flag |= rec->mate == 0 ? 64 : 128;
+	} else {
+		const Pair &p = pairs[b.first_pair + mate->pair];
+		ident = mate->ident;
+		read = p.read[1 - mate->mate]; qual = p.qual[1 - mate->mate];
+		flag |= 4;
+		flag |= mate->mate == 0 ? 128 : 64;
+	}
+	if (mate) {
+		if (rec && is_pair(*rec, *mate)) flag |= 2;
+		if (mate->rev) flag |= 32;
+	} else flag |= 8;
+	o->append(ident); o->push_back('\t'); put_int(o, flag); o->push_back('\t'); o->append(chrom); o->push_back('\t');
+	put_int(o, pos); o->push_back('\t'); put_int(o, mapq); o->push_back('\t');
+	if (rec) put_cigar(o, rec->aln); else o->push_back('*');
+	if (mate) {
+		const bool same = rec && mate->chrom == rec->chrom;
+		o->push_back('\t');
+		if (same) o->push_back('='); else o->append(s->fai_names[mate->chrom]);
+		o->push_back('\t'); put_int(o, (int)mate->pos);
+		if (same) {
+			const emab_aln_t *r = rec->aln, *m = mate->aln;
+			const int64_t p0 = r->pos + (r->is_rev ? get_rlen(r) - 1 : 0), p1 = m->pos + (m->is_rev ? get_rlen(m) - 1 : 0);
+			o->push_back('\t');
+			if (m->n_cigar == 0 || r->n_cigar == 0) o->push_back('0');
+			else put_int(o, -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
+		} else o->append("\t0");
+	} else o->append("\t*\t0\t0");
+	o->push_back('\t');
+	if (rec && rec->rev) {
+		for (size_t i = read.size(); i-- > 0;) o->push_back(rc(read[i]));
+		o->push_back('\t');
+		for (size_t i = qual.size(); i-- > 0;) o->push_back(qual[i]);
+	} else { o->append(read); o->push_back('\t'); o->append(qual); }
+	std::string bc_str;
+	decode_bc(s, b.bc, &bc_str);
+	if (rec) {
+		char buf[64];
+		o->append("\tNM:i:"); put_int(o, rec->aln->NM);
+		o->append("\tBX:Z:"); o->append(bc_str);
+		if (!s->is_haplotag) { o->push_back('-'); o->append(s->bx_index); }
+		snprintf(buf, sizeof buf, "\tXG:f:%.5g", rec->gamma);
+		o->append(buf);
+		o->append("\tMI:i:"); put_int(o, cloud_base + rec->cloud);
+		o->append("\tXF:i:"); put_int(o, b.clouds[rec->cloud].bad ? 1 : 0);
+	} else {
+		o->append("\tBX:Z:"); o->append(bc_str);
+		if (!s->is_haplotag) o->append("-1");
+	}
+	if (s->has_rg) {
+		o->append("\tRG:Z:");
+		size_t p = s->rg.find("ID:");
+		for (size_t i = p + 3; i < s->rg.size() && !isspace((unsigned char)s->rg[i]); ++i) o->push_back(s->rg[i]);
+	}
+	if (rec && rec->alt >= 0) {
+		const Rec &a = b.recs[rec->alt];
+		o->append("\tXA:Z:"); o->append(s->fai_names[a.chrom]); o->push_back(','); o->push_back(a.rev ? '-' : '+'); put_int(o, (int)a.pos); o->push_back(',');
+		put_cigar(o, a.aln);
+		o->push_back(','); put_int(o, a.aln->NM); o->push_back(';');
+	}
+	o->push_back('\n');
+}
+
+// ---------------------------------------------------------------------------------------------
+// one batch of barcode-sorted pairs: device alignment, clouds, EM, choice, SAM
+// ---------------------------------------------------------------------------------------------
+static const uint8_t *nt4_table()
+{
+	static uint8_t t[256];
+	static bool init = false;
+	if (!init) {
+		memset(t, 4, sizeof t);
+		t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
+		init = true;
+	}
+	return t;
+}
+
+static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string *out)
+{
+	const double t0 = now_ms();
+	const size_t np = pairs.size();
+	emab_run_stats_t &st = s->last;
+	memset(&st, 0, sizeof st);
+	st.n_pairs = (int64_t)np;
+	if (np == 0) return EMAB_OK;
+	// ---- encode and align the whole batch on the device
+	const uint8_t *tab = nt4_table();
+	std::vector<int64_t> off(2 * np + 1, 0);
+	for (size_t i = 0; i < np; ++i) {
+		off[2 * i + 1] = off[2 * i] + (int64_t)pairs[i].read[0].size();
+		off[2 * i + 2] = off[2 * i + 1] + (int64_t)pairs[i].read[1].size();
+	}
+	std::vector<uint8_t> seq((size_t)off[2 * np] + 1);
+	#pragma omp parallel for num_threads(s->n_threads) schedule(static)
+	for (size_t i = 0; i < np; ++i)
+		for (int m = 0; m < 2; ++m) {
+			uint8_t *d = seq.data() + off[2 * i + m];
+			const std::string_view r = pairs[i].read[m];
+			for (size_t k = 0; k < r.size(); ++k) d[k] = tab[(uint8_t)r[k]];
+		}
+	std::vector<int32_t> n_regs(2 * np);
+	std::vector<emab_aln_t> alns;
+	int64_t n_alns = 0;
+	size_t cap = 4 * np + 1024;
+	emab_stats_t ds;
+	const double t1 = now_ms();
+	for (;;) {
+		alns.resize(cap);
+		int rc = emab_align_pairs(s->ctx, (int)np, seq.data(), off.data(), 3, n_regs.data(), alns.data(), (int64_t)cap, &n_alns, nullptr, &ds);
+		if (rc == EMAB_ERR_OVERFLOW && n_alns > (int64_t)cap) { cap = (size_t)n_alns + 1024; continue; }
+		if (rc) { s->err = emab_last_error(); return rc; }
+		break;
+	}
+	const double t2 = now_ms();
+	st.align_ms = t2 - t1; st.kernel_ms = ds.kernel_ms; st.launches = ds.launches;
+	st.extend_cells = ds.extend_cells; st.global_cells = ds.global_cells; st.local_cells = ds.local_cells; st.occ_touches = ds.occ_touches;
+	std::vector<int64_t> aoff(2 * np + 1, 0);
+	for (size_t i = 0; i < 2 * np; ++i) aoff[i + 1] = aoff[i] + n_regs[i];
+	// ---- barcode groups (consecutive pairs with one barcode)
+	std::vector<Barcode> bcs;
+	for (size_t i = 0; i < np;) {
+		size_t j = i + 1;
+		while (j < np && pairs[j].bc == pairs[i].bc) ++j;
+		bcs.emplace_back();
+		bcs.back().bc = pairs[i].bc; bcs.back().first_pair = (int)i; bcs.back().n_pairs = (int)(j - i);
+		i = j;
+	}
+	const int nb = (int)bcs.size();
+	st.n_barcodes = nb;
+	// ---- records + clouds per barcode
+	#pragma omp parallel for num_threads(s->n_threads) schedule(dynamic, 1)
+	for (int b = 0; b < nb; ++b) {
+		Barcode &B = bcs[b];
+		for (int pi = 0; pi < B.n_pairs; ++pi) {  // append_alignments' bookkeeping (src/align.c:1010-1060)
+			const size_t gp = (size_t)B.first_pair + pi;
+			for (int m = 0; m < 2; ++m) {
+				int added = 0;
+				for (int64_t k = aoff[2 * gp + m]; k < aoff[2 * gp + m + 1]; ++k) {
+					const emab_aln_t &a = alns[k];
+					if (!a.keep) continue;
+					Rec r;
+					r.chrom = (uint32_t)s->rid2chrom[a.rid]; r.pos = (uint32_t)(a.pos + 1);
+					r.ident = m == 0 ? pairs[gp].id1 : pairs[gp].id2;
+					r.score = a.em_score; r.mapq = a.mapq; r.score_mapq = a.score_mapq; r.clip = a.clip; r.clip_edit_dist = a.clip_edit_dist;
+					r.mate = (uint8_t)m; r.rev = (uint8_t)a.is_rev; r.duplicate = 0; r.unique = 0; r.active = 1; r.visited = 0;
+					r.pair = pi; r.aln = &a; r.gamma = 0; r.cloud = -1; r.selected_mate = -1; r.alt = -1;
+					B.recs.push_back(r);
+					++added;
+				}
+				if (added == 1) B.recs.back().unique = 1;
+			}
+		}
+		B.build_clouds(s, pairs);
+	}
+	const double t3 = now_ms();
+	// ---- flatten for the device EM
+	std::vector<int32_t> bc_entry_off(nb + 1, 0), bc_cloud_off(nb + 1, 0), bc_group_off(nb + 1, 0), bc_unit_off(nb + 1, 0), bc_full(nb, 0);
+	std::vector<int64_t> bc_cand_off(nb + 1, 0);
+	for (int b = 0; b < nb; ++b) {
+		const Barcode &B = bcs[b];
+		int64_t k = 0; int groups = 0, units = 0;
+		for (const Entry &e : B.entries) { k += (int64_t)e.cand_rec.size(); if (e.mate < 0 || e.mate < (int)(&e - B.entries.data())) ++units; }
+		for (const Cloud &c : B.clouds) if (c.parent < 0) ++groups;
+		bc_entry_off[b + 1] = bc_entry_off[b] + (int)B.entries.size();
+		bc_cloud_off[b + 1] = bc_cloud_off[b] + (int)B.clouds.size();
+		bc_group_off[b + 1] = bc_group_off[b] + groups;
+		bc_unit_off[b + 1] = bc_unit_off[b] + units;
+		bc_cand_off[b + 1] = bc_cand_off[b] + k;
+		bc_full[b] = B.n_pairs >= 30;
+	}
+	const int E = bc_entry_off[nb], C = bc_cloud_off[nb], G = bc_group_off[nb], U = bc_unit_off[nb];
+	const int64_t K = bc_cand_off[nb];
+	if (K > 0x7fffffff) { s->err = "too many candidates in one batch"; return EMAB_ERR_OVERFLOW; }
+	st.n_cands = K; st.n_clouds = C;
+	std::vector<int32_t> entry_cand_off(E + 1, 0), entry_mate(E), cand_cloud(K), cand_chrom(K), group_off(G + 1, 0), group_clouds(C),
+	    contrib_off(C + 1, 0), contrib(K), unit_first(U), unit_second(U);
+	std::vector<double> cand_score(K), gamma(K);
+	std::vector<uint32_t> cand_pos(K);
+	std::vector<uint8_t> cand_flags(K);
+	#pragma omp parallel for num_threads(s->n_threads) schedule(dynamic, 1)
+	for (int b = 0; b < nb; ++b) {
+		const Barcode &B = bcs[b];
+		const int ne = (int)B.entries.size(), e0 = bc_entry_off[b], c0 = bc_cloud_off[b];
+		// entries in the reference's walk order: newest first (sd->head, src/samdict.c:131-132)
+		auto pos_of = [&](int ei) { return e0 + (ne - 1 - ei); };
+		int64_t k = bc_cand_off[b];
+		std::vector<int> cnt(B.clouds.size() + 1, 0);
+		for (int ei = ne - 1; ei >= 0; --ei) {
+			const Entry &e = B.entries[ei];
+			const int p = pos_of(ei);
+			entry_cand_off[p] = (int32_t)k;   // start; the global array is made cumulative below
+			entry_mate[p] = e.mate >= 0 ? pos_of(e.mate) : -1;
+			for (size_t i = 0; i < e.cand_rec.size(); ++i, ++k) {
+				const Rec &r = B.recs[e.cand_rec[i]];
+				cand_score[k] = r.score; cand_cloud[k] = c0 + e.cand_cloud[i]; cand_chrom[k] = (int32_t)r.chrom; cand_pos[k] = r.pos;
+				cand_flags[k] = (uint8_t)((r.rev ? 1 : 0) | (r.active ? 2 : 0));
+				++cnt[e.cand_cloud[i] + 1];
+			}
+		}
+		// contributions of each cloud, in walk order
+		for (size_t c = 0; c < B.clouds.size(); ++c) cnt[c + 1] += cnt[c];
+		for (size_t c = 0; c < B.clouds.size(); ++c) contrib_off[c0 + c] = (int32_t)(bc_cand_off[b] + cnt[c]);
+		{
+			std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+			int64_t kk = bc_cand_off[b];
+			for (int ei = ne - 1; ei >= 0; --ei)
+				for (size_t i = 0; i < B.entries[ei].cand_rec.size(); ++i, ++kk)
+					contrib[bc_cand_off[b] + fill[B.entries[ei].cand_cloud[i]]++] = (int32_t)kk;
+		}
+		// linked cloud sets in chain order (src/align.c:125-143)
+		int g = bc_group_off[b], gc = c0;
+		for (size_t c = 0; c < B.clouds.size(); ++c) {
+			if (B.clouds[c].parent >= 0) continue;
+			group_off[g++] = gc;
+			for (int ch = (int)c; ch >= 0; ch = B.clouds[ch].child) group_clouds[gc++] = c0 + ch;
+		}
+		// mate pairs in walk order
+		int u = bc_unit_off[b];
+		std::vector<char> done(ne, 0);
+		for (int ei = ne - 1; ei >= 0; --ei) {
+			if (done[ei]) continue;
+			const Entry &e = B.entries[ei];
+			unit_first[u] = pos_of(ei);
+			unit_second[u] = e.mate >= 0 ? pos_of(e.mate) : -1;
+			done[ei] = 1;
+			if (e.mate >= 0) done[e.mate] = 1;
+			++u;
+		}
+	}
+	entry_cand_off[E] = (int32_t)K; contrib_off[C] = (int32_t)K; group_off[G] = C;
+	const double t4 = now_ms();
+	if (K > 0) {
+		emab_em_problem_t P;
+		memset(&P, 0, sizeof P);
+		P.n_bc = nb; P.n_entries = E; P.n_cands = (int32_t)K; P.n_clouds = C; P.n_groups = G; P.n_units = U; P.many_clouds = s->tech->many_clouds;
+		P.bc_entry_off = bc_entry_off.data(); P.bc_cloud_off = bc_cloud_off.data(); P.bc_group_off = bc_group_off.data(); P.bc_unit_off = bc_unit_off.data();
+		P.bc_full_em = bc_full.data(); P.entry_cand_off = entry_cand_off.data(); P.entry_mate = entry_mate.data();
+		P.cand_score = cand_score.data(); P.cand_cloud = cand_cloud.data(); P.cand_chrom = cand_chrom.data(); P.cand_pos = cand_pos.data(); P.cand_flags = cand_flags.data();
+		P.group_off = group_off.data(); P.group_clouds = group_clouds.data(); P.cloud_contrib_off = contrib_off.data(); P.cloud_contrib = contrib.data();
+		P.unit_first = unit_first.data(); P.unit_second = unit_second.data();
+		int rc = emab_em_batch(s->ctx, &P, gamma.data());
+		if (rc) { s->err = emab_last_error(); return rc; }
+		st.em_kernel_ms = emab_last_kernel_ms(s->ctx);
+		st.launches += 1;
+	}
+	const double t5 = now_ms();
+	// ---- choose, mark duplicates, print; cloud ids continue the session-wide counter in barcode order
+	std::vector<int> cloud_base(nb + 1, s->cloud_id);
+	for (int b = 0; b < nb; ++b) cloud_base[b + 1] = cloud_base[b] + (int)bcs[b].clouds.size();
+	s->cloud_id = cloud_base[nb];
+	#pragma omp parallel for num_threads(s->n_threads) schedule(dynamic, 1)
+	for (int b = 0; b < nb; ++b) {
+		Barcode &B = bcs[b];
+		const int ne = (int)B.entries.size(), e0 = bc_entry_off[b];
+		for (int ei = 0; ei < ne; ++ei) {
+			Entry &e = B.entries[ei];
+			const int p = e0 + (ne - 1 - ei);
+			e.gamma.assign(gamma.begin() + entry_cand_off[p], gamma.begin() + entry_cand_off[p] + (int64_t)e.cand_rec.size());
+		}
+		B.choose(s);
+		B.sam.reserve(B.final_.size() * 520);
+		for (int ri : B.final_) {
+			Rec &best = B.recs[ri];
+			if (best.visited) continue;
+			const int mi = best.selected_mate;
+			if (mi >= 0) B.recs[mi].visited = 1;
+			print_sam_record(s, B, pairs, ri, mi, cloud_base[b], &B.sam);
+			print_sam_record(s, B, pairs, mi, ri, cloud_base[b], &B.sam);
+		}
+	}
+	size_t total = 0;
+	for (const Barcode &B : bcs) total += B.sam.size();
+	out->reserve(out->size() + total);
+	for (const Barcode &B : bcs) out->append(B.sam);
+	const double t6 = now_ms();
+	st.encode_ms = t1 - t0; st.cloud_ms = t3 - t2; st.flatten_ms = t4 - t3; st.em_ms = t5 - t4; st.format_ms = t6 - t5; st.total_ms = t6 - t0;
+	st.sam_bytes = (int64_t)total;
+	return EMAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// inputs
+// ---------------------------------------------------------------------------------------------
+static inline std::string_view token(const char *&p, const char *end)
+{  // copy_until_space (src/util.c:11-20): up to the next whitespace, then skip one character
+	const char *b = p;
+	while (p < end && !isspace((unsigned char)*p)) ++p;
+	std::string_view t(b, (size_t)(p - b));
+	if (p < end) ++p;
+	return t;
+}
+
+// read_special_fastq (src/align.c:759-806): one pair per line "BC @id read1 qual1 read2 qual2",
+// lines stably sorted by their first BC_LEN characters.
+int align_special_fastq(Session *s, const char *data, size_t len, std::string *out)
+{
+	const double t0 = now_ms();
+	std::vector<std::string_view> lines;
+	{
+		const char *p = data, *end = data + len;
+		while (p < end) {
+			const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+			const char *e = nl ? nl : end;
+			lines.emplace_back(p, (size_t)(e - p));   // an empty line is a record with empty fields in the reference; rejected below
+			p = nl ? nl + 1 : end;
+		}
+	}
+	const size_t bl = (size_t)s->bc_len;
+	std::stable_sort(lines.begin(), lines.end(), [bl](std::string_view a, std::string_view b) {
+		// strncmp over at most BC_LEN characters; a line end compares as NUL/newline would
+		const size_t n = std::min(bl, std::min(a.size(), b.size()));
+		int c = memcmp(a.data(), b.data(), n);
+		if (c != 0) return c < 0;
+		if (n == bl) return false;
+		return a.size() < b.size();
+	});
+	std::vector<Pair> pairs(lines.size());
+	for (size_t i = 0; i < lines.size(); ++i) {
+		const char *p = lines[i].data(), *end = p + lines[i].size();
+		std::string_view bc = token(p, end);
+		Pair &P = pairs[i];
+		if (!encode_bc(s, bc.data(), bc.size(), &P.bc)) { s->err = "error: malformed barcode in input line " + std::to_string(i + 1); return EMAB_ERR_ARG; }
+		std::string_view id = token(p, end);
+		if (!id.empty()) id.remove_prefix(1);  // skip the '@' (src/align.c:927)
+		P.id1 = P.id2 = id;
+		P.read[0] = token(p, end); P.qual[0] = token(p, end); P.read[1] = token(p, end); P.qual[1] = token(p, end);
+		if (P.read[0].size() > 200 || P.read[1].size() > 200) { s->err = "error: read longer than MAX_READ_LEN (200)"; return EMAB_ERR_ARG; }
+	}
+	const double t1 = now_ms();
+	int rc = process_pairs(s, pairs, out);
+	s->last.parse_ms = t1 - t0;
+	s->last.total_ms += t1 - t0;
+	return rc;
+}
+
+// ---- standard FASTQ (src/align.c:632-744, src/techs.c:5-69) -----------------------------------------
+struct FqRec { std::string_view id, read, qual; uint64_t bc; };
+
+static bool next_fastq(const Session *s, const char *&p, const char *end, FqRec *r, std::string *err)
+{
+	if (p >= end) return false;
+	auto line = [&](std::string_view *o) {
+		const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+		const char *e = nl ? nl : end;
+		*o = std::string_view(p, (size_t)(e - p));
+		p = nl ? nl + 1 : end;
+	};
+	std::string_view id, sep;
+	line(&id); line(&r->read); line(&sep); line(&r->qual);
+	// extract_bc_* edit the id in place; here the id is narrowed instead
+	std::string_view bcs;
+	switch (s->tech->kind) {
+	case BC_TRUSEQ: {  // atoi after the optional '@' (src/techs.c:57-61)
+		const char *q = id.data() + (id.size() && id[0] == '@' ? 1 : 0);
+		r->bc = (uint64_t)(int64_t)atoi(std::string(q, (size_t)(id.data() + id.size() - q)).c_str());
+		break;
+	}
+	case BC_CPTSEQ: {
+		size_t c = id.rfind(':');
+		if (c == std::string_view::npos) { *err = "error: no ':' in FASTQ id"; return false; }
+		r->bc = (uint64_t)(int64_t)atoi(std::string(id.substr(std::min(id.size(), c + 3))).c_str());
+		id = id.substr(0, c);
+		break;
+	}
+	case BC_TELLSEQ: {
+		size_t sp = id.find(' ');
+		if (sp != std::string_view::npos && id.compare(sp, 6, " BX:Z:") == 0) {
+			size_t c = id.rfind(':');
+			bcs = id.substr(c + 1);
+			id = id.substr(0, sp);
+		} else {
+			if (sp != std::string_view::npos) id = id.substr(0, sp);
+			size_t c = id.rfind(':');
+			if (c == std::string_view::npos) { *err = "error: no ':' in FASTQ id"; return false; }
+			bcs = id.substr(c + 1);
+			id = id.substr(0, c);
+		}
+		if (!encode_bc(s, bcs.data(), bcs.size(), &r->bc)) { *err = "error: malformed barcode in FASTQ id"; return false; }
+		break;
+	}
+	default: {  // haplotag / 10x / dbs: text after the last ':', id cut at it and at the first space
+		size_t c = id.rfind(':');
+		if (c == std::string_view::npos) { *err = "error: no ':' in FASTQ id"; return false; }
+		bcs = id.substr(c + 1);
+		id = id.substr(0, c);
+		size_t sp = id.find(' ');
+		if (sp != std::string_view::npos) id = id.substr(0, sp);
+		if (!encode_bc(s, bcs.data(), bcs.size(), &r->bc)) { *err = "error: malformed barcode in FASTQ id"; return false; }
+	}
+	}
+	if (!id.empty()) id.remove_prefix(1);
+	r->id = id;
+	return true;
+}
+
+int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2, std::string *out)
+{
+	const double t0 = now_ms();
+	std::vector<Pair> pairs;
+	const char *p1 = d1, *e1 = d1 + l1, *p2 = d2, *e2 = d2 ? d2 + l2 : nullptr;
+	FqRec a, b;
+	std::string err;
+	for (;;) {
+		if (!next_fastq(s, p1, e1, &a, &err)) break;
+		bool ok = d2 ? next_fastq(s, p2, e2, &b, &err) : next_fastq(s, p1, e1, &b, &err);
+		if (!ok) { s->err = err.empty() ? "error: unpaired FASTQ record" : err; return EMAB_ERR_ARG; }
+		if (a.bc != b.bc) { s->err = "error: mates carry different barcodes"; return EMAB_ERR_ARG; }
+		if (a.read.size() > 200 || b.read.size() > 200) { s->err = "error: read longer than MAX_READ_LEN (200)"; return EMAB_ERR_ARG; }
+		Pair P;
+		P.bc = a.bc; P.id1 = a.id; P.id2 = b.id;
+		P.read[0] = a.read; P.qual[0] = a.qual; P.read[1] = b.read; P.qual[1] = b.qual;
+		pairs.push_back(P);
+	}
+	if (!err.empty()) { s->err = err; return EMAB_ERR_ARG; }
+	const double t1 = now_ms();
+	int rc = process_pairs(s, pairs, out);
+	s->last.parse_ms = t1 - t0;
+	s->last.total_ms += t1 - t0;
+	return rc;
+}
+
+}  // namespace emab

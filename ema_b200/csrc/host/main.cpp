@@ -1,0 +1,143 @@
+// ema-b200: the `ema align` command line (src/main.c:243-425) over libema_b200.so.
+// Same option grammar (getopt "r:1:2:s:xo:R:dp:i:t:"), same messages, same SAM bytes; `count` and
+// `preproc` are out of scope and are reported as such.
+#include <getopt.h>
+#include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../../include/ema_b200.h"
+
+static char *escape(char *s)
+{  // src/util.c:22-39
+	char *p, *q;
+	for (p = q = s; *p; ++p) {
+		if (*p == '\\') {
+			++p;
+			if (*p == 't') *q++ = '\t';
+			else if (*p == 'n') *q++ = '\n';
+			else if (*p == 'r') *q++ = '\r';
+			else if (*p == '\\') *q++ = '\\';
+		} else *q++ = *p;
+	}
+	*q = '\0';
+	return s;
+}
+
+static bool slurp(const char *path, std::string *out)
+{
+	FILE *f = fopen(path, "r");
+	if (!f) return false;
+	char buf[1 << 16];
+	size_t n;
+	while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->append(buf, n);
+	fclose(f);
+	return true;
+}
+
+static void usage(const char *argv0, int error)
+{
+	FILE *out = error ? stderr : stdout;
+	fprintf(out, "usage: %s <align|help> [options]\n\n", argv0);
+	fprintf(out, "align: choose best alignments based on barcodes\n");
+	fprintf(out, "  -1 <FASTQ1 path>: first (preprocessed and sorted) FASTQ file [none]\n");
+	fprintf(out, "  -2 <FASTQ2 path>: second (preprocessed and sorted) FASTQ file [none]\n");
+	fprintf(out, "  -s <EMA-FASTQ path>: specify special FASTQ path [none]\n");
+	fprintf(out, "  -x: multi-input mode; takes input files after flags [off]\n");
+	fprintf(out, "  -r <FASTA path>: indexed reference [required]\n");
+	fprintf(out, "  -o <SAM file>: output SAM file [stdout]\n");
+	fprintf(out, "  -R <RG string>: full read group string (e.g. '@RG\\tID:foo\\tSM:bar') [none]\n");
+	fprintf(out, "  -d: apply fragment read density optimization [off]\n");
+	fprintf(out, "  -p <platform>: sequencing platform (one of '10x', 'tru', 'haplotag', 'dbs', 'cpt', 'tellseq') [10x]\n");
+	fprintf(out, "  -i <index>: index to follow 'BX' tag in SAM output [1]\n");
+	fprintf(out, "  -t <threads>: set number of host threads [1]\n");
+	fprintf(out, "  all other arguments (only for -x): list of all preprocessed inputs\n\n");
+	fprintf(out, "count / preproc: not part of this build (use the reference's `ema preproc` to make buckets)\n");
+	exit(error ? EXIT_FAILURE : EXIT_SUCCESS);
+}
+
+#define IOERROR(fn) do { fprintf(stderr, "error: file %s could not be opened\n", (fn)); exit(EXIT_FAILURE); } while (0)
+
+int main(int argc, char *argv[])
+{
+	const char *argv0 = argv[0];
+	if (argc < 2) {
+		fprintf(stderr, "EMA version 0.6.2 (ema-b200)\nnote: use '%s help' for usage information.\n", argv0);
+		return EXIT_SUCCESS;
+	}
+	const char *mode = argv[1];
+	if (strcmp(mode, "help") == 0) usage(argv0, 0);
+	if (strcmp(mode, "align") != 0) {
+		fprintf(stderr, "error: unrecognized mode\n");
+		usage(argv0, 1);
+	}
+	char *ref = NULL, *fq1 = NULL, *fq2 = NULL, *fqx = NULL, *out = NULL, *rg = NULL, *bx = NULL;
+	const char *platform = "10x";
+	int apply_opt = 0, multi = 0, t = 1, device = 0;
+	int c;
+	if (const char *d = getenv("EMAB_DEVICE")) device = atoi(d);
+	while ((c = getopt(argc - 1, &argv[1], "r:1:2:s:xo:R:dp:i:t:")) != -1) {
+		switch (c) {
+		case 'r': ref = strdup(optarg); break;
+		case '1': fq1 = strdup(optarg); break;
+		case '2': fq2 = strdup(optarg); break;
+		case 's': fqx = strdup(optarg); break;
+		case 'x': multi = 1; break;
+		case 'o': out = strdup(optarg); break;
+		case 'R': rg = escape(strdup(optarg)); break;
+		case 'd': apply_opt = 1; break;
+		case 'p': platform = strdup(optarg); break;
+		case 'i': bx = strdup(optarg); break;
+		case 't': t = atoi(optarg); break;
+		default: usage(argv0, 1);
+		}
+	}
+	if (multi + (fqx != NULL) + (fq1 != NULL || fq2 != NULL) != 1) {
+		fprintf(stderr, "error: must specify *exactly one* of -1/-2, -s or -x\n");
+		exit(EXIT_FAILURE);
+	}
+	if (fq1 == NULL && fq2 != NULL) { fprintf(stderr, "error: cannot specify -2 without -1\n"); exit(EXIT_FAILURE); }
+	if (ref == NULL) { fprintf(stderr, "error: specify reference FASTA with -r\n"); exit(EXIT_FAILURE); }
+	FILE *out_file = out == NULL ? stdout : fopen(out, "w");
+	if (!out_file) IOERROR(out);
+	fprintf(stderr, "BWA initialization...\n");
+	emab_session_t *s = NULL;
+	if (emab_session_open(ref, platform, device, &s)) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
+	if (emab_session_config(s, rg, bx, apply_opt, t)) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
+	char *text = NULL;
+	uint64_t len = 0;
+	emab_sam_header(s, argc, argv, &text, &len);
+	fwrite(text, 1, len, out_file);
+	emab_free(text);
+	auto emit = [&](int rc) {
+		if (rc) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
+		fwrite(text, 1, len, out_file);
+		emab_free(text);
+	};
+	if (multi) {
+		const int n_inputs = argc - optind - 1;
+		if (n_inputs == 0) { fprintf(stderr, "warning: no input files specified; nothing to do\n"); exit(EXIT_SUCCESS); }
+		for (int i = optind + 1; i < argc; ++i) {  // buckets are processed in argument order
+			std::string data;
+			if (!slurp(argv[i], &data)) IOERROR(argv[i]);
+			fprintf(stderr, "Processing reads...\n");
+			emit(emab_align_bucket(s, data.data(), data.size(), &text, &len));
+		}
+	} else if (fqx) {
+		std::string data;
+		if (!slurp(fqx, &data)) IOERROR(fqx);
+		fprintf(stderr, "Processing reads...\n");
+		emit(emab_align_bucket(s, data.data(), data.size(), &text, &len));
+	} else {
+		std::string d1, d2;
+		if (!slurp(fq1, &d1)) IOERROR(fq1);
+		if (fq2 && !slurp(fq2, &d2)) IOERROR(fq2);
+		fprintf(stderr, "Processing reads...\n");
+		emit(emab_align_fastq(s, d1.data(), d1.size(), fq2 ? d2.data() : NULL, d2.size(), &text, &len));
+	}
+	if (out_file != stdout) fclose(out_file);
+	emab_session_close(s);
+	return EXIT_SUCCESS;
+}

@@ -128,6 +128,65 @@ int emab_align_pairs(emab_ctx_t *ctx, int n_pairs, const uint8_t *seq, const int
                      int32_t *n_regs, emab_aln_t *alns, int64_t aln_cap, int64_t *n_alns, int64_t *regs_dbg,
                      emab_stats_t *stats);
 
+/* ---- the barcode-cloud EM (src/align.c:410-543) ------------------------------------------------
+ * The host groups candidates into clouds and links mates (the SAMDict bookkeeping of
+ * src/samdict.c, src/align.c:354-408) and flattens every barcode of a bucket into the arrays
+ * below; the device runs the initialisation and the 5 EM sweeps and returns the posteriors
+ * gamma[n_cands] (double).  Lists are in the reference's iteration order (sd->head order for
+ * entries, chain order for linked cloud sets) so the floating-point summation order is the
+ * reference's.  Indices are global across the batch. */
+typedef struct {
+	int32_t n_bc, n_entries, n_cands, n_clouds, n_groups, n_units, many_clouds, pad;
+	const int32_t *bc_entry_off, *bc_cloud_off, *bc_group_off, *bc_unit_off; /* [n_bc+1] */
+	const int32_t *bc_full_em;       /* [n_bc] 1 if the barcode has >= 30 pairs (src/align.c:345) */
+	const int32_t *entry_cand_off;   /* [n_entries+1] */
+	const int32_t *entry_mate;       /* [n_entries] entry index of the mate, or -1 */
+	const double *cand_score;        /* [n_cands] EM log-likelihood score */
+	const int32_t *cand_cloud;       /* [n_cands] */
+	const int32_t *cand_chrom;       /* [n_cands] */
+	const uint32_t *cand_pos;        /* [n_cands] 1-based position */
+	const uint8_t *cand_flags;       /* [n_cands] bit0 = reverse strand, bit1 = active */
+	const int32_t *group_off;        /* [n_groups+1] */
+	const int32_t *group_clouds;     /* [n_clouds] clouds of each linked set, chain order */
+	const int32_t *cloud_contrib_off;/* [n_clouds+1] */
+	const int32_t *cloud_contrib;    /* [n_cands] candidates of each cloud in entry-list order */
+	const int32_t *unit_first, *unit_second; /* [n_units] the entries of a mate pair in list order (second = -1 if single) */
+} emab_em_problem_t;
+
+int emab_em_batch(emab_ctx_t *ctx, const emab_em_problem_t *problem, double *gamma_out);
+
+/* ---- the operator the reference's main() calls: find_clouds_and_align --------------------------
+ * (include/align.h:10-21; src/align.c:180-212,214-630).  A session replaces the reference's
+ * process globals (ref, opts, tech, chroms, rg, bx_index: src/align.c:177-178, src/main.c:23-34):
+ *   emab_session_open    = read_fai("<ref>.fai") + bwa_init(ref) + platform profile (-p)
+ *   emab_session_config  = -R / -i / -d / -t
+ *   emab_sam_header      = write_sam_header (argv is echoed into @PG as the reference does)
+ *   emab_align_bucket    = find_clouds_and_align(NULL, NULL, fqx, ...) on the CONTENTS of one
+ *                          preprocessed bucket file ("special FASTQ", -s / -x inputs)
+ *   emab_align_fastq     = find_clouds_and_align(fq1, fq2, NULL, ...) on the contents of
+ *                          barcode-sorted FASTQ(s); d2 == NULL means interleaved (-1 only)
+ * SAM text is returned in a malloc'ed buffer the caller releases with emab_free().  Output is in
+ * barcode order — byte-identical to the reference run with -t 1 (MI cloud ids included; they
+ * continue across calls on one session like the reference's process-wide counter). */
+typedef struct emab_session emab_session_t;
+
+typedef struct {
+	double parse_ms, encode_ms, align_ms, kernel_ms, cloud_ms, flatten_ms, em_ms, em_kernel_ms, format_ms, total_ms;
+	int64_t n_pairs, n_barcodes, n_cands, n_clouds, sam_bytes;
+	int64_t extend_cells, global_cells, local_cells, occ_touches;
+	int32_t launches, pad;
+} emab_run_stats_t;
+
+int emab_session_open(const char *ref_path, const char *platform, int device, emab_session_t **out);
+void emab_session_close(emab_session_t *s);
+int emab_session_config(emab_session_t *s, const char *rg, const char *bx_index, int apply_opt, int n_threads);
+int emab_sam_header(emab_session_t *s, int argc, const char *const *argv, char **text, uint64_t *len);
+int emab_align_bucket(emab_session_t *s, const char *data, uint64_t len, char **sam, uint64_t *sam_len);
+int emab_align_fastq(emab_session_t *s, const char *d1, uint64_t l1, const char *d2, uint64_t l2, char **sam, uint64_t *sam_len);
+int emab_session_stats(const emab_session_t *s, emab_run_stats_t *out);
+emab_ctx_t *emab_session_ctx(emab_session_t *s);
+void emab_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,111 @@
+"""GPU parity tests (-m gpu) of the whole `ema align` path: SAM bytes.  The body must be
+byte-identical to the reference's `ema align ... -t 1`; the header is compared minus @PG, which
+echoes argv (src/align.c:208-211)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+CLI = os.path.join(helpers.ROOT, "ema_b200", "ema-b200")
+
+
+def split_sam(text: bytes):
+    lines = text.split(b"\n")
+    head = [l for l in lines if l.startswith(b"@") and not l.startswith(b"@PG")]
+    body = [l for l in lines if l and not l.startswith(b"@")]
+    return head, body
+
+
+def diff_msg(a, b):
+    for i, (x, y) in enumerate(zip(a, b)):
+        if x != y:
+            return f"first difference at record {i}:\n ours: {x[:300]!r}\n ref:  {y[:300]!r}"
+    return f"record counts differ: {len(a)} vs {len(b)}"
+
+
+def test_cli_golden_tiny(tmp_path):
+    out = tmp_path / "out.sam"
+    subprocess.run([CLI, "align", "-s", os.path.join(G, "tiny_rep", "ema-bin-000.10x"), "-r", os.path.join(G, "tiny_rep", "ref.fa"),
+                    "-p", "10x", "-t", "4", "-o", str(out)], check=True)
+    h1, b1 = split_sam(out.read_bytes())
+    h2, b2 = split_sam(open(os.path.join(G, "tiny_rep", "ref.sam"), "rb").read())
+    assert h1 == h2
+    assert b1 == b2, diff_msg(b1, b2)
+
+
+def test_cli_errors(tmp_path):
+    r = subprocess.run([CLI, "align", "-r", "x.fa"], capture_output=True, text=True)
+    assert r.returncode != 0 and "exactly one" in r.stderr
+    r = subprocess.run([CLI, "align", "-s", "nope", "-r", os.path.join(G, "tiny_rep", "ref.fa"), "-p", "bogus"], capture_output=True, text=True)
+    assert r.returncode != 0 and "invalid platform name" in r.stderr
+    r = subprocess.run([CLI, "align", "-s", "nope", "-r", "/nonexistent.fa"], capture_output=True, text=True)
+    assert r.returncode != 0 and "could not be opened" in r.stderr
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c1_rep"])
+def test_session_vs_reference_c1(cfg, tmp_path):
+    """BASELINE config 1 (10k pairs, 200 barcodes, 5 Mbp) and its repeat/indel variant against the
+    reference binary run on the same files."""
+    if not os.path.exists(helpers.ref_bin("ema")):
+        pytest.skip("oracle/_ref/ema missing")
+    import ema_b200
+    from tools import synth
+    p = synth.build_config(cfg, helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    ref_sam = tmp_path / "ref.sam"
+    subprocess.run([helpers.ref_bin("ema"), "align", "-s", p["bucket"], "-r", p["fasta"], "-p", "10x", "-t", "1", "-o", str(ref_sam)],
+                   check=True, stderr=subprocess.DEVNULL)
+    s = ema_b200.Session(p["fasta"], "10x", threads=8)
+    body = s.align_bucket(open(p["bucket"], "rb").read())
+    _, b1 = split_sam(body)
+    h2, b2 = split_sam(ref_sam.read_bytes())
+    assert b1 == b2, diff_msg(b1, b2)
+    h1, _ = split_sam(s.header(["ema", "align"]))
+    assert h1 == h2
+    st = s.stats
+    assert st.n_pairs == p["n_pairs"] and st.launches >= 8
+
+
+def test_em_posteriors_vs_reference(tmp_path):
+    """EM posteriors at full precision (the SAM only carries %.5g): within 1e-6 relative of the
+    reference's, with identical chosen alignments (north_star tolerance)."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref missing")
+    import ctypes as C
+    import ema_b200
+    from tools import synth
+    p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    R = helpers.ref()
+    R.ref_ema_init.argtypes = [C.c_char_p, C.c_char_p]
+    assert R.ref_ema_init(p["fasta"].encode(), b"10x") == 0
+    dump = tmp_path / "gamma.tsv"
+    R.ref_ema_run_bucket.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    assert R.ref_ema_run_bucket(p["bucket"].encode(), str(tmp_path / "r.sam").encode(), str(dump).encode(), 0, 1) == 0
+    want = {}
+    for ln in open(dump):
+        f = ln.rstrip("\n").split("\t")
+        chosen = f[-1].split(":")
+        want[(f[0], int(f[1]))] = (int(chosen[0]), int(chosen[1]), float(chosen[2]))
+    s = ema_b200.Session(p["fasta"], "10x", threads=8)
+    body = s.align_bucket(open(p["bucket"], "rb").read())
+    fai = [l.split("\t")[0] for l in open(p["fasta"] + ".fai")]
+    n = 0
+    worst = 0.0
+    for ln in body.decode().split("\n"):
+        if not ln:
+            continue
+        f = ln.split("\t")
+        flag = int(f[1])
+        if flag & 4:
+            continue
+        key = (f[0], 0 if flag & 64 else 1)
+        chrom, pos, gamma = want[key]
+        assert fai[chrom] == f[2] and pos == int(f[3]), key
+        xg = float([t for t in f if t.startswith("XG:f:")][0][5:])
+        assert abs(xg - gamma) <= 1e-6 * max(abs(gamma), 1e-300) + 5e-6 * gamma, (key, xg, gamma)  # %.5g rounding
+        n += 1
+    assert n > 15000
