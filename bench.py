@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — `ema align` hot path on B200: read pairs/sec (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+One "step" = one barcode bucket (one device batch) of synthetic 2x150-class linked reads through
+the whole path: bucket text -> barcode batcher -> FM-index SMEM seeding -> chaining -> banded SW
+extension -> mate rescue -> CIGARs -> barcode-cloud EM -> SAM text.  The default workload is
+BASELINE.json configs[1]: a synthetic 100 Mbp reference (10 x 10 Mbp with planted duplications),
+1 M read pairs across 5 000 barcodes split into 25 buckets of 40 000 pairs (200 barcodes x 200 pairs),
+-p 10x.  Reported on one JSON line:
+
+  value    pairs/s with the bucket's inputs already resident in HBM (device time of the kernel
+           sequence, CUDA events on the library's stream, max over ranks)
+  e2e      pairs/s through the reference-facing C ABI (emab_align_bucket) from HOST bucket text to
+           HOST SAM text: parse, H2D, kernels, D2H, cloud building, EM, SAM formatting all inside
+  roofline the dominant kernel (SMEM seeding): algorithmic bytes = 64 B x Occ-block touches
+            / its CUDA-event time, against the measured HBM copy bandwidth
+  cpu_baseline   the unmodified reference (`oracle/_ref/ema align -t <cores>`) on one bucket of the
+           same workload on this box's host cores (rank 0, N=1 only)
+
+--impl reference times that reference binary alone, one bucket per step, all host threads.
+Multi-GPU (torchrun, one rank per GPU): buckets are independent, so ranks take disjoint buckets with
+no data-path collective ("scaling": "weak"); the only communication is the timing barrier.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tools import synth  # noqa: E402
+
+REF_EMA = os.path.join(ROOT, "oracle", "_ref", "ema")
+REF_BWA = os.path.join(ROOT, "oracle", "_ref", "bwa")
+
+WORKLOADS = {
+    # name: (synth reference config, n_buckets, barcodes per bucket, pairs per barcode, description)
+    "c2": ("c2", 25, 200, 200, "synthetic 100 Mbp reference (10x10 Mbp, planted duplications), 1M read pairs across 5k barcodes, -p 10x"),
+    "c1_rep": ("c1_rep", 4, 200, 50, "synthetic 5 Mbp reference with planted duplications, 10k-pair buckets of 200 barcodes, -p 10x"),
+    "c1": ("c1", 4, 200, 50, "synthetic 5 Mbp iid reference, 10k-pair buckets of 200 barcodes, -p 10x"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def prepare(workload, data_root, need_buckets):
+    """Reference FASTA + bwa index + bucket files, cached under data_root (shared by both arms)."""
+    cfg, n_buckets, nbc, ppb, _ = WORKLOADS[workload]
+    n_contigs, clen, rseed, dup, _, _, indel = synth.CONFIGS[cfg]
+    d = os.path.join(data_root, "bench_" + workload)
+    os.makedirs(d, exist_ok=True)
+    fa = os.path.join(d, "ref.fa")
+    contigs = None
+    t0 = time.time()
+    if not os.path.exists(fa + ".fai"):
+        contigs = synth.make_reference(n_contigs, clen, rseed, dup)
+        synth.write_fasta(fa, contigs)
+    if not os.path.exists(fa + ".sa"):
+        if not os.path.exists(REF_BWA):
+            raise SystemExit("oracle/_ref/bwa is missing: the FM index is built with the reference's own `bwa index`")
+        log(f"[bench] bwa index {fa} ...")
+        subprocess.run([REF_BWA, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    buckets = []
+    for b in range(min(need_buckets, n_buckets)):
+        path = os.path.join(d, f"ema-bin-{b:03d}")
+        if not os.path.exists(path):
+            if contigs is None:
+                contigs = synth.make_reference(n_contigs, clen, rseed, dup)
+            sim = synth.simulate_pairs(contigs, nbc, ppb, rseed + 1000 + b, indel=indel)
+            synth.write_bucket(path + ".tmp", sim)
+            os.replace(path + ".tmp", path)
+        buckets.append(path)
+    log(f"[bench] data ready in {time.time() - t0:.1f}s: {fa}, {len(buckets)} buckets of {nbc * ppb} pairs")
+    return fa, buckets, nbc * ppb
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = False
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop = True
+        if self._t:
+            self._t.join(timeout=6)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def time_reference(fa, bucket, threads):
+    """Wall time of the unmodified reference on one bucket (includes its index load, as in the
+    README's one-process-per-bucket workflow).  Returns (seconds, index_load_seconds)."""
+    out = "/dev/shm/emab_ref_out.sam" if os.path.isdir("/dev/shm") else "/tmp/emab_ref_out.sam"
+    t0 = time.time()
+    subprocess.run([REF_EMA, "align", "-s", bucket, "-r", fa, "-p", "10x", "-t", str(threads), "-o", out], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t = time.time() - t0
+    return t
+
+
+def index_load_time(fa, threads):
+    empty = "/tmp/emab_empty_bucket"
+    open(empty, "w").close()
+    t0 = time.time()
+    subprocess.run([REF_EMA, "align", "-s", empty, "-r", fa, "-p", "10x", "-t", str(threads), "-o", "/dev/null"],
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.time() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--data-dir", default=os.environ.get("EMAB_DATA", "/tmp/emab_data"))
+    ap.add_argument("--threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    threads = args.threads or max(1, cores // world)
+    cfg, n_buckets, nbc, ppb, desc = WORKLOADS[args.workload]
+    pairs_per_bucket = nbc * ppb
+    config = {"workload": f"BASELINE configs[1]: {desc}" if args.workload == "c2" else desc,
+              "bucket_pairs": pairs_per_bucket, "barcodes_per_bucket": nbc, "platform": "10x",
+              "l2_policy": "inputs larger than L2: the FM index + dense SA are ~1.3 GB and every step is a different bucket",
+              "host_threads_per_rank": threads}
+
+    # ------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        if not os.path.exists(REF_EMA):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ema was not built (needs /root/reference at build time)"}))
+            return
+        fa, buckets, ppbk = prepare(args.workload, args.data_dir, args.warmup + args.steps)
+        for i in range(args.warmup):
+            time_reference(fa, buckets[i % len(buckets)], cores)
+        t0 = time.time()
+        for i in range(args.steps):
+            time_reference(fa, buckets[(args.warmup + i) % len(buckets)], cores)
+        dt = time.time() - t0
+        v = args.steps * ppbk / dt
+        sample = f"{args.steps} steps x one bucket of {ppbk} pairs per `ema align -s -t {cores}` process (index load included, README workflow)"
+        print(json.dumps({"impl": "reference", "metric": "read pairs/sec (ema align)", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
+                          "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    import ema_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ema_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    need = (args.warmup + args.steps) * world
+    if rank == 0:
+        fa, buckets, _ = prepare(args.workload, args.data_dir, min(need, n_buckets))
+    barrier()
+    if rank != 0:
+        fa, buckets, _ = prepare(args.workload, args.data_dir, min(need, n_buckets))
+
+    t0 = time.time()
+    sess = ema_b200.Session(fa, "10x", device=local_rank, threads=threads)
+    log(f"[bench] rank {rank}: index resident in {time.time() - t0:.1f}s")
+    # each rank takes disjoint buckets: step i of rank r is bucket (i * world + r) mod n
+    data = {}
+
+    def bucket_bytes(i):
+        p = buckets[(i * world + rank) % len(buckets)]
+        if p not in data:
+            data[p] = open(p, "rb").read()
+        return data[p]
+
+    for i in range(args.warmup + args.steps):
+        bucket_bytes(i)
+    for i in range(args.warmup):
+        sess.align_bucket(bucket_bytes(i))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_start = time.time()
+    kern_ms = 0.0
+    agg = {}
+    launches = 0
+    for i in range(args.steps):
+        sam = sess.align_bucket(bucket_bytes(args.warmup + i))
+        st = sess.stats
+        kern_ms += st.kernel_ms + st.em_kernel_ms
+        launches += st.launches
+        for k in ("ms_seed", "ms_chain", "ms_align1", "ms_rescue", "ms_finalize", "em_kernel_ms", "parse_ms", "encode_ms", "align_ms",
+                  "cloud_ms", "flatten_ms", "em_ms", "format_ms", "total_ms", "occ_touches", "extend_cells", "global_cells", "local_cells",
+                  "h2d_bytes", "d2h_bytes", "sam_bytes"):
+            agg[k] = agg.get(k, 0) + getattr(st, k)
+    barrier()
+    wall = time.time() - t_start
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([wall, kern_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, kern_ms = float(t[0]), float(t[1])
+    total_pairs = args.steps * pairs_per_bucket * world
+    K = args.steps
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        seed_bytes = agg["occ_touches"] * 64.0 / K
+        seed_ms = agg["ms_seed"] / K
+        achieved = seed_bytes / (seed_ms * 1e-3) / 1e9 if seed_ms > 0 else 0.0
+        ext_ms = (agg["ms_align1"]) / K
+        out = {
+            "metric": "read pairs/sec (ema align)", "value": total_pairs / (kern_ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic", "config": config,
+            "e2e": {"value": total_pairs / wall, "unit": "pairs/s", "h2d_bytes_per_step": agg["h2d_bytes"] / K, "d2h_bytes_per_step": agg["d2h_bytes"] / K,
+                    "host_bucket_text_bytes_per_step": len(bucket_bytes(args.warmup)), "sam_bytes_per_step": agg["sam_bytes"] / K},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "k_seed (SMEM seeding, mem_collect_intv)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_launch": seed_bytes, "ms_per_launch": seed_ms},
+            "device_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain", "ms_align1", "ms_rescue", "ms_finalize", "em_kernel_ms")},
+            "host_ms_per_step": {k: agg[k] / K for k in ("parse_ms", "encode_ms", "align_ms", "cloud_ms", "flatten_ms", "em_ms", "format_ms", "total_ms")},
+            "sw": {"extend_cells_per_step": agg["extend_cells"] / K, "global_cells_per_step": agg["global_cells"] / K,
+                   "local_cells_per_step": agg["local_cells"] / K,
+                   "gcups_in_pipeline": (agg["extend_cells"] + agg["global_cells"]) / K / (max(ext_ms, 1e-9) * 1e-3) / 1e9},
+        }
+        if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_EMA):
+            b = buckets[0]
+            t_ref = time_reference(fa, b, cores)
+            t_idx = index_load_time(fa, cores)
+            out["cpu_baseline"] = {"value": pairs_per_bucket / t_ref, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                                   "sample": f"one bucket of {pairs_per_bucket} pairs, `ema align -s -t {cores}` wall {t_ref:.2f}s incl. index load {t_idx:.2f}s",
+                                   "value_excluding_index_load": pairs_per_bucket / max(t_ref - t_idx, 1e-9)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

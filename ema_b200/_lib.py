@@ -181,7 +181,9 @@ ALN_DTYPE = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("NM", 
 
 class Stats(C.Structure):
     _fields_ = [("extend_cells", C.c_int64), ("global_cells", C.c_int64), ("local_cells", C.c_int64), ("occ_touches", C.c_int64),
-                ("n_occ", C.c_int64), ("n_regs", C.c_int64), ("kernel_ms", C.c_double), ("launches", C.c_int32), ("pad", C.c_int32)]
+                ("n_occ", C.c_int64), ("n_regs", C.c_int64), ("kernel_ms", C.c_double), ("ms_seed", C.c_double), ("ms_chain", C.c_double),
+                ("ms_align1", C.c_double), ("ms_rescue", C.c_double), ("ms_finalize", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("launches", C.c_int32), ("pad", C.c_int32)]
 
 
 def align_pairs(ctx: Context, reads, stage=3, want_regs=False, aln_cap=None):
@@ -205,7 +207,8 @@ def align_pairs(ctx: Context, reads, stage=3, want_regs=False, aln_cap=None):
 
 class RunStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("parse_ms", "encode_ms", "align_ms", "kernel_ms", "cloud_ms", "flatten_ms", "em_ms",
-                                          "em_kernel_ms", "format_ms", "total_ms")] + \
+                                          "em_kernel_ms", "format_ms", "total_ms", "ms_seed", "ms_chain", "ms_align1", "ms_rescue",
+                                          "ms_finalize")] + [("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)] + \
                [(n, C.c_int64) for n in ("n_pairs", "n_barcodes", "n_cands", "n_clouds", "sam_bytes", "extend_cells", "global_cells",
                                          "local_cells", "occ_touches")] + [("launches", C.c_int32), ("pad", C.c_int32)]
 
@@ -243,6 +246,9 @@ class Session:
         text, n = C.c_void_p(), C.c_uint64()
         _check(lib().emab_align_fastq(self._h, d1, len(d1), d2, len(d2) if d2 else 0, C.byref(text), C.byref(n)))
         return self._take(text, n)
+
+    def dump_posteriors(self, path: str | None):
+        _check(lib().emab_session_dump_posteriors(self._h, path.encode() if path else None))
 
     @property
     def stats(self) -> RunStats:

@@ -92,6 +92,13 @@ int emab_session_stats(const emab_session_t *h, emab_run_stats_t *out)
 	return EMAB_OK;
 }
 
+int emab_session_dump_posteriors(emab_session_t *h, const char *path)
+{
+	if (!h) return EMAB_ERR_ARG;
+	h->s->gamma_dump = path ? path : "";
+	return EMAB_OK;
+}
+
 emab_ctx_t *emab_session_ctx(emab_session_t *h) { return h ? h->s->ctx : nullptr; }
 void emab_free(void *p) { free(p); }
 

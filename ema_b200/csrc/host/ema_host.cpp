@@ -684,6 +684,8 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 	}
 	const double t2 = now_ms();
 	st.align_ms = t2 - t1; st.kernel_ms = ds.kernel_ms; st.launches = ds.launches;
+	st.ms_seed = ds.ms_seed; st.ms_chain = ds.ms_chain; st.ms_align1 = ds.ms_align1; st.ms_rescue = ds.ms_rescue; st.ms_finalize = ds.ms_finalize;
+	st.h2d_bytes = ds.h2d_bytes; st.d2h_bytes = ds.d2h_bytes;
 	st.extend_cells = ds.extend_cells; st.global_cells = ds.global_cells; st.local_cells = ds.local_cells; st.occ_touches = ds.occ_touches;
 	std::vector<int64_t> aoff(2 * np + 1, 0);
 	for (size_t i = 0; i < 2 * np; ++i) aoff[i + 1] = aoff[i] + n_regs[i];
@@ -812,6 +814,8 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 		int rc = emab_em_batch(s->ctx, &P, gamma.data());
 		if (rc) { s->err = emab_last_error(); return rc; }
 		st.em_kernel_ms = emab_last_kernel_ms(s->ctx);
+		st.h2d_bytes += (int64_t)K * 29 + (int64_t)(E + C + G + U + 4 * nb) * 4;
+		st.d2h_bytes += (int64_t)K * 8;
 		st.launches += 1;
 	}
 	const double t5 = now_ms();
@@ -837,6 +841,17 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 			if (mi >= 0) B.recs[mi].visited = 1;
 			print_sam_record(s, B, pairs, ri, mi, cloud_base[b], &B.sam);
 			print_sam_record(s, B, pairs, mi, ri, cloud_base[b], &B.sam);
+		}
+	}
+	if (!s->gamma_dump.empty()) {  // test hook: chosen alignments with full-precision posteriors
+		FILE *f = fopen(s->gamma_dump.c_str(), "w");
+		if (f) {
+			for (const Barcode &B : bcs)
+				for (int ri : B.final_) {
+					const Rec &r = B.recs[ri];
+					fprintf(f, "%.*s\t%d\t%u\t%u\t%.17g\n", (int)r.ident.size(), r.ident.data(), (int)r.mate, r.chrom, r.pos, r.gamma);
+				}
+			fclose(f);
 		}
 	}
 	size_t total = 0;

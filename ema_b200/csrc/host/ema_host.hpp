@@ -41,6 +41,7 @@ struct Session {  // the reference's process globals (src/main.c:23-34, src/alig
 	std::vector<int32_t> sq_len;
 	int cloud_id = 0;                     // init_cloud's static counter (src/align.c:19-23)
 	std::string err;
+	std::string gamma_dump;               // test hook: path for full-precision posteriors of the chosen alignments
 	emab_run_stats_t last{};
 };
 

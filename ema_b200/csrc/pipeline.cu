@@ -268,10 +268,13 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, st));
 	CUDA_TRY(cudaMemsetAsync(d_occ_cnt, 0, (size_t)(R + 1) * 4, st));
 	int launches = 0;
+	if (!c->stage_ev[0]) for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&c->stage_ev[i]));
 	CUDA_TRY(cudaEventRecord(c->ev0, st));
+	CUDA_TRY(cudaEventRecord(c->stage_ev[0], st));
 	k_seed<<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(),
 	                                        c->b[4].as<Intv>(), d_occ_cnt, d_err, c->d_counters);
 	++launches;
+	CUDA_TRY(cudaEventRecord(c->stage_ev[1], st));
 	size_t tmp_bytes = 0;
 	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_occ_cnt, d_occ_off, R + 1, st);
 	TRY(c->b[6].ensure(tmp_bytes + 16));
@@ -299,15 +302,19 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	const size_t z_cap = (size_t)EMAB_MAX_READ_LEN * 1024;
 	TRY(c->b[16].ensure((size_t)n_warps * z_cap));
 	TRY(c->b[17].ensure((size_t)n_warps * EMAB_MAX_CIGAR * 4));
+	CUDA_TRY(cudaEventRecord(c->stage_ev[2], st));
 	k_chain<<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(), d_occ_off, p);
+	CUDA_TRY(cudaEventRecord(c->stage_ev[3], st));
 	k_align1<<<grid, PL_WARPS * 32, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
 	                                          c->b[17].as<uint32_t>(), d_err, c->d_counters);
 	launches += 2;
+	CUDA_TRY(cudaEventRecord(c->stage_ev[4], st));
 	if (stage >= 2) {
 		k_rescue<<<grid, PL_WARPS * 32, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
 		                                          c->b[17].as<uint32_t>(), d_err, c->d_counters);
 		++launches;
 	}
+	CUDA_TRY(cudaEventRecord(c->stage_ev[5], st));
 	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, p.n_regs, d_aln_off, R + 1, st);
 	TRY(c->b[6].ensure(tmp_bytes + 16));
 	cub::DeviceScan::ExclusiveSum(c->b[6].p, tmp_bytes, p.n_regs, d_aln_off, R + 1, st);
@@ -318,6 +325,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	CUDA_TRY(cudaGetLastError());
 	if (n_alns) *n_alns = A;
 	if (A > aln_cap) { snprintf(emab_errbuf, sizeof emab_errbuf, "%d candidate regions exceed the caller's capacity %lld", A, (long long)aln_cap); return EMAB_ERR_OVERFLOW; }
+	CUDA_TRY(cudaEventRecord(c->stage_ev[6], st));
 	if (stage >= 3) {
 		TRY(c->b[18].ensure(((size_t)A + 1) * sizeof(Aln)));
 		k_finalize<<<grid, PL_WARPS * 32, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, d_aln_off, c->b[18].as<Aln>(),
@@ -325,6 +333,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		++launches;
 	}
 	CUDA_TRY(cudaEventRecord(c->ev1, st));
+	CUDA_TRY(cudaEventRecord(c->stage_ev[7], st));
 	if (regs_dbg) {
 		TRY(c->b[19].ensure(((size_t)A + 1) * 18 * 8));
 		k_export_regs<<<(R + 127) / 128, 128, 0, st>>>(R, d_occ_off, d_aln_off, p, c->b[19].as<int64_t>());
@@ -343,6 +352,14 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	if (stats) {
 		stats->extend_cells = (int64_t)cnt[0]; stats->occ_touches = (int64_t)cnt[2]; stats->global_cells = (int64_t)cnt[3];
 		stats->local_cells = (int64_t)cnt[4]; stats->n_occ = T; stats->n_regs = A; stats->kernel_ms = ms; stats->launches = launches;
+		float t;
+		cudaEventElapsedTime(&t, c->stage_ev[0], c->stage_ev[1]); stats->ms_seed = t;
+		cudaEventElapsedTime(&t, c->stage_ev[2], c->stage_ev[3]); stats->ms_chain = t;
+		cudaEventElapsedTime(&t, c->stage_ev[3], c->stage_ev[4]); stats->ms_align1 = t;
+		cudaEventElapsedTime(&t, c->stage_ev[4], c->stage_ev[5]); stats->ms_rescue = t;
+		cudaEventElapsedTime(&t, c->stage_ev[6], c->stage_ev[7]); stats->ms_finalize = t;
+		stats->h2d_bytes = (int64_t)off[R] + (int64_t)(R + 1) * 8;
+		stats->d2h_bytes = (int64_t)R * 4 + (int64_t)A * (int64_t)sizeof(Aln) + 8;
 	}
 	if (h_err[0]) {
 		snprintf(emab_errbuf, sizeof emab_errbuf, "device pipeline error %d (1: backtrack scratch too small, 2: rescue window too long, 3: too many SA intervals)", h_err[0]);

@@ -44,6 +44,7 @@ struct emab_ctx {
 	emab_index *ix = nullptr;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t stage_ev[8] = {};
 	double last_ms = 0;
 	int last_launches = 0;
 	DevBuf b[24];            // scratch slots, meaning assigned by each entry point

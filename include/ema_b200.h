@@ -118,7 +118,9 @@ typedef struct {
 	int64_t extend_cells, global_cells, local_cells;  /* DP cells visited */
 	int64_t occ_touches;                              /* 64-byte Occ block loads */
 	int64_t n_occ, n_regs;
-	double kernel_ms;                                 /* device time, first kernel to last */
+	double kernel_ms;                                 /* device time, first kernel to last (CUDA events on the ctx stream) */
+	double ms_seed, ms_chain, ms_align1, ms_rescue, ms_finalize; /* per-kernel device time */
+	int64_t h2d_bytes, d2h_bytes;                     /* bytes copied inside the call */
 	int32_t launches;
 	int32_t pad;
 } emab_stats_t;
@@ -172,6 +174,8 @@ typedef struct emab_session emab_session_t;
 
 typedef struct {
 	double parse_ms, encode_ms, align_ms, kernel_ms, cloud_ms, flatten_ms, em_ms, em_kernel_ms, format_ms, total_ms;
+	double ms_seed, ms_chain, ms_align1, ms_rescue, ms_finalize;
+	int64_t h2d_bytes, d2h_bytes;
 	int64_t n_pairs, n_barcodes, n_cands, n_clouds, sam_bytes;
 	int64_t extend_cells, global_cells, local_cells, occ_touches;
 	int32_t launches, pad;
@@ -184,6 +188,8 @@ int emab_sam_header(emab_session_t *s, int argc, const char *const *argv, char *
 int emab_align_bucket(emab_session_t *s, const char *data, uint64_t len, char **sam, uint64_t *sam_len);
 int emab_align_fastq(emab_session_t *s, const char *d1, uint64_t l1, const char *d2, uint64_t l2, char **sam, uint64_t *sam_len);
 int emab_session_stats(const emab_session_t *s, emab_run_stats_t *out);
+/* test hook: write "ident<TAB>mate<TAB>chrom<TAB>pos<TAB>gamma(%.17g)" of every chosen alignment of later calls to path (NULL = off) */
+int emab_session_dump_posteriors(emab_session_t *s, const char *path);
 emab_ctx_t *emab_session_ctx(emab_session_t *s);
 void emab_free(void *p);
 

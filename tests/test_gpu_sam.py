@@ -91,21 +91,16 @@ def test_em_posteriors_vs_reference(tmp_path):
         chosen = f[-1].split(":")
         want[(f[0], int(f[1]))] = (int(chosen[0]), int(chosen[1]), float(chosen[2]))
     s = ema_b200.Session(p["fasta"], "10x", threads=8)
-    body = s.align_bucket(open(p["bucket"], "rb").read())
-    fai = [l.split("\t")[0] for l in open(p["fasta"] + ".fai")]
-    n = 0
-    worst = 0.0
-    for ln in body.decode().split("\n"):
-        if not ln:
-            continue
-        f = ln.split("\t")
-        flag = int(f[1])
-        if flag & 4:
-            continue
-        key = (f[0], 0 if flag & 64 else 1)
-        chrom, pos, gamma = want[key]
-        assert fai[chrom] == f[2] and pos == int(f[3]), key
-        xg = float([t for t in f if t.startswith("XG:f:")][0][5:])
-        assert abs(xg - gamma) <= 1e-6 * max(abs(gamma), 1e-300) + 5e-6 * gamma, (key, xg, gamma)  # %.5g rounding
+    mine = tmp_path / "mine.tsv"
+    s.dump_posteriors(str(mine))
+    s.align_bucket(open(p["bucket"], "rb").read())
+    n, worst = 0, 0.0
+    for ln in open(mine):
+        ident, mate, chrom, pos, gamma = ln.rstrip("\n").split("\t")
+        wc, wp, wg = want[(ident, int(mate))]
+        assert (wc, wp) == (int(chrom), int(pos)), (ident, mate)
+        rel = abs(float(gamma) - wg) / max(abs(wg), 1e-300)
+        worst = max(worst, rel)
         n += 1
-    assert n > 15000
+    assert n == len(want) and n > 15000
+    assert worst <= 1e-6, worst
