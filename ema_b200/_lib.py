@@ -177,6 +177,10 @@ def sa_batch(ctx: Context, ks, mode=0):
 ALN_DTYPE = np.dtype([("pos", "<i8"), ("rid", "<i4"), ("is_rev", "<i4"), ("NM", "<i4"), ("n_cigar", "<i4"), ("score", "<i4"),
                       ("mapq", "<i4"), ("score_mapq", "<i4"), ("clip", "<i4"), ("clip_edit_dist", "<i4"), ("keep", "<i4"),
                       ("em_score", "<f8"), ("cigar", "<u4", (64,))])
+CAND_DTYPE = np.dtype([("pos", "<i8"), ("em_score", "<f8"), ("rid", "<i4"), ("NM", "<i4"), ("score", "<i4"), ("mapq", "<i4"),
+                       ("score_mapq", "<i4"), ("clip", "<i4"), ("clip_edit_dist", "<i4"), ("cigar_off", "<u4"), ("n_cigar", "<u2"),
+                       ("is_rev", "u1"), ("keep", "u1"), ("pad", "<u4")])
+assert CAND_DTYPE.itemsize == 56
 
 
 class Stats(C.Structure):
@@ -186,23 +190,34 @@ class Stats(C.Structure):
                 ("d2h_bytes", C.c_int64), ("launches", C.c_int32), ("pad", C.c_int32)]
 
 
-def align_pairs(ctx: Context, reads, stage=3, want_regs=False, aln_cap=None):
+class PairsResult(C.Structure):
+    _fields_ = [("n_cands", C.c_int64), ("n_cigar_ops", C.c_int64), ("n_regs", C.POINTER(C.c_int32)), ("cands", C.c_void_p),
+                ("cigars", C.POINTER(C.c_uint32)), ("regs_dbg", C.POINTER(C.c_int64))]
+
+
+def align_pairs(ctx: Context, reads, stage=3, want_regs=False):
     """emab_align_pairs over nt4 reads laid out pair0/mate1, pair0/mate2, pair1/mate1, ...
-    Returns dict(n_regs[2n], alns (structured array, all regions incl. keep==0), regs (A,18) or None, stats)."""
+    Returns dict(n_regs[2n], alns (structured array with inline CIGARs, all regions incl. keep==0),
+    regs (A,18) or None, stats)."""
     assert len(reads) % 2 == 0
     s, off = _pack(reads)
     R = len(reads)
-    cap = aln_cap if aln_cap is not None else max(1024, 16 * R)
-    n_regs = np.zeros(R, dtype=np.int32)
-    alns = np.zeros(cap, dtype=ALN_DTYPE)
-    regs = np.zeros((cap, 18), dtype=np.int64) if want_regs else None
-    n_alns = C.c_int64(0)
+    res = PairsResult()
     st = Stats()
-    _check(lib().emab_align_pairs(ctx._h, R // 2, _p(s, C.c_uint8), _p(off, C.c_int64), stage, _p(n_regs, C.c_int32),
-                                  alns.ctypes.data_as(C.c_void_p), cap, C.byref(n_alns),
-                                  _p(regs, C.c_int64) if want_regs else None, C.byref(st)))
-    A = n_alns.value
-    return dict(n_regs=n_regs, alns=alns[:A], regs=regs[:A] if want_regs else None, stats=st)
+    _check(lib().emab_align_pairs(ctx._h, R // 2, _p(s, C.c_uint8), _p(off, C.c_int64), stage, int(want_regs), C.byref(res), C.byref(st)))
+    A = res.n_cands
+    n_regs = np.ctypeslib.as_array(res.n_regs, shape=(R,)).copy() if R else np.zeros(0, np.int32)
+    alns = np.zeros(A, dtype=ALN_DTYPE)
+    if stage >= 3 and A:
+        cands = np.frombuffer(C.string_at(res.cands, A * 56), dtype=CAND_DTYPE)
+        pool = np.ctypeslib.as_array(res.cigars, shape=(max(int(res.n_cigar_ops), 1),)).copy()
+        for f in ("pos", "rid", "is_rev", "NM", "n_cigar", "score", "mapq", "score_mapq", "clip", "clip_edit_dist", "keep", "em_score"):
+            alns[f] = cands[f]
+        for i in np.nonzero(cands["n_cigar"])[0]:
+            n, o = int(cands["n_cigar"][i]), int(cands["cigar_off"][i])
+            alns["cigar"][i, :n] = pool[o:o + n]
+    regs = np.ctypeslib.as_array(res.regs_dbg, shape=(A, 18)).copy() if want_regs and A else (np.zeros((0, 18), np.int64) if want_regs else None)
+    return dict(n_regs=n_regs, alns=alns, regs=regs, stats=st)
 
 
 class RunStats(C.Structure):
@@ -241,6 +256,24 @@ class Session:
         text, n = C.c_void_p(), C.c_uint64()
         _check(lib().emab_align_bucket(self._h, data, len(data), C.byref(text), C.byref(n)))
         return self._take(text, n)
+
+    def set_workers(self, n: int):
+        _check(lib().emab_session_workers(self._h, n))
+
+    def align_buckets(self, datas, keep_text=True):
+        """emab_align_buckets (-x mode): up to `workers` buckets in flight; returns the SAM texts in input
+        order (or only their lengths when keep_text is False, which skips the copy into Python objects)."""
+        n = len(datas)
+        arr = (C.c_char_p * n)(*datas)
+        lens = (C.c_uint64 * n)(*[len(d) for d in datas])
+        outs = (C.c_void_p * n)()
+        olens = (C.c_uint64 * n)()
+        _check(lib().emab_align_buckets(self._h, n, arr, lens, outs, olens))
+        res = []
+        for i in range(n):
+            res.append(C.string_at(outs[i], olens[i]) if keep_text else int(olens[i]))
+            lib().emab_free(outs[i])
+        return res
 
     def align_fastq(self, d1: bytes, d2: bytes | None = None) -> bytes:
         text, n = C.c_void_p(), C.c_uint64()

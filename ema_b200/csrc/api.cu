@@ -201,11 +201,20 @@ extern "C" void emab_ctx_free(emab_ctx_t *c)
 {
 	if (!c) return;
 	for (auto &b : c->b) b.release();
+	for (auto &b : c->h) b.release();
 	cudaFree(c->d_counters);
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
+
+extern "C" void *emab_pinned_alloc(uint64_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { snprintf(emab_errbuf, sizeof emab_errbuf, "cudaMallocHost(%llu) failed", (unsigned long long)bytes); return nullptr; }
+	return p;
+}
+extern "C" void emab_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" double emab_last_kernel_ms(const emab_ctx_t *c) { return c ? c->last_ms : 0; }
 extern "C" int emab_last_launches(const emab_ctx_t *c) { return c ? c->last_launches : 0; }

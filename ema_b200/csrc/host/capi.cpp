@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "ema_host.hpp"
 
 extern thread_local char emab_errbuf[512];
@@ -70,19 +71,40 @@ int emab_sam_header(emab_session_t *h, int argc, const char *const *argv, char *
 int emab_align_bucket(emab_session_t *h, const char *data, uint64_t len, char **sam, uint64_t *sam_len)
 {
 	if (!h || (!data && len)) return fail(EMAB_ERR_ARG, "null argument");
-	std::string o;
-	int rc = emab::align_special_fastq(h->s, data, (size_t)len, &o);
+	size_t n = 0;
+	int rc = emab::align_special_fastq(h->s, data, (size_t)len, sam, &n);
+	*sam_len = n;
 	if (rc) return fail(rc, h->s->err);
-	return give(o, sam, sam_len);
+	return EMAB_OK;
+}
+
+int emab_align_buckets(emab_session_t *h, int n, const char *const *data, const uint64_t *len, char **sam, uint64_t *sam_len)
+{
+	if (!h || n < 0 || (n && (!data || !len || !sam || !sam_len))) return fail(EMAB_ERR_ARG, "null argument");
+	std::vector<size_t> l(n), ol(n);
+	for (int i = 0; i < n; ++i) l[i] = (size_t)len[i];
+	int rc = emab::align_special_fastq_multi(h->s, n, data, l.data(), sam, ol.data());
+	for (int i = 0; i < n; ++i) sam_len[i] = ol[i];
+	if (rc) return fail(rc, h->s->err);
+	return EMAB_OK;
+}
+
+int emab_session_workers(emab_session_t *h, int n_workers)
+{
+	if (!h) return fail(EMAB_ERR_ARG, "null session");
+	int rc = emab::session_set_workers(h->s, n_workers);
+	if (rc) return fail(rc, h->s->err);
+	return EMAB_OK;
 }
 
 int emab_align_fastq(emab_session_t *h, const char *d1, uint64_t l1, const char *d2, uint64_t l2, char **sam, uint64_t *sam_len)
 {
 	if (!h || (!d1 && l1)) return fail(EMAB_ERR_ARG, "null argument");
-	std::string o;
-	int rc = emab::align_fastq(h->s, d1, (size_t)l1, d2, (size_t)l2, &o);
+	size_t n = 0;
+	int rc = emab::align_fastq(h->s, d1, (size_t)l1, d2, (size_t)l2, sam, &n);
+	*sam_len = n;
 	if (rc) return fail(rc, h->s->err);
-	return give(o, sam, sam_len);
+	return EMAB_OK;
 }
 
 int emab_session_stats(const emab_session_t *h, emab_run_stats_t *out)
@@ -99,7 +121,7 @@ int emab_session_dump_posteriors(emab_session_t *h, const char *path)
 	return EMAB_OK;
 }
 
-emab_ctx_t *emab_session_ctx(emab_session_t *h) { return h ? h->s->ctx : nullptr; }
+emab_ctx_t *emab_session_ctx(emab_session_t *h) { return h ? h->s->workers[0].ctx : nullptr; }
 void emab_free(void *p) { free(p); }
 
 }  // extern "C"

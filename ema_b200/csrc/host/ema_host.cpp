@@ -24,7 +24,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <atomic>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 
 namespace emab {
@@ -102,9 +104,34 @@ static void decode_bc(const Session *s, uint64_t bc, std::string *out)
 	for (int i = 0; i < s->bc_len; ++i) { out->push_back("ACGT"[bc & 3]); bc >>= 2; }
 }
 
+int PinnedBuf::ensure(size_t bytes)
+{
+	if (bytes <= cap) return 0;
+	if (p) emab_pinned_free(p);
+	cap = bytes + bytes / 4 + 4096;
+	p = emab_pinned_alloc(cap);
+	if (!p) { cap = 0; return -1; }
+	return 0;
+}
+PinnedBuf::~PinnedBuf() { if (p) emab_pinned_free(p); }
+
 // ---------------------------------------------------------------------------------------------
 // session
 // ---------------------------------------------------------------------------------------------
+int session_set_workers(Session *s, int n_workers)
+{
+	if (n_workers < 1) n_workers = 1;
+	if (n_workers > 8) n_workers = 8;
+	while ((int)s->workers.size() > n_workers) { emab_ctx_free(s->workers.back().ctx); s->workers.pop_back(); }
+	while ((int)s->workers.size() < n_workers) {
+		s->workers.emplace_back();
+		int rc = emab_ctx_create(s->ix, &s->workers.back().ctx);
+		if (rc) { s->err = emab_last_error(); s->workers.pop_back(); return rc; }
+		emab_set_error_rate(s->workers.back().ctx, s->tech->error_rate);
+	}
+	return EMAB_OK;
+}
+
 int session_open(const char *ref_path, const char *platform, int device, Session **out, std::string *err)
 {
 	*out = nullptr;
@@ -128,9 +155,8 @@ int session_open(const char *ref_path, const char *platform, int device, Session
 	}
 	int rc = emab_index_load(ref_path, device, &s->ix);
 	if (rc) { *err = std::string("error: could not load reference at ") + ref_path + ": " + emab_last_error(); delete s; return rc; }
-	rc = emab_ctx_create(s->ix, &s->ctx);
-	if (rc) { *err = emab_last_error(); emab_index_free(s->ix); delete s; return rc; }
-	emab_set_error_rate(s->ctx, tech->error_rate);
+	rc = session_set_workers(s, 1);
+	if (rc) { *err = s->err; emab_index_free(s->ix); delete s; return rc; }
 	int64_t info[12];
 	emab_index_info(s->ix, info);
 	for (int i = 0; i < (int)info[1]; ++i) {
@@ -153,7 +179,8 @@ int session_open(const char *ref_path, const char *platform, int device, Session
 void session_close(Session *s)
 {
 	if (!s) return;
-	emab_ctx_free(s->ctx);
+	for (Worker &w : s->workers) emab_ctx_free(w.ctx);
+	s->workers.clear();
 	emab_index_free(s->ix);
 	delete s;
 }
@@ -188,7 +215,8 @@ struct Rec {  // SAMRecord (include/samrecord.h:22-58), fields on the path only
 	int mapq, score_mapq, clip, clip_edit_dist;
 	uint8_t mate, rev, duplicate, unique, active, visited;
 	int pair;                 // index of the pair inside its barcode
-	const emab_aln_t *aln;
+	const emab_cand_t *aln;
+	const uint32_t *cig;      // aln's CIGAR ops
 	double gamma;
 	int cloud;                // index into Barcode::clouds
 	int selected_mate;        // record index or -1
@@ -518,10 +546,10 @@ void Barcode::choose(const Session *s)
 // ---------------------------------------------------------------------------------------------
 // SAM text (src/samrecord.c:104-284)
 // ---------------------------------------------------------------------------------------------
-static inline int get_rlen(const emab_aln_t *a)
+static inline int get_rlen(const emab_cand_t *a, const uint32_t *cig)
 {
 	int l = 0;
-	for (int k = 0; k < a->n_cigar; ++k) { int op = a->cigar[k] & 0xf; if (op == 0 || op == 2) l += a->cigar[k] >> 4; }
+	for (int k = 0; k < a->n_cigar; ++k) { int op = cig[k] & 0xf; if (op == 0 || op == 2) l += cig[k] >> 4; }
 	return l;
 }
 
@@ -536,9 +564,9 @@ static inline void put_int(std::string *o, long long v)
 	while (n) o->push_back(buf[--n]);
 }
 
-static inline void put_cigar(std::string *o, const emab_aln_t *a)
+static inline void put_cigar(std::string *o, const emab_cand_t *a, const uint32_t *cig)
 {
-	for (int i = 0; i < a->n_cigar; ++i) { put_int(o, a->cigar[i] >> 4); o->push_back("MIDSS"[a->cigar[i] & 0xf]); }
+	for (int i = 0; i < a->n_cigar; ++i) { put_int(o, cig[i] >> 4); o->push_back("MIDSS"[cig[i] & 0xf]); }
 }
 
 static inline char rc(char c)
@@ -582,15 +610,15 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 	} else flag |= 8;
 	o->append(ident); o->push_back('\t'); put_int(o, flag); o->push_back('\t'); o->append(chrom); o->push_back('\t');
 	put_int(o, pos); o->push_back('\t'); put_int(o, mapq); o->push_back('\t');
-	if (rec) put_cigar(o, rec->aln); else o->push_back('*');
+	if (rec) put_cigar(o, rec->aln, rec->cig); else o->push_back('*');
 	if (mate) {
 		const bool same = rec && mate->chrom == rec->chrom;
 		o->push_back('\t');
 		if (same) o->push_back('='); else o->append(s->fai_names[mate->chrom]);
 		o->push_back('\t'); put_int(o, (int)mate->pos);
 		if (same) {
-			const emab_aln_t *r = rec->aln, *m = mate->aln;
-			const int64_t p0 = r->pos + (r->is_rev ? get_rlen(r) - 1 : 0), p1 = m->pos + (m->is_rev ? get_rlen(m) - 1 : 0);
+			const emab_cand_t *r = rec->aln, *m = mate->aln;
+			const int64_t p0 = r->pos + (r->is_rev ? get_rlen(r, rec->cig) - 1 : 0), p1 = m->pos + (m->is_rev ? get_rlen(m, mate->cig) - 1 : 0);
 			o->push_back('\t');
 			if (m->n_cigar == 0 || r->n_cigar == 0) o->push_back('0');
 			else put_int(o, -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
@@ -625,7 +653,7 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 	if (rec && rec->alt >= 0) {
 		const Rec &a = b.recs[rec->alt];
 		o->append("\tXA:Z:"); o->append(s->fai_names[a.chrom]); o->push_back(','); o->push_back(a.rev ? '-' : '+'); put_int(o, (int)a.pos); o->push_back(',');
-		put_cigar(o, a.aln);
+		put_cigar(o, a.aln, a.cig);
 		o->push_back(','); put_int(o, a.aln->NM); o->push_back(';');
 	}
 	o->push_back('\n');
@@ -646,42 +674,42 @@ static const uint8_t *nt4_table()
 	return t;
 }
 
-static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string *out)
+static int process_pairs(Session *s, Worker &wk, int ticket, const std::vector<Pair> &pairs, char **out_buf, size_t *out_len, emab_run_stats_t &st)
 {
 	const double t0 = now_ms();
 	const size_t np = pairs.size();
-	emab_run_stats_t &st = s->last;
+	const int nthr = wk.n_threads;
 	memset(&st, 0, sizeof st);
 	st.n_pairs = (int64_t)np;
-	if (np == 0) return EMAB_OK;
+	*out_buf = nullptr; *out_len = 0;
+	if (np == 0) { s->take_cloud_base(ticket, 0); *out_buf = (char *)malloc(1); return EMAB_OK; }
 	// ---- encode and align the whole batch on the device
 	const uint8_t *tab = nt4_table();
-	std::vector<int64_t> off(2 * np + 1, 0);
+	if (wk.off.ensure((2 * np + 1) * 8)) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
+	int64_t *off = (int64_t *)wk.off.p;
+	off[0] = 0;
 	for (size_t i = 0; i < np; ++i) {
 		off[2 * i + 1] = off[2 * i] + (int64_t)pairs[i].read[0].size();
 		off[2 * i + 2] = off[2 * i + 1] + (int64_t)pairs[i].read[1].size();
 	}
-	std::vector<uint8_t> seq((size_t)off[2 * np] + 1);
-	#pragma omp parallel for num_threads(s->n_threads) schedule(static)
+	if (wk.seq.ensure((size_t)off[2 * np] + 1)) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
+	uint8_t *seq = (uint8_t *)wk.seq.p;
+	#pragma omp parallel for num_threads(nthr) schedule(static)
 	for (size_t i = 0; i < np; ++i)
 		for (int m = 0; m < 2; ++m) {
-			uint8_t *d = seq.data() + off[2 * i + m];
+			uint8_t *d = seq + off[2 * i + m];
 			const std::string_view r = pairs[i].read[m];
 			for (size_t k = 0; k < r.size(); ++k) d[k] = tab[(uint8_t)r[k]];
 		}
-	std::vector<int32_t> n_regs(2 * np);
-	std::vector<emab_aln_t> alns;
-	int64_t n_alns = 0;
-	size_t cap = 4 * np + 1024;
 	emab_stats_t ds;
+	emab_pairs_result_t res;
 	const double t1 = now_ms();
-	for (;;) {
-		alns.resize(cap);
-		int rc = emab_align_pairs(s->ctx, (int)np, seq.data(), off.data(), 3, n_regs.data(), alns.data(), (int64_t)cap, &n_alns, nullptr, &ds);
-		if (rc == EMAB_ERR_OVERFLOW && n_alns > (int64_t)cap) { cap = (size_t)n_alns + 1024; continue; }
-		if (rc) { s->err = emab_last_error(); return rc; }
-		break;
+	{
+		int rc = emab_align_pairs(wk.ctx, (int)np, seq, off, 3, 0, &res, &ds);
+		if (rc) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
 	}
+	const int32_t *n_regs = res.n_regs;
+	const emab_cand_t *alns = res.cands;
 	const double t2 = now_ms();
 	st.align_ms = t2 - t1; st.kernel_ms = ds.kernel_ms; st.launches = ds.launches;
 	st.ms_seed = ds.ms_seed; st.ms_chain = ds.ms_chain; st.ms_align1 = ds.ms_align1; st.ms_rescue = ds.ms_rescue; st.ms_finalize = ds.ms_finalize;
@@ -701,7 +729,7 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 	const int nb = (int)bcs.size();
 	st.n_barcodes = nb;
 	// ---- records + clouds per barcode
-	#pragma omp parallel for num_threads(s->n_threads) schedule(dynamic, 1)
+	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 1)
 	for (int b = 0; b < nb; ++b) {
 		Barcode &B = bcs[b];
 		for (int pi = 0; pi < B.n_pairs; ++pi) {  // append_alignments' bookkeeping (src/align.c:1010-1060)
@@ -709,14 +737,14 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 			for (int m = 0; m < 2; ++m) {
 				int added = 0;
 				for (int64_t k = aoff[2 * gp + m]; k < aoff[2 * gp + m + 1]; ++k) {
-					const emab_aln_t &a = alns[k];
+					const emab_cand_t &a = alns[k];
 					if (!a.keep) continue;
 					Rec r;
 					r.chrom = (uint32_t)s->rid2chrom[a.rid]; r.pos = (uint32_t)(a.pos + 1);
 					r.ident = m == 0 ? pairs[gp].id1 : pairs[gp].id2;
 					r.score = a.em_score; r.mapq = a.mapq; r.score_mapq = a.score_mapq; r.clip = a.clip; r.clip_edit_dist = a.clip_edit_dist;
 					r.mate = (uint8_t)m; r.rev = (uint8_t)a.is_rev; r.duplicate = 0; r.unique = 0; r.active = 1; r.visited = 0;
-					r.pair = pi; r.aln = &a; r.gamma = 0; r.cloud = -1; r.selected_mate = -1; r.alt = -1;
+					r.pair = pi; r.aln = &a; r.cig = res.cigars + a.cigar_off; r.gamma = 0; r.cloud = -1; r.selected_mate = -1; r.alt = -1;
 					B.recs.push_back(r);
 					++added;
 				}
@@ -743,14 +771,14 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 	}
 	const int E = bc_entry_off[nb], C = bc_cloud_off[nb], G = bc_group_off[nb], U = bc_unit_off[nb];
 	const int64_t K = bc_cand_off[nb];
-	if (K > 0x7fffffff) { s->err = "too many candidates in one batch"; return EMAB_ERR_OVERFLOW; }
+	if (K > 0x7fffffff) { s->err = "too many candidates in one batch"; s->take_cloud_base(ticket, 0); return EMAB_ERR_OVERFLOW; }
 	st.n_cands = K; st.n_clouds = C;
 	std::vector<int32_t> entry_cand_off(E + 1, 0), entry_mate(E), cand_cloud(K), cand_chrom(K), group_off(G + 1, 0), group_clouds(C),
 	    contrib_off(C + 1, 0), contrib(K), unit_first(U), unit_second(U);
 	std::vector<double> cand_score(K), gamma(K);
 	std::vector<uint32_t> cand_pos(K);
 	std::vector<uint8_t> cand_flags(K);
-	#pragma omp parallel for num_threads(s->n_threads) schedule(dynamic, 1)
+	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 1)
 	for (int b = 0; b < nb; ++b) {
 		const Barcode &B = bcs[b];
 		const int ne = (int)B.entries.size(), e0 = bc_entry_off[b], c0 = bc_cloud_off[b];
@@ -811,19 +839,18 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 		P.cand_score = cand_score.data(); P.cand_cloud = cand_cloud.data(); P.cand_chrom = cand_chrom.data(); P.cand_pos = cand_pos.data(); P.cand_flags = cand_flags.data();
 		P.group_off = group_off.data(); P.group_clouds = group_clouds.data(); P.cloud_contrib_off = contrib_off.data(); P.cloud_contrib = contrib.data();
 		P.unit_first = unit_first.data(); P.unit_second = unit_second.data();
-		int rc = emab_em_batch(s->ctx, &P, gamma.data());
-		if (rc) { s->err = emab_last_error(); return rc; }
-		st.em_kernel_ms = emab_last_kernel_ms(s->ctx);
+		int rc = emab_em_batch(wk.ctx, &P, gamma.data());
+		if (rc) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
+		st.em_kernel_ms = emab_last_kernel_ms(wk.ctx);
 		st.h2d_bytes += (int64_t)K * 29 + (int64_t)(E + C + G + U + 4 * nb) * 4;
 		st.d2h_bytes += (int64_t)K * 8;
 		st.launches += 1;
 	}
 	const double t5 = now_ms();
 	// ---- choose, mark duplicates, print; cloud ids continue the session-wide counter in barcode order
-	std::vector<int> cloud_base(nb + 1, s->cloud_id);
+	std::vector<int> cloud_base(nb + 1, s->take_cloud_base(ticket, C));
 	for (int b = 0; b < nb; ++b) cloud_base[b + 1] = cloud_base[b] + (int)bcs[b].clouds.size();
-	s->cloud_id = cloud_base[nb];
-	#pragma omp parallel for num_threads(s->n_threads) schedule(dynamic, 1)
+	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 1)
 	for (int b = 0; b < nb; ++b) {
 		Barcode &B = bcs[b];
 		const int ne = (int)B.entries.size(), e0 = bc_entry_off[b];
@@ -854,10 +881,15 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 			fclose(f);
 		}
 	}
-	size_t total = 0;
-	for (const Barcode &B : bcs) total += B.sam.size();
-	out->reserve(out->size() + total);
-	for (const Barcode &B : bcs) out->append(B.sam);
+	std::vector<size_t> soff(nb + 1, 0);
+	for (int b = 0; b < nb; ++b) soff[b + 1] = soff[b] + bcs[b].sam.size();
+	const size_t total = soff[nb];
+	char *buf = (char *)malloc(total + 1);
+	if (!buf) { s->err = "out of memory"; return EMAB_ERR_NOMEM; }
+	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 4)
+	for (int b = 0; b < nb; ++b) memcpy(buf + soff[b], bcs[b].sam.data(), bcs[b].sam.size());
+	buf[total] = 0;
+	*out_buf = buf; *out_len = total;
 	const double t6 = now_ms();
 	st.encode_ms = t1 - t0; st.cloud_ms = t3 - t2; st.flatten_ms = t4 - t3; st.em_ms = t5 - t4; st.format_ms = t6 - t5; st.total_ms = t6 - t0;
 	st.sam_bytes = (int64_t)total;
@@ -867,10 +899,19 @@ static int process_pairs(Session *s, const std::vector<Pair> &pairs, std::string
 // ---------------------------------------------------------------------------------------------
 // inputs
 // ---------------------------------------------------------------------------------------------
+static const bool *ws_table()
+{  // isspace() in the C locale, as a table (the hot loop of the bucket parser)
+	static bool t[256];
+	static bool init = false;
+	if (!init) { for (int c = 0; c < 256; ++c) t[c] = c == ' ' || (c >= '\t' && c <= '\r'); init = true; }
+	return t;
+}
+
 static inline std::string_view token(const char *&p, const char *end)
 {  // copy_until_space (src/util.c:11-20): up to the next whitespace, then skip one character
+	static const bool *ws = ws_table();
 	const char *b = p;
-	while (p < end && !isspace((unsigned char)*p)) ++p;
+	while (p < end && !ws[(uint8_t)*p]) ++p;
 	std::string_view t(b, (size_t)(p - b));
 	if (p < end) ++p;
 	return t;
@@ -878,45 +919,122 @@ static inline std::string_view token(const char *&p, const char *end)
 
 // read_special_fastq (src/align.c:759-806): one pair per line "BC @id read1 qual1 read2 qual2",
 // lines stably sorted by their first BC_LEN characters.
-int align_special_fastq(Session *s, const char *data, size_t len, std::string *out)
+static int parse_bucket(Session *s, int nthr, const char *data, size_t len, std::vector<Pair> &pairs, std::string *err)
 {
-	const double t0 = now_ms();
 	std::vector<std::string_view> lines;
 	{
 		const char *p = data, *end = data + len;
 		while (p < end) {
 			const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
 			const char *e = nl ? nl : end;
-			lines.emplace_back(p, (size_t)(e - p));   // an empty line is a record with empty fields in the reference; rejected below
+			lines.emplace_back(p, (size_t)(e - p));
 			p = nl ? nl + 1 : end;
 		}
 	}
 	const size_t bl = (size_t)s->bc_len;
 	std::stable_sort(lines.begin(), lines.end(), [bl](std::string_view a, std::string_view b) {
-		// strncmp over at most BC_LEN characters; a line end compares as NUL/newline would
+		// strncmp over at most BC_LEN characters (special_fastq_record_cmp, src/align.c:752-757)
 		const size_t n = std::min(bl, std::min(a.size(), b.size()));
 		int c = memcmp(a.data(), b.data(), n);
 		if (c != 0) return c < 0;
 		if (n == bl) return false;
 		return a.size() < b.size();
 	});
-	std::vector<Pair> pairs(lines.size());
+	pairs.resize(lines.size());
+	ws_table();
+	int bad = 0;
+	#pragma omp parallel for num_threads(nthr) schedule(static) reduction(max : bad)
 	for (size_t i = 0; i < lines.size(); ++i) {
 		const char *p = lines[i].data(), *end = p + lines[i].size();
 		std::string_view bc = token(p, end);
 		Pair &P = pairs[i];
-		if (!encode_bc(s, bc.data(), bc.size(), &P.bc)) { s->err = "error: malformed barcode in input line " + std::to_string(i + 1); return EMAB_ERR_ARG; }
+		if (!encode_bc(s, bc.data(), bc.size(), &P.bc)) { bad = std::max(bad, 1); continue; }
 		std::string_view id = token(p, end);
 		if (!id.empty()) id.remove_prefix(1);  // skip the '@' (src/align.c:927)
 		P.id1 = P.id2 = id;
 		P.read[0] = token(p, end); P.qual[0] = token(p, end); P.read[1] = token(p, end); P.qual[1] = token(p, end);
-		if (P.read[0].size() > 200 || P.read[1].size() > 200) { s->err = "error: read longer than MAX_READ_LEN (200)"; return EMAB_ERR_ARG; }
+		if (P.read[0].size() > 200 || P.read[1].size() > 200) bad = std::max(bad, 2);
 	}
+	if (bad == 1) { *err = "error: malformed barcode in the input bucket"; return EMAB_ERR_ARG; }
+	if (bad == 2) { *err = "error: read longer than MAX_READ_LEN (200)"; return EMAB_ERR_ARG; }
+	return EMAB_OK;
+}
+
+// read_special_fastq (src/align.c:759-806): one pair per line "BC @id read1 qual1 read2 qual2",
+// lines stably sorted by their first BC_LEN characters.
+static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size_t len, char **out, size_t *out_len, emab_run_stats_t &st, std::string *err)
+{
+	const double t0 = now_ms();
+	std::vector<Pair> pairs;
+	int rc = parse_bucket(s, wk.n_threads, data, len, pairs, err);
+	if (rc) { s->take_cloud_base(ticket, 0); return rc; }
 	const double t1 = now_ms();
-	int rc = process_pairs(s, pairs, out);
-	s->last.parse_ms = t1 - t0;
-	s->last.total_ms += t1 - t0;
+	rc = process_pairs(s, wk, ticket, pairs, out, out_len, st);
+	if (rc) *err = s->err;
+	st.parse_ms = t1 - t0;
+	st.total_ms += t1 - t0;
 	return rc;
+}
+
+int align_special_fastq(Session *s, const char *data, size_t len, char **out, size_t *out_len)
+{
+	s->workers[0].n_threads = s->n_threads;
+	std::string err;
+	int rc = run_bucket(s, s->workers[0], s->new_ticket(), data, len, out, out_len, s->last, &err);
+	if (rc) s->err = err;
+	return rc;
+}
+
+// -x: several buckets in flight.  Each worker owns a device context (its own stream), so one bucket's
+// kernels overlap another's host-side parsing, cloud building and SAM formatting, and the copies of a
+// third.  Outputs and cloud ids are in input order.
+int align_special_fastq_multi(Session *s, int n, const char *const *data, const size_t *len, char **out, size_t *out_len)
+{
+	const int W = std::max(1, std::min((int)s->workers.size(), n));
+	const int per = std::max(1, s->n_threads / W);
+	std::vector<int> tickets(n);
+	for (int i = 0; i < n; ++i) { tickets[i] = s->new_ticket(); out[i] = nullptr; out_len[i] = 0; }
+	std::atomic<int> next(0), first_err(0);
+	std::vector<std::string> errs(W);
+	std::vector<emab_run_stats_t> sum(W);
+	for (auto &x : sum) memset(&x, 0, sizeof x);
+	const double t0 = now_ms();
+	auto body = [&](int w) {
+		Worker &wk = s->workers[w];
+		wk.n_threads = per;
+		for (;;) {
+			const int i = next.fetch_add(1);
+			if (i >= n) break;
+			emab_run_stats_t st;
+			memset(&st, 0, sizeof st);
+			int rc = first_err.load() ? (s->take_cloud_base(tickets[i], 0), 0) : run_bucket(s, wk, tickets[i], data[i], len[i], &out[i], &out_len[i], st, &errs[w]);
+			if (rc) { int z = 0; first_err.compare_exchange_strong(z, rc); if (errs[w].empty()) errs[w] = s->err; }
+			double *a = &sum[w].parse_ms; const double *b = &st.parse_ms;
+			for (int k = 0; k < 15; ++k) a[k] += b[k];
+			int64_t *ai = &sum[w].h2d_bytes; const int64_t *bi = &st.h2d_bytes;
+			for (int k = 0; k < 11; ++k) ai[k] += bi[k];
+			sum[w].launches += st.launches;
+		}
+	};
+	std::vector<std::thread> th;
+	for (int w = 1; w < W; ++w) th.emplace_back(body, w);
+	body(0);
+	for (auto &t : th) t.join();
+	memset(&s->last, 0, sizeof s->last);
+	for (int w = 0; w < W; ++w) {
+		double *a = &s->last.parse_ms; const double *b = &sum[w].parse_ms;
+		for (int k = 0; k < 15; ++k) a[k] += b[k];
+		int64_t *ai = &s->last.h2d_bytes; const int64_t *bi = &sum[w].h2d_bytes;
+		for (int k = 0; k < 11; ++k) ai[k] += bi[k];
+		s->last.launches += sum[w].launches;
+	}
+	s->last.total_ms = now_ms() - t0;
+	if (first_err.load()) {
+		for (int w = 0; w < W; ++w) if (!errs[w].empty()) { s->err = errs[w]; break; }
+		for (int i = 0; i < n; ++i) { free(out[i]); out[i] = nullptr; }
+		return first_err.load();
+	}
+	return EMAB_OK;
 }
 
 // ---- standard FASTQ (src/align.c:632-744, src/techs.c:5-69) -----------------------------------------
@@ -979,7 +1097,7 @@ static bool next_fastq(const Session *s, const char *&p, const char *end, FqRec 
 	return true;
 }
 
-int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2, std::string *out)
+int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2, char **out, size_t *out_len)
 {
 	const double t0 = now_ms();
 	std::vector<Pair> pairs;
@@ -999,7 +1117,8 @@ int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2
 	}
 	if (!err.empty()) { s->err = err; return EMAB_ERR_ARG; }
 	const double t1 = now_ms();
-	int rc = process_pairs(s, pairs, out);
+	s->workers[0].n_threads = s->n_threads;
+	int rc = process_pairs(s, s->workers[0], s->new_ticket(), pairs, out, out_len, s->last);
 	s->last.parse_ms = t1 - t0;
 	s->last.total_ms += t1 - t0;
 	return rc;

@@ -2,7 +2,9 @@
 // batcher, cloud construction, best-alignment choice, duplicate marking and SAM text.
 // Mirrors include/align.h, include/techs.h, include/samrecord.h of the reference; see ema_host.cpp.
 #pragma once
+#include <condition_variable>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../../include/ema_b200.h"
@@ -24,9 +26,22 @@ struct Platform {  // PlatformProfile (include/techs.h:10-22, src/techs.c:71-127
 
 const Platform *platform_by_name(const char *name);
 
+struct PinnedBuf {  // grow-only pinned host buffer (fast H2D path)
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes);
+	~PinnedBuf();
+};
+
+struct Worker {  // one in-flight bucket: a device context (stream + scratch) and its staging buffers
+	emab_ctx_t *ctx = nullptr;
+	PinnedBuf seq, off;
+	int n_threads = 1;
+};
+
 struct Session {  // the reference's process globals (src/main.c:23-34, src/align.c:177-178) as one object
 	emab_index_t *ix = nullptr;
-	emab_ctx_t *ctx = nullptr;
+	std::vector<Worker> workers;          // buckets in flight (-x mode / emab_align_buckets); workers[0] serves single calls
 	const Platform *tech = nullptr;
 	int bc_len = 16;
 	bool is_haplotag = false;
@@ -40,6 +55,21 @@ struct Session {  // the reference's process globals (src/main.c:23-34, src/alig
 	std::vector<std::string> sq_names;    // @SQ from the .ann
 	std::vector<int32_t> sq_len;
 	int cloud_id = 0;                     // init_cloud's static counter (src/align.c:19-23)
+	// cloud ids are handed out in bucket order even when buckets are processed concurrently
+	std::mutex mu;
+	std::condition_variable cv;
+	int next_ticket = 0, cloud_turn = 0;
+	int new_ticket() { std::lock_guard<std::mutex> g(mu); return next_ticket++; }
+	int take_cloud_base(int ticket, int n_clouds)
+	{
+		std::unique_lock<std::mutex> g(mu);
+		cv.wait(g, [&] { return cloud_turn == ticket; });
+		int base = cloud_id;
+		cloud_id += n_clouds;
+		++cloud_turn;
+		cv.notify_all();
+		return base;
+	}
 	std::string err;
 	std::string gamma_dump;               // test hook: path for full-precision posteriors of the chosen alignments
 	emab_run_stats_t last{};
@@ -48,8 +78,11 @@ struct Session {  // the reference's process globals (src/main.c:23-34, src/alig
 int session_open(const char *ref_path, const char *platform, int device, Session **out, std::string *err);
 void session_close(Session *s);
 void sam_header(const Session *s, int argc, const char *const *argv, std::string *out);
-// find_clouds_and_align (src/align.c:214) over the *contents* of the input file(s); appends SAM text to out
-int align_special_fastq(Session *s, const char *data, size_t len, std::string *out);
-int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2, std::string *out);  // d2 == nullptr: interleaved
+int session_set_workers(Session *s, int n_workers);
+// find_clouds_and_align (src/align.c:214) over the *contents* of the input file(s); SAM text in a malloc'ed buffer
+int align_special_fastq(Session *s, const char *data, size_t len, char **out, size_t *out_len);
+int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2, char **out, size_t *out_len);  // d2 == nullptr: interleaved
+// -x mode: n buckets, up to workers.size() in flight, outputs in input order
+int align_special_fastq_multi(Session *s, int n, const char *const *data, const size_t *len, char **out, size_t *out_len);
 
 }  // namespace emab

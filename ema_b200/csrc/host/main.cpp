@@ -119,12 +119,21 @@ int main(int argc, char *argv[])
 	if (multi) {
 		const int n_inputs = argc - optind - 1;
 		if (n_inputs == 0) { fprintf(stderr, "warning: no input files specified; nothing to do\n"); exit(EXIT_SUCCESS); }
-		for (int i = optind + 1; i < argc; ++i) {  // buckets are processed in argument order
-			std::string data;
-			if (!slurp(argv[i], &data)) IOERROR(argv[i]);
+		// buckets are emitted in argument order; EMAB_WORKERS of them (default 3) are in flight on the GPU
+		int workers = 3;
+		if (const char *w = getenv("EMAB_WORKERS")) workers = atoi(w);
+		emab_session_workers(s, workers);
+		std::vector<std::string> datas(n_inputs);
+		std::vector<const char *> ptrs(n_inputs);
+		std::vector<uint64_t> lens(n_inputs), olens(n_inputs);
+		std::vector<char *> outs(n_inputs);
+		for (int i = 0; i < n_inputs; ++i) {
+			if (!slurp(argv[optind + 1 + i], &datas[i])) IOERROR(argv[optind + 1 + i]);
+			ptrs[i] = datas[i].data(); lens[i] = datas[i].size();
 			fprintf(stderr, "Processing reads...\n");
-			emit(emab_align_bucket(s, data.data(), data.size(), &text, &len));
 		}
+		if (emab_align_buckets(s, n_inputs, ptrs.data(), lens.data(), outs.data(), olens.data())) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
+		for (int i = 0; i < n_inputs; ++i) { fwrite(outs[i], 1, olens[i], out_file); emab_free(outs[i]); }
 	} else if (fqx) {
 		std::string data;
 		if (!slurp(fqx, &data)) IOERROR(fqx);

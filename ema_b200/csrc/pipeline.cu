@@ -24,7 +24,7 @@
 #define PL_WARPS 8
 #define RESCUE_ROOM 51  // mem_matesw can add one region per anchor, at most max_matesw = 50 anchors
 
-static_assert(sizeof(emab_aln_t) == sizeof(Aln), "public and device candidate records must have one layout");
+static_assert(sizeof(emab_cand_t) == 56, "emab_cand_t is a 56-byte wire record");
 
 // ---------------------------------------------------------------------------------------------
 // device DP policy: the warp-cooperative kernels of ksw_warp.cuh
@@ -195,6 +195,27 @@ k_finalize(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, con
 	}
 }
 
+// candidates -> compact wire records + a CIGAR pool (most CIGARs have 1-3 ops; the device-side record reserves 64)
+__global__ void k_ncigar(int A, const Aln *alns, int32_t *ncig)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < A) ncig[i] = alns[i].n_cigar;
+	if (i == A) ncig[i] = 0;
+}
+
+__global__ void k_pack(int A, const Aln *alns, const int32_t *cig_off, emab_cand_t *out, uint32_t *pool)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= A) return;
+	const Aln &a = alns[i];
+	emab_cand_t o;
+	o.pos = a.pos; o.em_score = a.em_score; o.rid = a.rid; o.NM = a.NM; o.score = a.score; o.mapq = a.mapq; o.score_mapq = a.score_mapq;
+	o.clip = a.clip; o.clip_edit_dist = a.clip_edit_dist; o.cigar_off = (uint32_t)cig_off[i]; o.n_cigar = (uint16_t)a.n_cigar;
+	o.is_rev = (uint8_t)a.is_rev; o.keep = (uint8_t)a.keep;
+	out[i] = o;
+	for (int k = 0; k < a.n_cigar; ++k) pool[cig_off[i] + k] = a.cigar[k];
+}
+
 __global__ void k_export_regs(int n_reads, const int32_t *occ_off, const int32_t *aln_off, Pools p, int64_t *out)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,13 +259,12 @@ extern "C" int emab_set_error_rate(emab_ctx_t *c, double eps)
 	return EMAB_OK;
 }
 
-extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, const int64_t *off, int stage,
-                                int32_t *n_regs_out, emab_aln_t *alns_out, int64_t aln_cap, int64_t *n_alns, int64_t *regs_dbg,
-                                emab_stats_t *stats)
+extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, const int64_t *off, int stage, int want_regs,
+                                emab_pairs_result_t *res, emab_stats_t *stats)
 {
-	if (!c || !c->ix || n_pairs < 0 || stage < 1 || stage > 3) return EMAB_ERR_ARG;
+	if (!c || !c->ix || !res || n_pairs < 0 || stage < 1 || stage > 3) return EMAB_ERR_ARG;
 	const int R = 2 * n_pairs;
-	if (n_alns) *n_alns = 0;
+	memset(res, 0, sizeof *res);
 	if (stats) memset(stats, 0, sizeof *stats);
 	if (R == 0) return EMAB_OK;
 	for (int i = 0; i < R; ++i) {
@@ -323,30 +343,54 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	CUDA_TRY(cudaMemcpyAsync(&A, d_aln_off + R, 4, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaGetLastError());
-	if (n_alns) *n_alns = A;
-	if (A > aln_cap) { snprintf(emab_errbuf, sizeof emab_errbuf, "%d candidate regions exceed the caller's capacity %lld", A, (long long)aln_cap); return EMAB_ERR_OVERFLOW; }
+	int32_t NC = 0;
 	CUDA_TRY(cudaEventRecord(c->stage_ev[6], st));
 	if (stage >= 3) {
 		TRY(c->b[18].ensure(((size_t)A + 1) * sizeof(Aln)));
 		k_finalize<<<grid, PL_WARPS * 32, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, d_aln_off, c->b[18].as<Aln>(),
 		                                            c->b[23].as<ScoreConsts>(), c->b[16].as<uint8_t>(), z_cap, c->b[17].as<uint32_t>(), d_err, c->d_counters);
 		++launches;
+		// compact wire format: 56-byte records + CIGAR pool
+		TRY(c->b[20].ensure(((size_t)A + 2) * 4 * 2));
+		int32_t *d_ncig = c->b[20].as<int32_t>(), *d_cig_off = d_ncig + (A + 2);
+		k_ncigar<<<(A + 256) / 256, 256, 0, st>>>(A, c->b[18].as<Aln>(), d_ncig);
+		cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_ncig, d_cig_off, A + 1, st);
+		TRY(c->b[6].ensure(tmp_bytes + 16));
+		cub::DeviceScan::ExclusiveSum(c->b[6].p, tmp_bytes, d_ncig, d_cig_off, A + 1, st);
+		TRY(c->b[21].ensure(((size_t)A + 1) * sizeof(emab_cand_t)));
+		TRY(c->b[19].ensure(((size_t)A + 1) * EMAB_MAX_CIGAR * 4));  // upper bound; only the used prefix is copied back
+		k_pack<<<(A + 255) / 256, 256, 0, st>>>(A, c->b[18].as<Aln>(), d_cig_off, c->b[21].as<emab_cand_t>(), c->b[19].as<uint32_t>());
+		launches += 3;
+		CUDA_TRY(cudaEventRecord(c->ev1, st));
+		CUDA_TRY(cudaEventRecord(c->stage_ev[7], st));
+		CUDA_TRY(cudaMemcpyAsync(&NC, d_cig_off + A, 4, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		TRY(c->h[1].ensure(((size_t)A + 1) * sizeof(emab_cand_t)));
+		TRY(c->h[2].ensure(((size_t)NC + 1) * 4));
+		if (A) CUDA_TRY(cudaMemcpyAsync(c->h[1].p, c->b[21].p, (size_t)A * sizeof(emab_cand_t), cudaMemcpyDeviceToHost, st));
+		if (NC) CUDA_TRY(cudaMemcpyAsync(c->h[2].p, c->b[19].p, (size_t)NC * 4, cudaMemcpyDeviceToHost, st));
+	} else {
+		CUDA_TRY(cudaEventRecord(c->ev1, st));
+		CUDA_TRY(cudaEventRecord(c->stage_ev[7], st));
 	}
-	CUDA_TRY(cudaEventRecord(c->ev1, st));
-	CUDA_TRY(cudaEventRecord(c->stage_ev[7], st));
-	if (regs_dbg) {
-		TRY(c->b[19].ensure(((size_t)A + 1) * 18 * 8));
-		k_export_regs<<<(R + 127) / 128, 128, 0, st>>>(R, d_occ_off, d_aln_off, p, c->b[19].as<int64_t>());
-		CUDA_TRY(cudaMemcpyAsync(regs_dbg, c->b[19].p, (size_t)A * 18 * 8, cudaMemcpyDeviceToHost, st));
+	if (want_regs) {
+		TRY(c->b[24].ensure(((size_t)A + 1) * 18 * 8));
+		TRY(c->h[3].ensure(((size_t)A + 1) * 18 * 8));
+		k_export_regs<<<(R + 127) / 128, 128, 0, st>>>(R, d_occ_off, d_aln_off, p, c->b[24].as<int64_t>());
+		CUDA_TRY(cudaMemcpyAsync(c->h[3].p, c->b[24].p, (size_t)A * 18 * 8, cudaMemcpyDeviceToHost, st));
 	}
-	if (n_regs_out) CUDA_TRY(cudaMemcpyAsync(n_regs_out, p.n_regs, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
-	if (stage >= 3 && alns_out && A) CUDA_TRY(cudaMemcpyAsync(alns_out, c->b[18].p, (size_t)A * sizeof(Aln), cudaMemcpyDeviceToHost, st));
-	int h_err[4] = {0, 0, 0, 0};
-	unsigned long long cnt[8];
+	TRY(c->h[0].ensure((size_t)R * 4 + 128));
+	CUDA_TRY(cudaMemcpyAsync(c->h[0].p, p.n_regs, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+	int *h_err = (int *)((char *)c->h[0].p + (size_t)R * 4);
+	unsigned long long *cnt = (unsigned long long *)((char *)c->h[0].p + (((size_t)R * 4 + 16 + 7) & ~(size_t)7));
 	CUDA_TRY(cudaMemcpyAsync(h_err, d_err, 16, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaGetLastError());
+	res->n_cands = A; res->n_cigar_ops = NC; res->n_regs = (const int32_t *)c->h[0].p;
+	res->cands = stage >= 3 ? (const emab_cand_t *)c->h[1].p : nullptr;
+	res->cigars = stage >= 3 ? (const uint32_t *)c->h[2].p : nullptr;
+	res->regs_dbg = want_regs ? (const int64_t *)c->h[3].p : nullptr;
 	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
 	c->last_ms = ms; c->last_launches = launches;
 	if (stats) {
@@ -359,7 +403,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		cudaEventElapsedTime(&t, c->stage_ev[4], c->stage_ev[5]); stats->ms_rescue = t;
 		cudaEventElapsedTime(&t, c->stage_ev[6], c->stage_ev[7]); stats->ms_finalize = t;
 		stats->h2d_bytes = (int64_t)off[R] + (int64_t)(R + 1) * 8;
-		stats->d2h_bytes = (int64_t)R * 4 + (int64_t)A * (int64_t)sizeof(Aln) + 8;
+		stats->d2h_bytes = (int64_t)R * 4 + (int64_t)A * (int64_t)sizeof(emab_cand_t) + (int64_t)NC * 4 + 96;
 	}
 	if (h_err[0]) {
 		snprintf(emab_errbuf, sizeof emab_errbuf, "device pipeline error %d (1: backtrack scratch too small, 2: rescue window too long, 3: too many SA intervals)", h_err[0]);

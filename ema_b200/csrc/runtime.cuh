@@ -26,6 +26,27 @@ struct DevBuf {  // grow-only device buffer
 	template <class T> T *as() const { return (T *)p; }
 };
 
+struct HostBuf {  // grow-only pinned host buffer
+	void *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes)
+	{
+		if (bytes <= cap) return EMAB_OK;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaMallocHost(&p, want);
+		if (e != cudaSuccess) {
+			snprintf(emab_errbuf, sizeof emab_errbuf, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+			p = nullptr;
+			return EMAB_ERR_NOMEM;
+		}
+		cap = want;
+		return EMAB_OK;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct emab_index {
 	int device = 0;
 	DevIndex d{};            // device pointers + scalars (passed to kernels by value)
@@ -47,7 +68,8 @@ struct emab_ctx {
 	cudaEvent_t stage_ev[8] = {};
 	double last_ms = 0;
 	int last_launches = 0;
-	DevBuf b[24];            // scratch slots, meaning assigned by each entry point
+	DevBuf b[28];            // device scratch slots, meaning assigned by each entry point
+	HostBuf h[8];            // pinned host result buffers, owned by the ctx and valid until its next call
 	unsigned long long *d_counters = nullptr;  // 8 x u64 instrumentation counters
 	int n_sm = 148;
 	// resident SW microbench inputs

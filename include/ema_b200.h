@@ -90,29 +90,37 @@ int emab_smem_batch(emab_ctx_t *ctx, int n, const uint8_t *seq, const int64_t *o
  *
  * For every read the call returns its candidate regions IN THE ORDER the reference's
  * append_alignments visits them (region order of bwa_mem_mate_sw).  n_regs[r] regions of read r
- * start at alns[sum(n_regs[0..r))].  A record with keep == 0 was dropped by the reference's clip /
+ * start at cands[sum(n_regs[0..r))].  A record with keep == 0 was dropped by the reference's clip /
  * edit-distance filters (src/align.c:1017-1024) and must be ignored; the others carry exactly the
  * fields alignment_to_sam_rec stores in a SAMRecord (src/align.c:915-956).
  *
  * stage: 1 = stop after mem_align1_core, 2 = stop after mate rescue (regions only, via regs_dbg),
- *        3 = full.  regs_dbg (optional) receives 18 int64 per region: rb,re,qb,qe,rid,score,truesc,
+ *        3 = full.  regs_dbg (want_regs) holds 18 int64 per region: rb,re,qb,qe,rid,score,truesc,
  *        sub,csub,sub_n,w,seedcov,secondary,seedlen0,n_comp,is_alt,frac_rep(float bits),secondary_all.
  */
-typedef struct {
+typedef struct {            /* one candidate region of one read: 56-byte wire record */
 	int64_t pos;            /* 0-based leftmost reference position on contig rid */
+	double em_score;        /* src/align.c:904-907 */
 	int32_t rid;
-	int32_t is_rev;
 	int32_t NM;
-	int32_t n_cigar;
 	int32_t score;          /* SW score of the region (mem_alnreg_t.score) */
 	int32_t mapq;           /* mem_approx_mapq_se_insist (src/align.c:959-984) */
 	int32_t score_mapq;     /* src/align.c:909-912 */
 	int32_t clip;
 	int32_t clip_edit_dist;
-	int32_t keep;
-	double em_score;        /* src/align.c:904-907 */
-	uint32_t cigar[64];     /* BAM encoding len<<4|op, op 0..3 = M,I,D,S */
-} emab_aln_t;
+	uint32_t cigar_off;     /* first op in the CIGAR pool; BAM encoding len<<4|op, op 0..3 = M,I,D,S */
+	uint16_t n_cigar;
+	uint8_t is_rev;
+	uint8_t keep;
+} emab_cand_t;
+
+typedef struct {            /* arrays are pinned host memory owned by the ctx, valid until its next call */
+	int64_t n_cands, n_cigar_ops;
+	const int32_t *n_regs;      /* [2*n_pairs] regions per read */
+	const emab_cand_t *cands;   /* [n_cands] (stage 3) */
+	const uint32_t *cigars;     /* [n_cigar_ops] (stage 3) */
+	const int64_t *regs_dbg;    /* [n_cands*18] when want_regs */
+} emab_pairs_result_t;
 
 typedef struct {
 	int64_t extend_cells, global_cells, local_cells;  /* DP cells visited */
@@ -126,9 +134,11 @@ typedef struct {
 } emab_stats_t;
 
 int emab_set_error_rate(emab_ctx_t *ctx, double eps);  /* platform error_rate (src/techs.c:71-127); default 0.001 */
-int emab_align_pairs(emab_ctx_t *ctx, int n_pairs, const uint8_t *seq, const int64_t *off, int stage,
-                     int32_t *n_regs, emab_aln_t *alns, int64_t aln_cap, int64_t *n_alns, int64_t *regs_dbg,
-                     emab_stats_t *stats);
+int emab_align_pairs(emab_ctx_t *ctx, int n_pairs, const uint8_t *seq, const int64_t *off, int stage, int want_regs,
+                     emab_pairs_result_t *result, emab_stats_t *stats);
+/* pinned host memory for callers that want their input buffers to take the fast H2D path */
+void *emab_pinned_alloc(uint64_t bytes);
+void emab_pinned_free(void *p);
 
 /* ---- the barcode-cloud EM (src/align.c:410-543) ------------------------------------------------
  * The host groups candidates into clouds and links mates (the SAMDict bookkeeping of
@@ -187,6 +197,11 @@ int emab_session_config(emab_session_t *s, const char *rg, const char *bx_index,
 int emab_sam_header(emab_session_t *s, int argc, const char *const *argv, char **text, uint64_t *len);
 int emab_align_bucket(emab_session_t *s, const char *data, uint64_t len, char **sam, uint64_t *sam_len);
 int emab_align_fastq(emab_session_t *s, const char *d1, uint64_t l1, const char *d2, uint64_t l2, char **sam, uint64_t *sam_len);
+/* -x (multi-input) mode: n buckets with up to `workers` of them in flight on this GPU (each worker is a
+ * CUDA stream + scratch, so one bucket's kernels overlap another's host work and copies).  sam[i] /
+ * sam_len[i] are per bucket, in input order; cloud ids continue in input order. */
+int emab_session_workers(emab_session_t *s, int n_workers);
+int emab_align_buckets(emab_session_t *s, int n, const char *const *data, const uint64_t *len, char **sam, uint64_t *sam_len);
 int emab_session_stats(const emab_session_t *s, emab_run_stats_t *out);
 /* test hook: write "ident<TAB>mate<TAB>chrom<TAB>pos<TAB>gamma(%.17g)" of every chosen alignment of later calls to path (NULL = off) */
 int emab_session_dump_posteriors(emab_session_t *s, const char *path);

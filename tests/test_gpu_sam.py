@@ -104,3 +104,32 @@ def test_em_posteriors_vs_reference(tmp_path):
         n += 1
     assert n == len(want) and n > 15000
     assert worst <= 1e-6, worst
+
+
+def test_multi_bucket_pipeline_matches_serial(tmp_path):
+    """-x mode with several buckets in flight: same bytes as bucket-by-bucket, cloud ids in input order;
+    and the CLI's -x output equals the concatenation."""
+    import ema_b200
+    from tools import synth
+    if not os.path.exists(helpers.ref_bin("bwa")):
+        pytest.skip("oracle/_ref/bwa missing")
+    p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    lines = open(p["bucket"], "rb").read().split(b"\n")
+    lines = [l for l in lines if l]
+    parts = [b"\n".join(lines[i::4]) + b"\n" for i in range(4)] + [b""]
+    s1 = ema_b200.Session(p["fasta"], "10x", threads=8)
+    serial = [s1.align_bucket(d) for d in parts]
+    s2 = ema_b200.Session(p["fasta"], "10x", threads=8)
+    s2.set_workers(3)
+    multi = s2.align_buckets(parts)
+    assert multi == serial
+    assert sum(len(x) for x in multi) > 1_000_000
+    files = []
+    for i, d in enumerate(parts[:4]):
+        f = tmp_path / f"b{i}"
+        f.write_bytes(d)
+        files.append(str(f))
+    out = tmp_path / "x.sam"
+    subprocess.run([CLI, "align", "-x", "-r", p["fasta"], "-p", "10x", "-t", "8", "-o", str(out)] + files, check=True)
+    _, body = split_sam(out.read_bytes())
+    assert b"\n".join(body) + b"\n" == b"".join(serial)
