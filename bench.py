@@ -195,6 +195,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ema_b200
+    from ema_b200 import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: ema_b200 has no CPU path")
@@ -221,7 +222,7 @@ def main():
     data = {}
 
     def bucket_bytes(i):
-        p = buckets[(i * world + rank) % len(buckets)]
+        p = buckets[shard.bucket_for_step(i, rank, world, len(buckets))]
         if p not in data:
             data[p] = open(p, "rb").read()
         return data[p]
