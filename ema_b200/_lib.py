@@ -130,6 +130,38 @@ def extend_batch(ctx: Context, qs, ts, h0, w=100, end_bonus=5, zdrop=100):
     return out, cells.value
 
 
+def set_sw_mode(ctx: Context, mode: int):
+    """0 = one thread per task (ksw_lanes.cuh, default), 1 = one warp per task (ksw_warp.cuh)."""
+    _check(lib().emab_set_sw_mode(ctx._h, mode))
+
+
+def extend_resident_load(ctx: Context, q2d: np.ndarray, t2d: np.ndarray, h0):
+    """Upload n fixed-length tasks (q2d[n,qlen], t2d[n,tlen]) once for emab_extend_resident_run."""
+    n = q2d.shape[0]
+    q = np.ascontiguousarray(q2d, dtype=np.uint8).reshape(-1)
+    t = np.ascontiguousarray(t2d, dtype=np.uint8).reshape(-1)
+    qo = np.arange(n + 1, dtype=np.int64) * q2d.shape[1]
+    to = np.arange(n + 1, dtype=np.int64) * t2d.shape[1]
+    h0 = np.ascontiguousarray(h0, dtype=np.int32)
+    _check(lib().emab_extend_resident_load(ctx._h, n, _p(q, C.c_uint8), _p(qo, C.c_int64), _p(t, C.c_uint8), _p(to, C.c_int64), _p(h0, C.c_int32)))
+    return n
+
+
+def extend_resident_run(ctx: Context, n, reps=1, w=100, end_bonus=5, zdrop=100, want_out=True):
+    """-> (out[n,6] or None, visited cells per launch, device ms per launch)"""
+    out = np.zeros((n, 6), dtype=np.int32) if want_out else None
+    cells = C.c_int64(0)
+    _check(lib().emab_extend_resident_run(ctx._h, w, end_bonus, zdrop, reps, _p(out, C.c_int32) if want_out else None, C.byref(cells)))
+    return out, cells.value, ctx.last_kernel_ms / reps
+
+
+def int_peak(ctx: Context, kind: int, iters: int = 2000):
+    """Integer-pipe microbenchmark -> (1e9 lane-instructions/s, ms)"""
+    g, ms = C.c_double(0), C.c_double(0)
+    _check(lib().emab_int_peak(ctx._h, kind, iters, C.byref(g), C.byref(ms)))
+    return g.value, ms.value
+
+
 def global_batch(ctx: Context, qs, ts, ws, max_cigar=64):
     """ksw_global2 over a batch -> (out[n,2] = score,n_cigar ; cigar[n,max_cigar] ; cells)"""
     q, qo = _pack(qs)

@@ -1,5 +1,6 @@
 // C ABI of libema_b200.so (include/ema_b200.h): index residency, worker contexts and the
 // kernel-level batch entry points.  Pipeline entry points live in pipeline.cu.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -9,6 +10,7 @@
 #include "fmindex.cuh"
 #include "seed.cuh"
 #include "ksw_warp.cuh"
+#include "ksw_lanes.cuh"
 
 thread_local char emab_errbuf[512] = "";
 
@@ -326,6 +328,38 @@ k_local_batch(int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, co
 	}
 }
 
+
+// ksw_extend2, one thread per task (ksw_lanes.cuh): one-warp blocks, each warp takes 32 tasks of the
+// (size-sorted) order at a time.  Dynamic shared memory = lanes::smem_per_warp(qcap).
+__global__ void __launch_bounds__(32)
+k_extend_lanes(int n, const int32_t *order, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff, const int32_t *h0,
+               int w, int end_bonus, int zdrop, int32_t *out, unsigned long long *counters, int qcap)
+{
+	extern __shared__ uint32_t lanes_smem[];
+	const int lane = threadIdx.x;
+	uint32_t *eh = lanes_smem + lane;
+	unsigned long long visited = 0;
+	for (;;) {
+		unsigned long long b = 0;
+		if (lane == 0) b = atomicAdd(&counters[1], 32ull);
+		b = __shfl_sync(FULL_MASK, b, 0);
+		if (b >= (unsigned long long)n) break;
+		const int slot = (int)b + lane;
+		const bool valid = slot < n;
+		const int i = valid ? (order ? order[slot] : slot) : 0;
+		const int ql = valid ? (int)(qoff[i + 1] - qoff[i]) : 0, tl = valid ? (int)(toff[i + 1] - toff[i]) : 0;
+		lanes::BytesFetch qf{q + qoff[i], 1}, tf{t + toff[i], 1};
+		const ExtResult r = lanes::extend(eh, valid, ql, tl, valid ? h0[i] : 1, w, end_bonus, zdrop, qf, tf, visited);
+		if (valid) {
+			int32_t *o = out + (size_t)i * 6;
+			o[0] = r.score; o[1] = r.qle; o[2] = r.tle; o[3] = r.gtle; o[4] = r.gscore; o[5] = r.max_off;
+		}
+		__syncwarp();
+	}
+	for (int d = 16; d; d >>= 1) visited += __shfl_xor_sync(FULL_MASK, visited, d);
+	if (lane == 0 && visited) atomicAdd(&counters[0], visited);
+}
+
 static int check_lengths(int n, const int64_t *qoff, const int64_t *toff, int max_t)
 {
 	for (int i = 0; i < n; ++i) {
@@ -349,6 +383,52 @@ static int upload_sw_inputs(emab_ctx *c, int n, const uint8_t *q, const int64_t 
 	return EMAB_OK;
 }
 
+
+extern "C" int emab_set_sw_mode(emab_ctx_t *c, int mode)
+{
+	if (!c || mode < 0 || mode > 1) return EMAB_ERR_ARG;
+	c->sw_mode = mode;
+	return EMAB_OK;
+}
+
+// size-sorted task order (similar tasks share a warp: rows advance together) + the widest query
+static int prepare_lanes(emab_ctx *c, int n, const int64_t *qoff, const int64_t *toff, const int32_t *h0, int *qcap)
+{
+	std::vector<int32_t> order(n);
+	std::vector<uint64_t> key(n);
+	int qmax = 1;
+	for (int i = 0; i < n; ++i) {
+		const int64_t ql = qoff[i + 1] - qoff[i], tl = toff[i + 1] - toff[i];
+		if (h0[i] + ql * opt::a > lanes::MAX_SCORE) { snprintf(emab_errbuf, sizeof emab_errbuf, "task %d: h0 + qlen*a exceeds %d (12-bit DP field of the thread-per-task kernel)", i, lanes::MAX_SCORE); return EMAB_ERR_ARG; }
+		if (ql > qmax) qmax = (int)ql;
+		key[i] = (uint64_t)tl << 40 | (uint64_t)ql << 20 | (uint64_t)(h0[i] & 0xfffff);
+		order[i] = i;
+	}
+	std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] != key[b] ? key[a] > key[b] : a < b; });
+	TRY(upload(c, c->b[9], order.data(), (size_t)n * 4));
+	CUDA_TRY(cudaStreamSynchronize(c->stream));  // `order` is a local
+	*qcap = qmax;
+	return EMAB_OK;
+}
+
+static int launch_extend_lanes(emab_ctx *c, int n, int qcap, int w, int end_bonus, int zdrop)
+{
+	const size_t smem = lanes::smem_per_warp(qcap);
+	static size_t configured = 0;
+	if (smem > configured) {
+		CUDA_TRY(cudaFuncSetAttribute(k_extend_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+		configured = 227 * 1024;
+	}
+	int per_sm = (int)((227 * 1024) / (smem + 1024));  // 1 KB per block is reserved by the driver
+	per_sm = per_sm > 32 ? 32 : (per_sm < 1 ? 1 : per_sm);
+	int grid = c->n_sm * per_sm;
+	const int need = (n + 31) / 32;
+	if (grid > need) grid = need;
+	k_extend_lanes<<<grid, 32, smem, c->stream>>>(n, c->b[9].as<int32_t>(), c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(),
+	                                              c->b[3].as<int64_t>(), c->b[4].as<int32_t>(), w, end_bonus, zdrop, c->b[5].as<int32_t>(), c->d_counters, qcap);
+	return EMAB_OK;
+}
+
 extern "C" int emab_extend_batch(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
                                  const int32_t *h0, int w, int end_bonus, int zdrop, int32_t *out, int64_t *cells)
 {
@@ -360,7 +440,11 @@ extern "C" int emab_extend_batch(emab_ctx_t *c, int n, const uint8_t *q, const i
 	TRY(upload(c, c->b[4], h0, (size_t)n * 4));
 	TRY(c->b[5].ensure((size_t)n * 24));
 	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+	int qcap = 0;
+	if (c->sw_mode == 0) TRY(prepare_lanes(c, n, qoff, toff, h0, &qcap));
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+	if (c->sw_mode == 0) TRY(launch_extend_lanes(c, n, qcap, w, end_bonus, zdrop));
+	else
 	k_extend_batch<<<sw_grid(c), SW_WARPS * 32, 0, c->stream>>>(n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(), c->b[3].as<int64_t>(),
 	                                                             c->b[4].as<int32_t>(), w, end_bonus, zdrop, c->b[5].as<int32_t>(), c->d_counters);
 	c->last_launches = 1;
@@ -382,6 +466,7 @@ extern "C" int emab_extend_resident_load(emab_ctx_t *c, int n, const uint8_t *q,
 	TRY(upload_sw_inputs(c, n, q, qoff, t, toff));
 	TRY(upload(c, c->b[4], h0, (size_t)n * 4));
 	TRY(c->b[5].ensure((size_t)n * 24));
+	TRY(prepare_lanes(c, n, qoff, toff, h0, &c->res_qcap));
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	c->res_n = n;
 	return EMAB_OK;
@@ -395,6 +480,8 @@ extern "C" int emab_extend_resident_run(emab_ctx_t *c, int w, int end_bonus, int
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
 	for (int r = 0; r < reps; ++r) {
 		CUDA_TRY(cudaMemsetAsync(c->d_counters + 1, 0, 8, c->stream));
+		if (c->sw_mode == 0) TRY(launch_extend_lanes(c, n, c->res_qcap, w, end_bonus, zdrop));
+		else
 		k_extend_batch<<<sw_grid(c), SW_WARPS * 32, 0, c->stream>>>(n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(), c->b[3].as<int64_t>(),
 		                                                             c->b[4].as<int32_t>(), w, end_bonus, zdrop, c->b[5].as<int32_t>(), c->d_counters);
 	}

@@ -73,6 +73,7 @@ struct emab_ctx {
 	unsigned long long *d_counters = nullptr;  // 8 x u64 instrumentation counters
 	int n_sm = 148;
 	// resident SW microbench inputs
-	int res_n = 0;
+	int res_n = 0, res_qcap = 0;
+	int sw_mode = 0;         // 0 = thread-per-task SW kernels (ksw_lanes.cuh), 1 = warp-per-task (ksw_warp.cuh)
 	bool consts_ready = false;
 };

@@ -70,10 +70,18 @@ int emab_global_batch(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *q
 int emab_local_batch(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
                      int32_t *out, int64_t *cells);
 
+/* which kernel family serves the batch calls: 0 (default) = one thread per task, 32 tasks per warp advancing
+ * row by row (ksw_lanes.cuh); 1 = one warp per task (ksw_warp.cuh).  Results are identical. */
+int emab_set_sw_mode(emab_ctx_t *ctx, int mode);
+
 /* device-resident variant used by bench.py for the kernel-only number: uploads once, then
  * emab_extend_resident_run launches the kernel `reps` times on resident inputs. */
 int emab_extend_resident_load(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff, const int32_t *h0);
 int emab_extend_resident_run(emab_ctx_t *ctx, int w, int end_bonus, int zdrop, int reps, int32_t *out, int64_t *cells);
+
+/* Integer-pipe throughput of this GPU (the denominator of the SW roofline): kind 0 add, 1 max, 2 DPX viaddmax,
+ * 3 DPX vimax3, 4 mad (FMA pipe), 5 add+mad on both pipes, 6 viaddmax.s16x2.  Result in 1e9 lane-instructions/s. */
+int emab_int_peak(emab_ctx_t *ctx, int kind, int iters, double *gops_per_s, double *ms);
 
 /* ---- FM index --------------------------------------------------------------------------------
  * emab_sa_batch      = bwt_sa (bwa/bwt.c:86) for n SA indices; mode 0 = dense SA, 1 = LF walk

@@ -112,6 +112,29 @@ int hs_collect_intv(void *h_, int len, const uint8_t *seq, int64_t *out, int max
 	return ovf ? -1 : n;
 }
 
+// the nested (reference-shaped) form, for cross-checking the flattened one; *touches = Occ-block loads
+int hs_collect_intv_nested(void *h_, int len, const uint8_t *seq, int64_t *out, int max, int64_t *touches)
+{
+	HostIndex *h = (HostIndex *)h_;
+	std::vector<Intv> mem(EMAB_MAX_INTV), b0(EMAB_MAX_READ_LEN + 1), b1(EMAB_MAX_READ_LEN + 1);
+	Fm fm{h->d, 0};
+	int ovf = 0;
+	int n = collect_intv_nested(fm, len, seq, mem.data(), EMAB_MAX_INTV, b0.data(), b1.data(), &ovf);
+	for (int i = 0; i < n && i < max; ++i) { out[i*4] = mem[i].x0; out[i*4+1] = mem[i].x1; out[i*4+2] = mem[i].x2; out[i*4+3] = mem[i].info; }
+	if (touches) *touches = fm.touches;
+	return ovf ? -1 : n;
+}
+
+int64_t hs_collect_intv_touches(void *h_, int len, const uint8_t *seq)
+{
+	HostIndex *h = (HostIndex *)h_;
+	std::vector<Intv> mem(EMAB_MAX_INTV), b0(EMAB_MAX_READ_LEN + 1), b1(EMAB_MAX_READ_LEN + 1);
+	Fm fm{h->d, 0};
+	int ovf = 0;
+	collect_intv(fm, len, seq, mem.data(), EMAB_MAX_INTV, b0.data(), b1.data(), &ovf);
+	return fm.touches;
+}
+
 struct ReadWork {
 	std::vector<Intv> intv, b0, b1;
 	std::vector<Seed> w_seeds, seeds;

@@ -24,9 +24,12 @@ def emab():
     return ema_b200
 
 
-@pytest.fixture(scope="module")
-def ctx(emab):
-    return emab.Context()
+@pytest.fixture(scope="module", params=[0, 1], ids=["lanes", "warp"])
+def ctx(emab, request):
+    """both SW kernel families: one thread per task (ksw_lanes.cuh) and one warp per task (ksw_warp.cuh)"""
+    c = emab.Context()
+    emab.set_sw_mode(c, request.param)
+    return c
 
 
 @pytest.fixture(scope="module")
@@ -60,9 +63,15 @@ def test_extend_edge_cases(emab, ctx, port_lib):
     ts = [np.array([0], np.uint8), np.array([0, 1, 2, 3] * 100, np.uint8), np.full(700, 2, np.uint8), np.full(50, 4, np.uint8),
           np.array([1] * 64, np.uint8), np.array([1] * 400, np.uint8), np.array([3], np.uint8)]
     h0 = np.array([1, 19, 150, 30, 5, 7, 9], np.int32)
-    a, _ = emab.extend_batch(ctx, qs, ts, h0)
-    b, _ = helpers.sw_extend(port_lib, "orc", qs, ts, h0)
-    assert np.array_equal(a, b)
+    a, ca = emab.extend_batch(ctx, qs, ts, h0)
+    b, cb = helpers.sw_extend(port_lib, "orc", qs, ts, h0)
+    assert np.array_equal(a, b) and ca == cb
+    # ragged batch sizes around the 32-task warp granularity, mixed lengths in one warp
+    for n in (1, 31, 33, 65):
+        qs2, ts2, h02 = helpers.random_extend_tasks(n, 7 + n, max_q=256)
+        a, ca = emab.extend_batch(ctx, qs2, ts2, h02)
+        b, cb = helpers.sw_extend(port_lib, "orc", qs2, ts2, h02)
+        assert np.array_equal(a, b) and ca == cb
     out, cells = emab.extend_batch(ctx, [], [], np.zeros(0, np.int32))
     assert out.shape == (0, 6) and cells == 0
     with pytest.raises(emab.EmabError):

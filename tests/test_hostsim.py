@@ -62,6 +62,34 @@ def test_seeding_golden(hs):
         pos += n
 
 
+def test_seeding_flat_equals_nested(hs):
+    """The device kernel's flattened one-extend-per-iteration form of mem_collect_intv against the
+    reference-shaped nested form: same intervals and the same number of Occ-block loads, on reads
+    with repeats, N bases and every length from 1 up."""
+    hi = C.c_void_p(hs.hs_index_load(os.path.join(G, "tiny_rep", "ref.fa").encode()))
+    hs.hs_collect_intv_touches.restype = C.c_int64
+    lines = helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x"))
+    rng = np.random.default_rng(11)
+    reads = []
+    for f in lines[:200]:
+        for s in (helpers.nt4(f[2]), helpers.nt4(f[4])):
+            reads.append(s)
+            t = s.copy()
+            t[rng.integers(0, len(t), size=int(rng.integers(1, 6)))] = 4
+            reads.append(t)
+            reads.append(np.ascontiguousarray(s[:int(rng.integers(1, len(s)))]))
+    reads.append(np.full(30, 4, np.uint8))
+    reads.append(np.zeros(150, np.uint8))
+    for s in reads:
+        s = np.ascontiguousarray(s)
+        a, b = np.zeros((256, 4), np.int64), np.zeros((256, 4), np.int64)
+        tb = C.c_int64()
+        na = hs.hs_collect_intv(hi, len(s), _p(s, C.c_uint8), _p(a, C.c_int64), 256)
+        nb = hs.hs_collect_intv_nested(hi, len(s), _p(s, C.c_uint8), _p(b, C.c_int64), 256, C.byref(tb))
+        assert na == nb and np.array_equal(a, b)
+        assert hs.hs_collect_intv_touches(hi, len(s), _p(s, C.c_uint8)) == tb.value
+
+
 def _regs(lib, fn, idx, s, *extra):
     rg = np.zeros((4096, 18), np.int64)
     n = getattr(lib, fn)(idx, len(s), _p(s, C.c_uint8), _p(rg, C.c_int64), 4096, *extra)
