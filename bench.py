@@ -145,13 +145,13 @@ def index_load_time(fa, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--data-dir", default=os.environ.get("EMAB_DATA", "/tmp/emab_data"))
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
-    ap.add_argument("--workers", type=int, default=3, help="buckets in flight per GPU in the end-to-end pass")
+    ap.add_argument("--workers", type=int, default=6, help="buckets in flight per GPU in the end-to-end pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -232,7 +232,8 @@ def main():
     sess.set_workers(args.workers)
     for i in range(args.warmup):
         sess.align_bucket(bucket_bytes(i))
-    sess.align_buckets([bucket_bytes(i) for i in range(args.warmup)], keep_text=False)
+    # warm every worker context (device scratch and pinned buffers are grow-only and allocated on first use)
+    sess.align_buckets([bucket_bytes(i % (args.warmup + args.steps)) for i in range(max(args.warmup, 2 * args.workers))], keep_text=False)
     sampler = ClockSampler(local_rank)
     # ---- pass A: one bucket at a time; device time of the kernel sequence (inputs resident when the
     #      CUDA-event region starts) gives `value`, the per-kernel times give the roofline
@@ -260,6 +261,8 @@ def main():
     barrier()
     wall = time.time() - t_start
     launches_e2e = sess.stats.launches
+    stB = sess.stats
+    e2e_stage = {k: getattr(stB, k) / args.steps for k in ("parse_ms", "encode_ms", "align_ms", "kernel_ms", "cloud_ms", "flatten_ms", "em_ms", "format_ms")}
     clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([wall, kern_ms], dtype=torch.float64, device="cuda")
@@ -284,7 +287,7 @@ def main():
             "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic", "config": config,
             "e2e": {"value": total_pairs / wall, "unit": "pairs/s", "h2d_bytes_per_step": agg["h2d_bytes"] / K, "d2h_bytes_per_step": agg["d2h_bytes"] / K,
                     "host_bucket_text_bytes_per_step": len(bucket_bytes(args.warmup)), "sam_bytes_per_step": sum(sam_lens) / K,
-                    "buckets_in_flight": args.workers},
+                    "buckets_in_flight": args.workers, "stage_ms_per_step_summed_over_workers": e2e_stage},
             "gpu_launches": launches + launches_e2e,
             "clocks": clocks,
             "roofline": {"kernel": "k_seed (SMEM seeding, mem_collect_intv)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,

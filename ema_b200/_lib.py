@@ -255,7 +255,7 @@ def align_pairs(ctx: Context, reads, stage=3, want_regs=False):
 class RunStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("parse_ms", "encode_ms", "align_ms", "kernel_ms", "cloud_ms", "flatten_ms", "em_ms",
                                           "em_kernel_ms", "format_ms", "total_ms", "ms_seed", "ms_chain", "ms_align1", "ms_rescue",
-                                          "ms_finalize")] + [("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)] + \
+                                          "ms_finalize", "gate_wait_ms")] + [("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)] + \
                [(n, C.c_int64) for n in ("n_pairs", "n_barcodes", "n_cands", "n_clouds", "sam_bytes", "extend_cells", "global_cells",
                                          "local_cells", "occ_touches")] + [("launches", C.c_int32), ("pad", C.c_int32)]
 

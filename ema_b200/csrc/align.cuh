@@ -35,13 +35,16 @@ EMAB_HD int cal_max_gap(int qlen)
 struct U64Less { EMAB_HD bool operator()(uint64_t a, uint64_t b) const { return a < b; } };
 
 // ---------------------------------------------------------------------------------------------
-// mem_chain2aln: extend the seeds of one chain into alignment regions appended to av[*n_av..]
+// mem_chain2aln (bwa/bwamem.c:658-812) in pieces.  The pieces are shared by two drivers: chain2aln below
+// (one work item runs the whole function, DP calls delegated to a policy object: the warp-per-read kernels
+// and the host build of tests/hostsim) and the thread-per-read state machine of align_lanes.cuh, where
+// the DP calls of 32 reads are gathered and run together by the inter-task kernel of ksw_lanes.cuh.
 // ---------------------------------------------------------------------------------------------
-template <class DP>
-EMAB_HD void chain2aln(const DevIndex &ix, DP &dp, int l_query, const uint8_t *query, const Chain &c, const Seed *seeds,
-                       uint64_t *srt, Reg *av, int *n_av)
+struct ChainWin { int64_t rmax0, rmax1; };
+
+// the reference window of a chain (bwa/bwamem.c:668-685)
+EMAB_HD ChainWin chain_window(const DevIndex &ix, int l_query, const Chain &c, const Seed *seeds)
 {
-	if (c.n == 0) return;
 	const int64_t l_pac = ix.l_pac;
 	int64_t rmax0 = l_pac << 1, rmax1 = 0;
 	for (int i = 0; i < c.n; ++i) {
@@ -59,91 +62,186 @@ EMAB_HD void chain2aln(const DevIndex &ix, DP &dp, int l_query, const uint8_t *q
 	}
 	int rid;
 	bns_clamp(ix, &rmax0, seeds[0].rbeg, &rmax1, &rid);  // bns_fetch_seq's window (bwa/bwamem.c:685)
+	ChainWin w; w.rmax0 = rmax0; w.rmax1 = rmax1;
+	return w;
+}
 
+// seeds are visited by decreasing score (bwa/bwamem.c:687-690)
+EMAB_HD void chain_sort_seeds(const Chain &c, const Seed *seeds, uint64_t *srt)
+{
 	for (int i = 0; i < c.n; ++i) srt[i] = (uint64_t)seeds[i].score << 32 | (uint64_t)i;
 	ks_introsort((size_t)c.n, srt, U64Less());
+}
 
+// bwa/bwamem.c:693-729: is seed srt[k] worth extending given the regions found so far?  Clears srt[k] if not.
+EMAB_HD bool seed_wants_extension(int l_query, const Chain &c, const Seed *seeds, uint64_t *srt, int k, const Reg *av, int n_av)
+{
+	const Seed &s = seeds[(uint32_t)srt[k]];
+	int i;
+	for (i = 0; i < n_av; ++i) {  // has this seed been covered by an earlier extension?
+		const Reg &p = av[i];
+		if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+		if (s.len - p.seedlen0 > .1 * l_query) continue;
+		int qd = s.qbeg - p.qb;
+		int64_t rd = s.rbeg - p.rb;
+		int max_gap = cal_max_gap(qd < rd ? qd : (int)rd);
+		int w = max_gap < p.w ? max_gap : p.w;
+		if (qd - rd < w && rd - qd < w) break;
+		qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+		max_gap = cal_max_gap(qd < rd ? qd : (int)rd);
+		w = max_gap < p.w ? max_gap : p.w;
+		if (qd - rd < w && rd - qd < w) break;
+	}
+	if (i < n_av) {  // (almost) contained: extend only if an overlapping seed suggests a different alignment
+		for (i = k + 1; i < c.n; ++i) {
+			if (srt[i] == 0) continue;
+			const Seed &t = seeds[(uint32_t)srt[i]];
+			if (t.len < s.len * .95) continue;
+			if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+			if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+		}
+		if (i == c.n) { srt[k] = 0; return false; }
+	}
+	return true;
+}
+
+struct SeedExt {  // the region being built from one seed
+	Reg a;
+	int aw0, aw1, sc0;
+};
+
+EMAB_HD void seed_begin(const Chain &c, SeedExt &e)
+{
+	Reg &a = e.a;
+	a.rb = a.re = 0; a.qb = a.qe = 0; a.sub = a.csub = a.sub_n = 0; a.seedcov = 0; a.secondary = 0; a.n_comp = 0;
+	e.aw0 = opt::w; e.aw1 = opt::w; e.sc0 = 0;
+	a.w = opt::w;
+	a.score = a.truesc = -1;
+	a.rid = c.rid;
+	a.seedlen0 = 0; a.frac_rep = 0;
+}
+
+// One ksw_extend2 call of mem_chain2aln, as data: query base j = query[q0 + j*qstep], target base i =
+// ref[t0 + i*tstep].
+struct ExtTask { int q0, qstep, qlen; int64_t t0; int tstep, tlen, w, end_bonus, h0; };
+
+EMAB_HD ExtTask left_task(const Seed &s, const ChainWin &cw, int t)
+{  // reversed query prefix against the reversed reference prefix (bwa/bwamem.c:741-757)
+	ExtTask x;
+	x.q0 = s.qbeg - 1; x.qstep = -1; x.qlen = s.qbeg;
+	x.t0 = s.rbeg - 1; x.tstep = -1; x.tlen = (int)(s.rbeg - cw.rmax0);
+	x.w = opt::w << t; x.end_bonus = opt::pen_clip5; x.h0 = s.len * opt::a;
+	return x;
+}
+
+// consume one left try; returns true if the band must be doubled and the extension redone (MAX_BAND_TRY 2)
+EMAB_HD bool left_try_done(SeedExt &e, const ExtResult &r, int t)
+{
+	const int prev = e.a.score;
+	e.aw0 = opt::w << t;
+	e.a.score = r.score;
+	if (e.a.score == prev || r.max_off < (e.aw0 >> 1) + (e.aw0 >> 2)) return false;
+	return t + 1 < 2;
+}
+
+EMAB_HD void left_finish(const Seed &s, SeedExt &e, const ExtResult &r)
+{
+	Reg &a = e.a;
+	if (r.gscore <= 0 || r.gscore <= a.score - opt::pen_clip5) {  // local extension
+		a.qb = s.qbeg - r.qle; a.rb = s.rbeg - r.tle;
+		a.truesc = a.score;
+	} else {  // to-end extension
+		a.qb = 0; a.rb = s.rbeg - r.gtle;
+		a.truesc = r.gscore;
+	}
+}
+
+EMAB_HD void left_none(const Seed &s, SeedExt &e) { e.a.score = e.a.truesc = s.len * opt::a; e.a.qb = 0; e.a.rb = s.rbeg; }
+
+EMAB_HD ExtTask right_task(int l_query, const Seed &s, const ChainWin &cw, const SeedExt &e, int t)
+{  // bwa/bwamem.c:768-785; h0 is the score after the left extension
+	const int qe = s.qbeg + s.len;
+	const int64_t re = s.rbeg + s.len - cw.rmax0;
+	ExtTask x;
+	x.q0 = qe; x.qstep = 1; x.qlen = l_query - qe;
+	x.t0 = cw.rmax0 + re; x.tstep = 1; x.tlen = (int)(cw.rmax1 - cw.rmax0 - re);
+	x.w = opt::w << t; x.end_bonus = opt::pen_clip3; x.h0 = e.sc0;
+	return x;
+}
+
+EMAB_HD bool right_try_done(SeedExt &e, const ExtResult &r, int t)
+{
+	const int prev = e.a.score;
+	e.aw1 = opt::w << t;
+	e.a.score = r.score;
+	if (e.a.score == prev || r.max_off < (e.aw1 >> 1) + (e.aw1 >> 2)) return false;
+	return t + 1 < 2;
+}
+
+EMAB_HD void right_finish(int l_query, const Seed &s, const ChainWin &cw, SeedExt &e, const ExtResult &r)
+{
+	Reg &a = e.a;
+	const int qe = s.qbeg + s.len;
+	const int64_t re = s.rbeg + s.len - cw.rmax0;
+	if (r.gscore <= 0 || r.gscore <= a.score - opt::pen_clip3) {
+		a.qe = qe + r.qle; a.re = cw.rmax0 + re + r.tle;
+		a.truesc += a.score - e.sc0;
+	} else {
+		a.qe = l_query; a.re = cw.rmax0 + re + r.gtle;
+		a.truesc += r.gscore - e.sc0;
+	}
+}
+
+EMAB_HD void right_none(int l_query, const Seed &s, SeedExt &e) { e.a.qe = l_query; e.a.re = s.rbeg + s.len; }
+
+// bwa/bwamem.c:800-810: seed coverage and bookkeeping, then the region joins av[]
+EMAB_HD void seed_finish(const Chain &c, const Seed *seeds, const Seed &s, SeedExt &e, Reg *av, int *n_av)
+{
+	Reg &a = e.a;
+	a.seedcov = 0;
+	for (int j = 0; j < c.n; ++j) {
+		const Seed &t = seeds[j];
+		if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
+	}
+	a.w = e.aw0 > e.aw1 ? e.aw0 : e.aw1;
+	a.seedlen0 = s.len;
+	a.frac_rep = c.frac_rep;
+	av[(*n_av)++] = a;
+}
+
+// mem_chain2aln: extend the seeds of one chain into alignment regions appended to av[*n_av..]
+template <class DP>
+EMAB_HD void chain2aln(const DevIndex &ix, DP &dp, int l_query, const uint8_t *query, const Chain &c, const Seed *seeds,
+                       uint64_t *srt, Reg *av, int *n_av)
+{
+	if (c.n == 0) return;
+	const ChainWin cw = chain_window(ix, l_query, c, seeds);
+	chain_sort_seeds(c, seeds, srt);
 	for (int k = c.n - 1; k >= 0; --k) {
+		if (!seed_wants_extension(l_query, c, seeds, srt, k, av, *n_av)) continue;
 		const Seed &s = seeds[(uint32_t)srt[k]];
-		int i;
-		for (i = 0; i < *n_av; ++i) {  // has this seed been covered by an earlier extension?
-			const Reg &p = av[i];
-			if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
-			if (s.len - p.seedlen0 > .1 * l_query) continue;
-			int qd = s.qbeg - p.qb;
-			int64_t rd = s.rbeg - p.rb;
-			int max_gap = cal_max_gap(qd < rd ? qd : (int)rd);
-			int w = max_gap < p.w ? max_gap : p.w;
-			if (qd - rd < w && rd - qd < w) break;
-			qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
-			max_gap = cal_max_gap(qd < rd ? qd : (int)rd);
-			w = max_gap < p.w ? max_gap : p.w;
-			if (qd - rd < w && rd - qd < w) break;
-		}
-		if (i < *n_av) {  // (almost) contained: extend only if an overlapping seed suggests a different alignment
-			for (i = k + 1; i < c.n; ++i) {
-				if (srt[i] == 0) continue;
-				const Seed &t = seeds[(uint32_t)srt[i]];
-				if (t.len < s.len * .95) continue;
-				if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
-				if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
-			}
-			if (i == c.n) { srt[k] = 0; continue; }
-		}
-		Reg a;
-		a.rb = a.re = 0; a.qb = a.qe = 0; a.sub = a.csub = a.sub_n = 0; a.seedcov = 0; a.secondary = 0; a.n_comp = 0;
-		int aw0 = opt::w, aw1 = opt::w;
-		a.w = opt::w;
-		a.score = a.truesc = -1;
-		a.rid = c.rid;
-		if (s.qbeg) {  // left extension: reversed query prefix against the reversed reference prefix
+		SeedExt e;
+		seed_begin(c, e);
+		if (s.qbeg) {  // left extension
 			ExtResult r{};
-			const int tlen = (int)(s.rbeg - rmax0);
-			for (int t = 0; t < 2; ++t) {  // MAX_BAND_TRY
-				int prev = a.score;
-				aw0 = opt::w << t;
-				r = dp.extend(query, s.qbeg - 1, -1, s.qbeg, s.rbeg - 1, -1, tlen, aw0, opt::pen_clip5, s.len * opt::a);
-				a.score = r.score;
-				if (a.score == prev || r.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
+			for (int t = 0;; ++t) {
+				const ExtTask x = left_task(s, cw, t);
+				r = dp.extend(query, x.q0, x.qstep, x.qlen, x.t0, x.tstep, x.tlen, x.w, x.end_bonus, x.h0);
+				if (!left_try_done(e, r, t)) break;
 			}
-			if (r.gscore <= 0 || r.gscore <= a.score - opt::pen_clip5) {  // local extension
-				a.qb = s.qbeg - r.qle; a.rb = s.rbeg - r.tle;
-				a.truesc = a.score;
-			} else {  // to-end extension
-				a.qb = 0; a.rb = s.rbeg - r.gtle;
-				a.truesc = r.gscore;
-			}
-		} else { a.score = a.truesc = s.len * opt::a; a.qb = 0; a.rb = s.rbeg; }
+			left_finish(s, e, r);
+		} else left_none(s, e);
 		if (s.qbeg + s.len != l_query) {  // right extension
 			ExtResult r{};
-			const int sc0 = a.score;
-			const int qe = s.qbeg + s.len;
-			const int64_t re = s.rbeg + s.len - rmax0;
-			const int tlen = (int)(rmax1 - rmax0 - re);
-			for (int t = 0; t < 2; ++t) {
-				int prev = a.score;
-				aw1 = opt::w << t;
-				r = dp.extend(query, qe, 1, l_query - qe, rmax0 + re, 1, tlen, aw1, opt::pen_clip3, sc0);
-				a.score = r.score;
-				if (a.score == prev || r.max_off < (aw1 >> 1) + (aw1 >> 2)) break;
+			e.sc0 = e.a.score;
+			for (int t = 0;; ++t) {
+				const ExtTask x = right_task(l_query, s, cw, e, t);
+				r = dp.extend(query, x.q0, x.qstep, x.qlen, x.t0, x.tstep, x.tlen, x.w, x.end_bonus, x.h0);
+				if (!right_try_done(e, r, t)) break;
 			}
-			if (r.gscore <= 0 || r.gscore <= a.score - opt::pen_clip3) {
-				a.qe = qe + r.qle; a.re = rmax0 + re + r.tle;
-				a.truesc += a.score - sc0;
-			} else {
-				a.qe = l_query; a.re = rmax0 + re + r.gtle;
-				a.truesc += r.gscore - sc0;
-			}
-		} else { a.qe = l_query; a.re = s.rbeg + s.len; }
-		a.seedcov = 0;
-		for (int j = 0; j < c.n; ++j) {
-			const Seed &t = seeds[j];
-			if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
-		}
-		a.w = aw0 > aw1 ? aw0 : aw1;
-		a.seedlen0 = s.len;
-		a.frac_rep = c.frac_rep;
-		av[(*n_av)++] = a;
+			right_finish(l_query, s, cw, e, r);
+		} else right_none(l_query, s, e);
+		seed_finish(c, seeds, s, e, av, n_av);
 	}
 }
 

@@ -576,14 +576,19 @@ k_smem_batch(DevIndex ix, int n, const uint8_t *seq, const int64_t *off, Intv *i
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned touches = 0;
-	if (r < n) {
+	{   // every lane of the warp runs collect_intv (it votes); lanes past the end get an empty read
+		const bool valid = r < n;
+		const int rr = valid ? r : 0;
 		Fm fm{ix, 0};
-		const int len = (int)(off[r + 1] - off[r]);
-		Intv *buf0 = scratch + (size_t)r * 2 * (EMAB_MAX_READ_LEN + 1);
+		const int len = valid ? (int)(off[rr + 1] - off[rr]) : 0;
+		Intv *buf0 = scratch + (size_t)rr * 2 * (EMAB_MAX_READ_LEN + 1);
 		int ovf = 0;
-		n_intv[r] = collect_intv(fm, len, seq + off[r], intv + (size_t)r * max_intv, max_intv, buf0, buf0 + EMAB_MAX_READ_LEN + 1, &ovf);
-		if (ovf) *overflow = 1;
-		touches = fm.touches;
+		const int ni = collect_intv(fm, len, seq + off[rr], intv + (size_t)rr * max_intv, max_intv, buf0, buf0 + EMAB_MAX_READ_LEN + 1, &ovf);
+		if (valid) {
+			n_intv[r] = ni;
+			if (ovf) *overflow = 1;
+			touches = fm.touches;
+		}
 	}
 	// one atomic per warp
 	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(FULL_MASK, touches, d);

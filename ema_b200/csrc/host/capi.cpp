@@ -52,7 +52,7 @@ int emab_session_config(emab_session_t *h, const char *rg, const char *bx_index,
 	if (rg) {  // validate_read_group (src/main.c:73-76)
 		std::string r(rg);
 		if (r.rfind("@RG\t", 0) != 0 || r.find("\tID:") == std::string::npos) return fail(EMAB_ERR_ARG, "error: malformed read group: '" + r + "'");
-		h->s->rg = r;
+		h->s->set_rg(r);
 	}
 	if (bx_index) h->s->bx_index = bx_index;
 	h->s->apply_opt = apply_opt;

@@ -254,6 +254,7 @@ struct Barcode {
 	std::unordered_map<std::pair<std::string_view, int>, int, KeyHash> dict;
 	std::vector<int> final_;               // records_final
 	std::string sam;
+	std::string bc_str;                    // decode_bc(bc), printed in every BX tag of this barcode
 
 	int find(const Rec &k) const
 	{
@@ -626,19 +627,21 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 	} else o->append("\t*\t0\t0");
 	o->push_back('\t');
 	if (rec && rec->rev) {
-		for (size_t i = read.size(); i-- > 0;) o->push_back(rc(read[i]));
-		o->push_back('\t');
-		for (size_t i = qual.size(); i-- > 0;) o->push_back(qual[i]);
+		const size_t at = o->size(), nr = read.size(), nq = qual.size();
+		o->resize(at + nr + 1 + nq);
+		char *d = &(*o)[at];
+		for (size_t i = 0; i < nr; ++i) d[i] = rc(read[nr - 1 - i]);
+		d[nr] = '\t';
+		for (size_t i = 0; i < nq; ++i) d[nr + 1 + i] = qual[nq - 1 - i];
 	} else { o->append(read); o->push_back('\t'); o->append(qual); }
-	std::string bc_str;
-	decode_bc(s, b.bc, &bc_str);
+	const std::string &bc_str = b.bc_str;
 	if (rec) {
 		char buf[64];
 		o->append("\tNM:i:"); put_int(o, rec->aln->NM);
 		o->append("\tBX:Z:"); o->append(bc_str);
 		if (!s->is_haplotag) { o->push_back('-'); o->append(s->bx_index); }
-		snprintf(buf, sizeof buf, "\tXG:f:%.5g", rec->gamma);
-		o->append(buf);
+		if (rec->gamma == 1.0) o->append("\tXG:f:1");  // what %.5g prints for 1.0: the common case skips snprintf
+		else { snprintf(buf, sizeof buf, "\tXG:f:%.5g", rec->gamma); o->append(buf); }
 		o->append("\tMI:i:"); put_int(o, cloud_base + rec->cloud);
 		o->append("\tXF:i:"); put_int(o, b.clouds[rec->cloud].bad ? 1 : 0);
 	} else {
@@ -647,8 +650,7 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 	}
 	if (s->has_rg) {
 		o->append("\tRG:Z:");
-		size_t p = s->rg.find("ID:");
-		for (size_t i = p + 3; i < s->rg.size() && !isspace((unsigned char)s->rg[i]); ++i) o->push_back(s->rg[i]);
+		o->append(s->rg_id);
 	}
 	if (rec && rec->alt >= 0) {
 		const Rec &a = b.recs[rec->alt];
@@ -674,8 +676,9 @@ static const uint8_t *nt4_table()
 	return t;
 }
 
-static int process_pairs(Session *s, Worker &wk, int ticket, const std::vector<Pair> &pairs, char **out_buf, size_t *out_len, emab_run_stats_t &st)
+static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector<Pair> &pairs, char **out_buf, size_t *out_len, emab_run_stats_t &st)
 {
+	const int ticket = gp.ticket;
 	const double t0 = now_ms();
 	const size_t np = pairs.size();
 	const int nthr = wk.n_threads;
@@ -704,14 +707,19 @@ static int process_pairs(Session *s, Worker &wk, int ticket, const std::vector<P
 	emab_stats_t ds;
 	emab_pairs_result_t res;
 	const double t1 = now_ms();
+	gp.to(PH_DEVICE);
+	const double t1b = now_ms();
 	{
 		int rc = emab_align_pairs(wk.ctx, (int)np, seq, off, 3, 0, &res, &ds);
 		if (rc) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
 	}
 	const int32_t *n_regs = res.n_regs;
 	const emab_cand_t *alns = res.cands;
+	const double t2a = now_ms();
+	gp.to(PH_POST);
 	const double t2 = now_ms();
-	st.align_ms = t2 - t1; st.kernel_ms = ds.kernel_ms; st.launches = ds.launches;
+	st.gate_wait_ms = (t1b - t1) + (t2 - t2a);
+	st.align_ms = t2a - t1b; st.kernel_ms = ds.kernel_ms; st.launches = ds.launches;
 	st.ms_seed = ds.ms_seed; st.ms_chain = ds.ms_chain; st.ms_align1 = ds.ms_align1; st.ms_rescue = ds.ms_rescue; st.ms_finalize = ds.ms_finalize;
 	st.h2d_bytes = ds.h2d_bytes; st.d2h_bytes = ds.d2h_bytes;
 	st.extend_cells = ds.extend_cells; st.global_cells = ds.global_cells; st.local_cells = ds.local_cells; st.occ_touches = ds.occ_touches;
@@ -860,6 +868,8 @@ static int process_pairs(Session *s, Worker &wk, int ticket, const std::vector<P
 			e.gamma.assign(gamma.begin() + entry_cand_off[p], gamma.begin() + entry_cand_off[p] + (int64_t)e.cand_rec.size());
 		}
 		B.choose(s);
+		B.bc_str.clear();
+		decode_bc(s, B.bc, &B.bc_str);
 		B.sam.reserve(B.final_.size() * 520);
 		for (int ri : B.final_) {
 			Rec &best = B.recs[ri];
@@ -921,25 +931,79 @@ static inline std::string_view token(const char *&p, const char *end)
 // lines stably sorted by their first BC_LEN characters.
 static int parse_bucket(Session *s, int nthr, const char *data, size_t len, std::vector<Pair> &pairs, std::string *err)
 {
+	// ---- split into lines: each thread scans one slice of the buffer for '\n'
 	std::vector<std::string_view> lines;
 	{
-		const char *p = data, *end = data + len;
-		while (p < end) {
-			const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
-			const char *e = nl ? nl : end;
-			lines.emplace_back(p, (size_t)(e - p));
-			p = nl ? nl + 1 : end;
+		const int nt = std::max(1, nthr);
+		std::vector<std::vector<size_t>> nl(nt);
+		#pragma omp parallel num_threads(nt)
+		{
+			const int t = omp_get_thread_num(), T = omp_get_num_threads();
+			const size_t lo = len * (size_t)t / (size_t)T, hi = len * (size_t)(t + 1) / (size_t)T;
+			std::vector<size_t> &v = nl[t];
+			const char *p = data + lo, *end = data + hi;
+			while (p < end) {
+				const char *q = (const char *)memchr(p, '\n', (size_t)(end - p));
+				if (!q) break;
+				v.push_back((size_t)(q - data));
+				p = q + 1;
+			}
 		}
+		size_t total = 0;
+		for (auto &v : nl) total += v.size();
+		lines.reserve(total + 1);
+		size_t start = 0;
+		for (auto &v : nl)
+			for (size_t e : v) { lines.emplace_back(data + start, e - start); start = e + 1; }
+		if (start < len) lines.emplace_back(data + start, len - start);
 	}
+	// ---- stable sort by the first BC_LEN characters (strncmp order: special_fastq_record_cmp,
+	// src/align.c:752-757).  The key is the barcode prefix packed big-endian into two words, so comparing
+	// keys is comparing bytes; lines shorter than BC_LEN (malformed) fall back to the byte comparison.
 	const size_t bl = (size_t)s->bc_len;
-	std::stable_sort(lines.begin(), lines.end(), [bl](std::string_view a, std::string_view b) {
-		// strncmp over at most BC_LEN characters (special_fastq_record_cmp, src/align.c:752-757)
-		const size_t n = std::min(bl, std::min(a.size(), b.size()));
-		int c = memcmp(a.data(), b.data(), n);
-		if (c != 0) return c < 0;
-		if (n == bl) return false;
-		return a.size() < b.size();
-	});
+	const size_t n = lines.size();
+	bool short_line = false;
+	for (size_t i = 0; i < n && !short_line; ++i) short_line = lines[i].size() < bl;
+	if (short_line || bl > 16) {
+		std::stable_sort(lines.begin(), lines.end(), [bl](std::string_view a, std::string_view b) {
+			const size_t m = std::min(bl, std::min(a.size(), b.size()));
+			int c = memcmp(a.data(), b.data(), m);
+			if (c != 0) return c < 0;
+			if (m == bl) return false;
+			return a.size() < b.size();
+		});
+	} else {
+		struct Key { uint64_t hi, lo; uint32_t idx; };
+		std::vector<Key> keys(n);
+		#pragma omp parallel for num_threads(nthr) schedule(static)
+		for (size_t i = 0; i < n; ++i) {
+			uint64_t hi = 0, lo = 0;
+			const unsigned char *c = (const unsigned char *)lines[i].data();
+			for (size_t k = 0; k < bl; ++k) {
+				if (k < 8) hi |= (uint64_t)c[k] << (56 - 8 * k);
+				else lo |= (uint64_t)c[k] << (56 - 8 * (k - 8));
+			}
+			keys[i] = Key{hi, lo, (uint32_t)i};
+		}
+		auto less = [](const Key &a, const Key &b) { return a.hi != b.hi ? a.hi < b.hi : (a.lo != b.lo ? a.lo < b.lo : a.idx < b.idx); };
+		// sort slices in parallel, then merge pairwise (idx in the key makes the order total, hence stable)
+		const int nt = std::max(1, std::min(nthr, 16));
+		std::vector<size_t> cut(nt + 1);
+		for (int t = 0; t <= nt; ++t) cut[t] = n * (size_t)t / (size_t)nt;
+		#pragma omp parallel for num_threads(nt) schedule(static, 1)
+		for (int t = 0; t < nt; ++t) std::sort(keys.begin() + cut[t], keys.begin() + cut[t + 1], less);
+		for (int step = 1; step < nt; step <<= 1) {
+			#pragma omp parallel for num_threads(nt) schedule(static, 1)
+			for (int t = 0; t < nt; t += 2 * step) {
+				const int mid = std::min(t + step, nt), hi = std::min(t + 2 * step, nt);
+				if (mid < hi) std::inplace_merge(keys.begin() + cut[t], keys.begin() + cut[mid], keys.begin() + cut[hi], less);
+			}
+		}
+		std::vector<std::string_view> sorted(n);
+		#pragma omp parallel for num_threads(nthr) schedule(static)
+		for (size_t i = 0; i < n; ++i) sorted[i] = lines[keys[i].idx];
+		lines.swap(sorted);
+	}
 	pairs.resize(lines.size());
 	ws_table();
 	int bad = 0;
@@ -964,15 +1028,19 @@ static int parse_bucket(Session *s, int nthr, const char *data, size_t len, std:
 // lines stably sorted by their first BC_LEN characters.
 static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size_t len, char **out, size_t *out_len, emab_run_stats_t &st, std::string *err)
 {
+	GatePass gp(s, ticket);
+	const double tw = now_ms();
+	gp.to(PH_PARSE);
 	const double t0 = now_ms();
 	std::vector<Pair> pairs;
 	int rc = parse_bucket(s, wk.n_threads, data, len, pairs, err);
 	if (rc) { s->take_cloud_base(ticket, 0); return rc; }
 	const double t1 = now_ms();
-	rc = process_pairs(s, wk, ticket, pairs, out, out_len, st);
+	rc = process_pairs(s, wk, gp, pairs, out, out_len, st);
 	if (rc) *err = s->err;
 	st.parse_ms = t1 - t0;
 	st.total_ms += t1 - t0;
+	st.gate_wait_ms += t0 - tw;
 	return rc;
 }
 
@@ -991,7 +1059,12 @@ int align_special_fastq(Session *s, const char *data, size_t len, char **out, si
 int align_special_fastq_multi(Session *s, int n, const char *const *data, const size_t *len, char **out, size_t *out_len)
 {
 	const int W = std::max(1, std::min((int)s->workers.size(), n));
-	const int per = std::max(1, s->n_threads / W);
+	// Buckets walk through three ordered phases (parse+encode | device | clouds+EM+SAM) with at most two
+	// buckets inside a phase, so the host threads are split between two buckets per CPU phase while up to W
+	// buckets are in flight: bucket i's SAM text is written while i+1 runs on the GPU and i+2 is parsed.
+	const int cap = W > 1 ? 2 : 1;
+	for (int k = 0; k < PH_COUNT; ++k) s->gate[k].cap = cap;
+	const int per = std::max(1, s->n_threads / cap);
 	std::vector<int> tickets(n);
 	for (int i = 0; i < n; ++i) { tickets[i] = s->new_ticket(); out[i] = nullptr; out_len[i] = 0; }
 	std::atomic<int> next(0), first_err(0);
@@ -1007,10 +1080,10 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 			if (i >= n) break;
 			emab_run_stats_t st;
 			memset(&st, 0, sizeof st);
-			int rc = first_err.load() ? (s->take_cloud_base(tickets[i], 0), 0) : run_bucket(s, wk, tickets[i], data[i], len[i], &out[i], &out_len[i], st, &errs[w]);
+			int rc = first_err.load() ? (GatePass(s, tickets[i]).to(PH_POST), s->take_cloud_base(tickets[i], 0), 0) : run_bucket(s, wk, tickets[i], data[i], len[i], &out[i], &out_len[i], st, &errs[w]);
 			if (rc) { int z = 0; first_err.compare_exchange_strong(z, rc); if (errs[w].empty()) errs[w] = s->err; }
 			double *a = &sum[w].parse_ms; const double *b = &st.parse_ms;
-			for (int k = 0; k < 15; ++k) a[k] += b[k];
+			for (int k = 0; k < 16; ++k) a[k] += b[k];
 			int64_t *ai = &sum[w].h2d_bytes; const int64_t *bi = &st.h2d_bytes;
 			for (int k = 0; k < 11; ++k) ai[k] += bi[k];
 			sum[w].launches += st.launches;
@@ -1023,7 +1096,7 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 	memset(&s->last, 0, sizeof s->last);
 	for (int w = 0; w < W; ++w) {
 		double *a = &s->last.parse_ms; const double *b = &sum[w].parse_ms;
-		for (int k = 0; k < 15; ++k) a[k] += b[k];
+		for (int k = 0; k < 16; ++k) a[k] += b[k];
 		int64_t *ai = &s->last.h2d_bytes; const int64_t *bi = &sum[w].h2d_bytes;
 		for (int k = 0; k < 11; ++k) ai[k] += bi[k];
 		s->last.launches += sum[w].launches;
@@ -1118,7 +1191,9 @@ int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2
 	if (!err.empty()) { s->err = err; return EMAB_ERR_ARG; }
 	const double t1 = now_ms();
 	s->workers[0].n_threads = s->n_threads;
-	int rc = process_pairs(s, s->workers[0], s->new_ticket(), pairs, out, out_len, s->last);
+	GatePass gp(s, s->new_ticket());
+	gp.to(PH_PARSE);
+	int rc = process_pairs(s, s->workers[0], gp, pairs, out, out_len, s->last);
 	s->last.parse_ms = t1 - t0;
 	s->last.total_ms += t1 - t0;
 	return rc;

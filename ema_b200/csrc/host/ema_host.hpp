@@ -2,6 +2,7 @@
 // batcher, cloud construction, best-alignment choice, duplicate marking and SAM text.
 // Mirrors include/align.h, include/techs.h, include/samrecord.h of the reference; see ema_host.cpp.
 #pragma once
+#include <cctype>
 #include <condition_variable>
 #include <cstdint>
 #include <mutex>
@@ -33,6 +34,29 @@ struct PinnedBuf {  // grow-only pinned host buffer (fast H2D path)
 	~PinnedBuf();
 };
 
+// A pipeline phase that admits buckets strictly in ticket order, at most `cap` of them inside at once.
+// Every ticket passes every phase exactly once (GatePass below guarantees it, error paths included), so
+// ordered admission cannot deadlock and the in-order hand-out of cloud ids never waits on a later bucket.
+struct PhaseGate {
+	std::mutex mu;
+	std::condition_variable cv;
+	int turn = 0, active = 0, cap = 1;
+	void enter(int ticket)
+	{
+		std::unique_lock<std::mutex> g(mu);
+		cv.wait(g, [&] { return turn == ticket && active < cap; });
+		++turn; ++active;
+		cv.notify_all();
+	}
+	void leave()
+	{
+		std::lock_guard<std::mutex> g(mu);
+		--active;
+		cv.notify_all();
+	}
+};
+enum { PH_PARSE = 0, PH_DEVICE = 1, PH_POST = 2, PH_COUNT = 3 };
+
 struct Worker {  // one in-flight bucket: a device context (stream + scratch) and its staging buffers
 	emab_ctx_t *ctx = nullptr;
 	PinnedBuf seq, off;
@@ -46,6 +70,15 @@ struct Session {  // the reference's process globals (src/main.c:23-34, src/alig
 	int bc_len = 16;
 	bool is_haplotag = false;
 	std::string rg = "@RG\tID:rg1\tSM:sample1";  // src/main.c:25
+	std::string rg_id = "rg1";            // the ID: value of rg, printed as RG:Z: (src/samrecord.c:262-270)
+	void set_rg(const std::string &r)
+	{
+		rg = r;
+		rg_id.clear();
+		size_t p = rg.find("ID:");
+		if (p != std::string::npos)
+			for (size_t i = p + 3; i < rg.size() && !isspace((unsigned char)rg[i]); ++i) rg_id.push_back(rg[i]);
+	}
 	bool has_rg = true;
 	std::string bx_index = "1";
 	int apply_opt = 0;
@@ -59,6 +92,7 @@ struct Session {  // the reference's process globals (src/main.c:23-34, src/alig
 	std::mutex mu;
 	std::condition_variable cv;
 	int next_ticket = 0, cloud_turn = 0;
+	PhaseGate gate[PH_COUNT];             // parse+encode | device pipeline | clouds, EM, SAM text
 	int new_ticket() { std::lock_guard<std::mutex> g(mu); return next_ticket++; }
 	int take_cloud_base(int ticket, int n_clouds)
 	{
@@ -73,6 +107,27 @@ struct Session {  // the reference's process globals (src/main.c:23-34, src/alig
 	std::string err;
 	std::string gamma_dump;               // test hook: path for full-precision posteriors of the chosen alignments
 	emab_run_stats_t last{};
+};
+
+// One bucket's walk through the phases: to(ph) leaves the current phase and enters ph (phases are visited
+// in increasing order); the destructor walks through whatever is left so that later tickets are admitted.
+struct GatePass {
+	Session *s; int ticket; int cur = -1;
+	GatePass(Session *s_, int t) : s(s_), ticket(t) {}
+	void to(int ph)
+	{
+		if (cur >= 0) s->gate[cur].leave();
+		for (int k = cur + 1; k < ph; ++k) { s->gate[k].enter(ticket); s->gate[k].leave(); }
+		s->gate[ph].enter(ticket);
+		cur = ph;
+	}
+	~GatePass()
+	{
+		if (cur >= 0) s->gate[cur].leave();
+		for (int k = cur + 1; k < PH_COUNT; ++k) { s->gate[k].enter(ticket); s->gate[k].leave(); }
+	}
+	GatePass(const GatePass &) = delete;
+	GatePass &operator=(const GatePass &) = delete;
 };
 
 int session_open(const char *ref_path, const char *platform, int device, Session **out, std::string *err);

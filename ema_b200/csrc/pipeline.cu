@@ -97,20 +97,24 @@ k_seed(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, Intv *i
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned touches = 0;
-	if (r < n_reads) {
+	{   // every lane of the warp runs collect_intv (it votes); lanes past the end get an empty read
+		const bool valid = r < n_reads;
+		const int rr = valid ? r : 0;
 		Fm fm{ix, 0};
-		const int len = (int)(off[r + 1] - off[r]);
-		Intv *buf0 = scratch + (size_t)r * 2 * (EMAB_MAX_READ_LEN + 1);
-		Intv *mine = intv + (size_t)r * EMAB_MAX_INTV;
+		const int len = valid ? (int)(off[rr + 1] - off[rr]) : 0;
+		Intv *buf0 = scratch + (size_t)rr * 2 * (EMAB_MAX_READ_LEN + 1);
+		Intv *mine = intv + (size_t)rr * EMAB_MAX_INTV;
 		int ovf = 0;
-		const int n = collect_intv(fm, len, seq + off[r], mine, EMAB_MAX_INTV, buf0, buf0 + EMAB_MAX_READ_LEN + 1, &ovf);
-		if (ovf) *err = 3;
-		n_intv[r] = n;
-		int occ = 0;
-		if (len >= opt::min_seed_len)
-			for (int i = 0; i < n; ++i) occ += intv_occ_count(mine[i].x2);
-		occ_cnt[r] = occ;
-		touches = fm.touches;
+		const int n = collect_intv(fm, len, seq + off[rr], mine, EMAB_MAX_INTV, buf0, buf0 + EMAB_MAX_READ_LEN + 1, &ovf);
+		if (valid) {
+			if (ovf) *err = 3;
+			n_intv[r] = n;
+			int occ = 0;
+			if (len >= opt::min_seed_len)
+				for (int i = 0; i < n; ++i) occ += intv_occ_count(mine[i].x2);
+			occ_cnt[r] = occ;
+			touches = fm.touches;
+		}
 	}
 	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(FULL_MASK, touches, d);
 	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(&counters[2], (unsigned long long)touches);

@@ -275,8 +275,16 @@ EMAB_HD int collect_intv(Fm &fm, int len, const uint8_t *seq, Intv *mem, int mem
 				else { x = i < len ? i + 1 : len; st = SD_NEXT; }  // bwa/bwt.c:376-378
 			}
 		}
+		// ---- the one convergent step.  On the device the warp votes here every iteration: the vote is
+		// the reconvergence point that brings all lanes to the bwt_extend below together (without it the
+		// lanes leave the bookkeeping loop one by one and each runs the extend code on its own), and
+		// lanes whose read is finished idle until the whole warp is.  ALL 32 LANES MUST CALL collect_intv.
+#ifdef __CUDA_ARCH__
+		if (!__any_sync(0xffffffffu, st != SD_DONE)) break;
+		if (st == SD_DONE) continue;
+#else
 		if (st == SD_DONE) break;
-		// ---- the one convergent step
+#endif
 		const Intv ok0 = bwt_extend1(fm, ik, c, back);
 		Intv ok = ok0;
 		// ---- consume

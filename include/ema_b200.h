@@ -193,6 +193,7 @@ typedef struct emab_session emab_session_t;
 typedef struct {
 	double parse_ms, encode_ms, align_ms, kernel_ms, cloud_ms, flatten_ms, em_ms, em_kernel_ms, format_ms, total_ms;
 	double ms_seed, ms_chain, ms_align1, ms_rescue, ms_finalize;
+	double gate_wait_ms;                              /* time spent waiting for a pipeline phase (emab_align_buckets) */
 	int64_t h2d_bytes, d2h_bytes;
 	int64_t n_pairs, n_barcodes, n_cands, n_clouds, sam_bytes;
 	int64_t extend_cells, global_cells, local_cells, occ_touches;
