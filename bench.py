@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--data-dir", default=os.environ.get("EMAB_DATA", "/tmp/emab_data"))
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
-    ap.add_argument("--workers", type=int, default=6, help="buckets in flight per GPU in the end-to-end pass")
+    ap.add_argument("--workers", type=int, default=8, help="buckets in flight per GPU in the end-to-end pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

@@ -1,0 +1,189 @@
+// mem_align1_core after chaining (mem_chain2aln over every chain + mem_sort_dedup_patch,
+// bwa/bwamem.c:1081-1117) with ONE THREAD PER READ and the ksw_extend2 calls of the 32 reads of a warp run
+// together by the inter-task kernel of ksw_lanes.cuh.
+//
+// mem_chain2aln is sequential per read (every seed is tested against the regions earlier seeds produced,
+// the right extension starts from the left one's score, a band retry depends on the first try), so the
+// parallelism is across reads.  Each lane walks the reference's control flow as a small state machine built
+// from the same pieces chain2aln uses (align.cuh) and stops whenever it needs a ksw_extend2 result; the
+// warp then runs all pending extensions at once, one per lane, and every lane consumes its result.  A lane
+// that finishes its read takes the next one from a global counter, so lanes always arrive with a task until
+// the bucket runs dry.  Control code therefore costs one instruction slot per 32 reads instead of one per
+// read (the warp-per-read kernel runs it redundantly on all lanes), and the DP costs ~18 instructions per
+// cell instead of ~50.
+#pragma once
+#include "align.cuh"
+#include "ksw_lanes.cuh"
+
+// Thread-scalar ksw_global2 score (bwa/ksw.c:540-622 without the backtrack), used for mem_patch_reg's
+// score-only bwa_gen_cigar2 call (bwa/bwamem.c:448): rare (two colinear regions of one read), so it runs
+// inline on the lane that needs it.  h/e live in local memory.
+struct ScalarPatchDP {
+	const DevIndex &ix;
+	int *err;
+	unsigned long long *cells;
+	EMAB_HD ExtResult extend(const uint8_t *, int, int, int, int64_t, int, int, int, int, int)
+	{
+		*err = 4;  // never reached: mem_sort_dedup_patch only aligns globally
+		return ExtResult{};
+	}
+	EMAB_HD LocResult local(const uint8_t *, int, int64_t, int)
+	{
+		*err = 4;
+		return LocResult{};
+	}
+	EMAB_HD int global(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, uint32_t *cigar, int *n_cigar)
+	{
+		const int NEG = -0x40000000;
+		const int e_del = opt::e_del, e_ins = opt::e_ins, oe_del = opt::oe_del, oe_ins = opt::oe_ins;
+		if (cigar != nullptr || qlen > EMAB_MAX_READ_LEN) { *err = 4; if (n_cigar) *n_cigar = 0; return 0; }
+		int H[EMAB_MAX_READ_LEN + 1], E[EMAB_MAX_READ_LEN + 1];
+		H[0] = 0; E[0] = NEG;
+		for (int j = 1; j <= qlen; ++j) { H[j] = j <= w ? -(opt::o_ins + e_ins * j) : NEG; E[j] = NEG; }
+		unsigned long long visited = 0;
+		for (int i = 0; i < tlen; ++i) {
+			const int tb = ref_base(ix, t0 + (int64_t)i * tstep);
+			const int beg = i > w ? i - w : 0;
+			const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+			int h1 = beg == 0 ? -(opt::o_del + e_del * (i + 1)) : NEG, f = NEG;
+			if (end > beg) visited += end - beg;
+			for (int j = beg; j < end; ++j) {
+				const int M = H[j] + sc_mat(tb, query[q0 + j * qstep]);
+				int e = E[j];
+				H[j] = h1;
+				int h = M >= e ? M : e;
+				h = h >= f ? h : f;
+				h1 = h;
+				int t = M - oe_del;
+				e -= e_del;
+				e = e > t ? e : t;
+				E[j] = e;
+				t = M - oe_ins;
+				f -= e_ins;
+				f = f > t ? f : t;
+			}
+			H[end] = h1; E[end] = NEG;
+		}
+#ifdef __CUDA_ARCH__
+		if (cells && visited) atomicAdd(cells, visited);
+#else
+		if (cells) *cells += visited;
+#endif
+		return H[qlen];
+	}
+};
+
+#ifdef __CUDACC__
+namespace lanes {
+
+struct QueryFetch {  // query base j of an ExtTask
+	const uint8_t *q; int q0, qstep;
+	__device__ __forceinline__ int operator()(int j) const { return q[q0 + j * qstep]; }
+};
+struct RefLaneFetch {  // target base i of an ExtTask, straight from the packed reference
+	const DevIndex *ix; int64_t t0; int tstep;
+	__device__ __forceinline__ int operator()(int i) const { return ref_base(*ix, t0 + (int64_t)i * tstep); }
+};
+
+enum { A_FETCH = 0, A_CHAIN, A_SEED, A_LEFT, A_RIGHT_BEGIN, A_RIGHT, A_IDLE };
+
+// One warp: 32 reads in flight.  `next` is the global read counter, eh this lane's DP column 0.
+template <class Pools_>
+__device__ void align1_warp(const DevIndex &ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, const Pools_ &p,
+                            int rescue_room, uint32_t *eh, unsigned long long *next, int *err, unsigned long long *cells_ext,
+                            unsigned long long *cells_glo)
+{
+	int st = A_FETCH;
+	// read
+	int r = 0, l_query = 0, n_chains = 0, ci = 0, n_av = 0;
+	const uint8_t *query = nullptr;
+	const Chain *chains = nullptr;
+	const Seed *seeds_all = nullptr;
+	uint64_t *srt = nullptr;
+	Reg *regs = nullptr;
+	// chain
+	ChainWin cw; cw.rmax0 = cw.rmax1 = 0;
+	const Seed *seeds = nullptr;
+	int k = -1, cn = 0;
+	// seed
+	SeedExt e;
+	seed_begin(Chain{}, e);
+	Seed s{};
+	int t_try = 0;
+	ExtTask x{};
+	ExtResult res{};
+	unsigned long long visited = 0;
+	for (;;) {
+		bool req = false;
+		while (!req && st != A_IDLE) {
+			if (st == A_LEFT || st == A_RIGHT) { req = true; break; }  // a band retry: x is already set
+			if (st == A_FETCH) {
+				const unsigned long long rr = atomicAdd(next, 1ull);
+				if (rr >= (unsigned long long)n_reads) { st = A_IDLE; break; }
+				r = (int)rr;
+				const int o = occ_off[r];
+				l_query = (int)(off[r + 1] - off[r]);
+				query = seq + off[r];
+				chains = p.chains + o; seeds_all = p.seeds + o; srt = p.srt + o;
+				regs = p.regs + (o + (size_t)rescue_room * r);
+				n_chains = p.n_chains[r];
+				ci = 0; n_av = 0;
+				st = A_CHAIN;
+			} else if (st == A_CHAIN) {
+				if (ci >= n_chains) {  // all chains extended: mem_sort_dedup_patch, then the next read
+					ScalarPatchDP sdp{ix, err, cells_glo};
+					p.n_regs[r] = sort_dedup_patch(ix, sdp, query, n_av, regs);
+					st = A_FETCH;
+				} else {
+					const Chain &c = chains[ci];
+					cn = c.n;
+					if (cn == 0) { ++ci; continue; }
+					seeds = seeds_all + c.seed_beg;
+					cw = chain_window(ix, l_query, c, seeds);
+					chain_sort_seeds(c, seeds, srt);
+					k = cn - 1;
+					st = A_SEED;
+				}
+			} else if (st == A_SEED) {
+				if (k < 0) { ++ci; st = A_CHAIN; continue; }
+				const Chain &c = chains[ci];
+				if (!seed_wants_extension(l_query, c, seeds, srt, k, regs, n_av)) { --k; continue; }
+				s = seeds[(uint32_t)srt[k]];
+				seed_begin(c, e);
+				if (s.qbeg) { t_try = 0; x = left_task(s, cw, 0); req = true; st = A_LEFT; }
+				else { left_none(s, e); st = A_RIGHT_BEGIN; }
+			} else if (st == A_RIGHT_BEGIN) {
+				if (s.qbeg + s.len != l_query) {
+					e.sc0 = e.a.score;
+					t_try = 0; x = right_task(l_query, s, cw, e, 0); req = true; st = A_RIGHT;
+				} else {
+					right_none(l_query, s, e);
+					seed_finish(chains[ci], seeds, s, e, regs, &n_av);
+					--k; st = A_SEED;
+				}
+			}
+		}
+		if (!__any_sync(FULL_MASK, req)) break;   // every lane idle: the bucket is done
+		QueryFetch qf{query, x.q0, x.qstep};
+		RefLaneFetch tf{&ix, x.t0, x.tstep};
+		res = extend(eh, req, x.qlen, x.tlen, x.h0, x.w, x.end_bonus, opt::zdrop, qf, tf, visited);
+		if (req) {
+			if (st == A_LEFT) {
+				if (left_try_done(e, res, t_try)) { ++t_try; x = left_task(s, cw, t_try); }   // again, with the band doubled
+				else { left_finish(s, e, res); st = A_RIGHT_BEGIN; }
+			} else {  // A_RIGHT
+				if (right_try_done(e, res, t_try)) { ++t_try; x = right_task(l_query, s, cw, e, t_try); }
+				else {
+					right_finish(l_query, s, cw, e, res);
+					seed_finish(chains[ci], seeds, s, e, regs, &n_av);
+					--k; st = A_SEED;
+				}
+			}
+		}
+	}
+	for (int d = 16; d; d >>= 1) visited += __shfl_xor_sync(FULL_MASK, visited, d);
+	if ((threadIdx.x & 31) == 0 && visited) atomicAdd(cells_ext, visited);
+}
+
+}  // namespace lanes
+#endif

@@ -386,7 +386,7 @@ static int upload_sw_inputs(emab_ctx *c, int n, const uint8_t *q, const int64_t 
 
 extern "C" int emab_set_sw_mode(emab_ctx_t *c, int mode)
 {
-	if (!c || mode < 0 || mode > 1) return EMAB_ERR_ARG;
+	if (!c || mode < 0 || mode > 2) return EMAB_ERR_ARG;
 	c->sw_mode = mode;
 	return EMAB_OK;
 }
@@ -441,9 +441,9 @@ extern "C" int emab_extend_batch(emab_ctx_t *c, int n, const uint8_t *q, const i
 	TRY(c->b[5].ensure((size_t)n * 24));
 	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
 	int qcap = 0;
-	if (c->sw_mode == 0) TRY(prepare_lanes(c, n, qoff, toff, h0, &qcap));
+	if (c->sw_mode != 1) TRY(prepare_lanes(c, n, qoff, toff, h0, &qcap));
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-	if (c->sw_mode == 0) TRY(launch_extend_lanes(c, n, qcap, w, end_bonus, zdrop));
+	if (c->sw_mode != 1) TRY(launch_extend_lanes(c, n, qcap, w, end_bonus, zdrop));
 	else
 	k_extend_batch<<<sw_grid(c), SW_WARPS * 32, 0, c->stream>>>(n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(), c->b[3].as<int64_t>(),
 	                                                             c->b[4].as<int32_t>(), w, end_bonus, zdrop, c->b[5].as<int32_t>(), c->d_counters);
@@ -480,7 +480,7 @@ extern "C" int emab_extend_resident_run(emab_ctx_t *c, int w, int end_bonus, int
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
 	for (int r = 0; r < reps; ++r) {
 		CUDA_TRY(cudaMemsetAsync(c->d_counters + 1, 0, 8, c->stream));
-		if (c->sw_mode == 0) TRY(launch_extend_lanes(c, n, c->res_qcap, w, end_bonus, zdrop));
+		if (c->sw_mode != 1) TRY(launch_extend_lanes(c, n, c->res_qcap, w, end_bonus, zdrop));
 		else
 		k_extend_batch<<<sw_grid(c), SW_WARPS * 32, 0, c->stream>>>(n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<uint8_t>(), c->b[3].as<int64_t>(),
 		                                                             c->b[4].as<int32_t>(), w, end_bonus, zdrop, c->b[5].as<int32_t>(), c->d_counters);

@@ -1059,11 +1059,13 @@ int align_special_fastq(Session *s, const char *data, size_t len, char **out, si
 int align_special_fastq_multi(Session *s, int n, const char *const *data, const size_t *len, char **out, size_t *out_len)
 {
 	const int W = std::max(1, std::min((int)s->workers.size(), n));
-	// Buckets walk through three ordered phases (parse+encode | device | clouds+EM+SAM) with at most two
-	// buckets inside a phase, so the host threads are split between two buckets per CPU phase while up to W
+	// Buckets walk through three ordered phases (parse+encode | device | clouds+EM+SAM) with at most three
+	// buckets inside a phase, so the host threads are split between three buckets per CPU phase while up to W
 	// buckets are in flight: bucket i's SAM text is written while i+1 runs on the GPU and i+2 is parsed.
-	const int cap = W > 1 ? 2 : 1;
-	for (int k = 0; k < PH_COUNT; ++k) s->gate[k].cap = cap;
+	int caps[PH_COUNT] = {3, 3, 3};
+	if (const char *e = getenv("EMAB_GATE_CAPS")) sscanf(e, "%d,%d,%d", &caps[0], &caps[1], &caps[2]);  // tuning knob
+	for (int k = 0; k < PH_COUNT; ++k) s->gate[k].cap = W > 1 ? std::max(1, std::min(caps[k], W)) : 1;
+	const int cap = W > 1 ? std::max(s->gate[PH_PARSE].cap, s->gate[PH_POST].cap) : 1;
 	const int per = std::max(1, s->n_threads / cap);
 	std::vector<int> tickets(n);
 	for (int i = 0; i < n; ++i) { tickets[i] = s->new_ticket(); out[i] = nullptr; out_len[i] = 0; }

@@ -43,9 +43,7 @@ struct RefFetch {  // straight from the packed reference: base i = ref[t0 + i*st
 
 __device__ __forceinline__ int warp_max(int v)
 {
-#pragma unroll
-	for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, d));
-	return v;
+	return __reduce_max_sync(FULL_MASK, v);  // one REDUX instead of a 5-step shuffle butterfly
 }
 
 // inclusive prefix max across lanes

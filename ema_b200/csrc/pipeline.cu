@@ -19,6 +19,7 @@
 #include "chain.cuh"
 #include "ksw_warp.cuh"
 #include "align.cuh"
+#include "align_lanes.cuh"
 
 #define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 #define PL_WARPS 8
@@ -160,6 +161,15 @@ k_align1(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const
 	}
 }
 
+// mem_align1_core with one thread per read (align_lanes.cuh): one-warp blocks, dynamic shared memory =
+// lanes::smem_per_warp(longest read of the batch)
+__global__ void __launch_bounds__(32)
+k_align1_lanes(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p, int *err, unsigned long long *counters)
+{
+	extern __shared__ uint32_t lanes_smem[];
+	lanes::align1_warp(ix, n_reads, seq, off, occ_off, p, RESCUE_ROOM, lanes_smem + threadIdx.x, &counters[5], err, &counters[0], &counters[3]);
+}
+
 __global__ void __launch_bounds__(PL_WARPS * 32)
 k_rescue(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p,
          uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
@@ -271,8 +281,10 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	memset(res, 0, sizeof *res);
 	if (stats) memset(stats, 0, sizeof *stats);
 	if (R == 0) return EMAB_OK;
+	int max_len = 1;
 	for (int i = 0; i < R; ++i) {
 		int64_t l = off[i + 1] - off[i];
+		if (l > max_len && l <= EMAB_MAX_READ_LEN) max_len = (int)l;
 		if (l < 0 || l > EMAB_MAX_READ_LEN) { snprintf(emab_errbuf, sizeof emab_errbuf, "read %d: length %lld out of range (max %d)", i, (long long)l, EMAB_MAX_READ_LEN); return EMAB_ERR_ARG; }
 	}
 	if (!c->consts_ready) TRY(emab_set_error_rate(c, 0.001));
@@ -329,6 +341,16 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	CUDA_TRY(cudaEventRecord(c->stage_ev[2], st));
 	k_chain<<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(), d_occ_off, p);
 	CUDA_TRY(cudaEventRecord(c->stage_ev[3], st));
+	if (c->sw_mode == 2) {  // thread-per-read mem_align1_core: wins only when a batch holds many more reads than the GPU has lanes
+		const size_t smem = lanes::smem_per_warp(max_len);
+		static bool configured = false;
+		if (!configured) { CUDA_TRY(cudaFuncSetAttribute(k_align1_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); configured = true; }
+		int per_sm = (int)((227 * 1024) / (smem + 1024));
+		per_sm = per_sm > 32 ? 32 : (per_sm < 1 ? 1 : per_sm);
+		int lgrid = c->n_sm * per_sm;
+		if (lgrid > (R + 31) / 32) lgrid = (R + 31) / 32;
+		k_align1_lanes<<<lgrid, 32, smem, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, d_err, c->d_counters);
+	} else
 	k_align1<<<grid, PL_WARPS * 32, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
 	                                          c->b[17].as<uint32_t>(), d_err, c->d_counters);
 	launches += 2;
@@ -410,7 +432,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		stats->d2h_bytes = (int64_t)R * 4 + (int64_t)A * (int64_t)sizeof(emab_cand_t) + (int64_t)NC * 4 + 96;
 	}
 	if (h_err[0]) {
-		snprintf(emab_errbuf, sizeof emab_errbuf, "device pipeline error %d (1: backtrack scratch too small, 2: rescue window too long, 3: too many SA intervals)", h_err[0]);
+		snprintf(emab_errbuf, sizeof emab_errbuf, "device pipeline error %d (1: backtrack scratch too small, 2: rescue window too long, 3: too many SA intervals, 4: internal DP dispatch)", h_err[0]);
 		return EMAB_ERR_OVERFLOW;
 	}
 	return EMAB_OK;

@@ -74,6 +74,6 @@ struct emab_ctx {
 	int n_sm = 148;
 	// resident SW microbench inputs
 	int res_n = 0, res_qcap = 0;
-	int sw_mode = 0;         // 0 = thread-per-task SW kernels (ksw_lanes.cuh), 1 = warp-per-task (ksw_warp.cuh)
+	int sw_mode = 0;         // see emab_set_sw_mode (include/ema_b200.h)
 	bool consts_ready = false;
 };

@@ -70,8 +70,10 @@ int emab_global_batch(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *q
 int emab_local_batch(emab_ctx_t *ctx, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
                      int32_t *out, int64_t *cells);
 
-/* which kernel family serves the batch calls: 0 (default) = one thread per task, 32 tasks per warp advancing
- * row by row (ksw_lanes.cuh); 1 = one warp per task (ksw_warp.cuh).  Results are identical. */
+/* which kernel family serves the SW work: 0 (default) = batch calls use one thread per task, 32 tasks per warp
+ * advancing row by row (ksw_lanes.cuh), the pipeline one warp per read; 1 = one warp per task everywhere
+ * (ksw_warp.cuh); 2 = thread-per-task everywhere, including mem_align1_core inside emab_align_pairs
+ * (align_lanes.cuh).  Results are identical. */
 int emab_set_sw_mode(emab_ctx_t *ctx, int mode);
 
 /* device-resident variant used by bench.py for the kernel-only number: uploads once, then

@@ -15,6 +15,7 @@
 #include "../../ema_b200/csrc/seed.cuh"
 #include "../../ema_b200/csrc/chain.cuh"
 #include "../../ema_b200/csrc/align.cuh"
+#include "../../ema_b200/csrc/align_lanes.cuh"
 #include "../../oracle/oracle.h"
 #define RESCUE_ROOM_HS 51
 
@@ -28,6 +29,8 @@ struct HostIndex {
 	std::vector<uint64_t> sa64;
 };
 
+static thread_local long long hs_cnt[6];  // DP calls: extend, global, local; cells: extend, global, local (instrumentation for tools)
+
 struct HostDP {  // scalar stand-in for WarpPolicy (pipeline.cu)
 	const DevIndex &ix;
 	int8_t mat[25];
@@ -38,7 +41,9 @@ struct HostDP {  // scalar stand-in for WarpPolicy (pipeline.cu)
 		for (int j = 0; j < qlen; ++j) q[j] = query[q0 + j * qstep];
 		for (int i = 0; i < tlen; ++i) t[i] = (uint8_t)ref_base(ix, t0 + (int64_t)i * tstep);
 		ExtResult r;
-		r.score = orc_ksw_extend2(qlen, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, w, end_bonus, opt::zdrop, h0, &r.qle, &r.tle, &r.gtle, &r.gscore, &r.max_off, 0);
+		int64_t cells = 0;
+		r.score = orc_ksw_extend2(qlen, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, w, end_bonus, opt::zdrop, h0, &r.qle, &r.tle, &r.gtle, &r.gscore, &r.max_off, &cells);
+		++hs_cnt[0]; hs_cnt[3] += cells;
 		return r;
 	}
 	int global(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, uint32_t *cigar, int *n_cigar)
@@ -46,7 +51,10 @@ struct HostDP {  // scalar stand-in for WarpPolicy (pipeline.cu)
 		std::vector<uint8_t> q(qlen + 1), t(tlen + 1);
 		for (int j = 0; j < qlen; ++j) q[j] = query[q0 + j * qstep];
 		for (int i = 0; i < tlen; ++i) t[i] = (uint8_t)ref_base(ix, t0 + (int64_t)i * tstep);
-		return orc_ksw_global2(qlen, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, w, cigar ? n_cigar : 0, cigar, EMAB_MAX_CIGAR, 0);
+		int64_t cells = 0;
+		int sc = orc_ksw_global2(qlen, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, w, cigar ? n_cigar : 0, cigar, EMAB_MAX_CIGAR, &cells);
+		++hs_cnt[1]; hs_cnt[4] += cells;
+		return sc;
 	}
 	LocResult local(const uint8_t *ms, int l_ms, int64_t rb, int tlen)
 	{
@@ -54,7 +62,9 @@ struct HostDP {  // scalar stand-in for WarpPolicy (pipeline.cu)
 		for (int j = 0; j < l_ms; ++j) q[l_ms - 1 - j] = ms[j] < 4 ? 3 - ms[j] : 4;
 		for (int i = 0; i < tlen; ++i) t[i] = (uint8_t)ref_base(ix, rb + i);
 		int out[7];
-		orc_ksw_align2(l_ms, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, 19, l_ms * opt::a < 250, out, 0);
+		int64_t cells = 0;
+		orc_ksw_align2(l_ms, q.data(), tlen, t.data(), 5, mat, 6, 1, 6, 1, 19, l_ms * opt::a < 250, out, &cells);
+		++hs_cnt[2]; hs_cnt[5] += cells;
 		LocResult r{out[0], out[1], out[2], out[3], out[4], out[5], out[6]};
 		return r;
 	}
@@ -239,5 +249,20 @@ int hs_candidates(void *h_, double eps, int l1, const uint8_t *s1, int l2, const
 }
 
 int hs_sizeof_aln(void) { return (int)sizeof(Aln); }
+void hs_dp_counters(long long *out, int reset) { for (int i = 0; i < 6; ++i) { out[i] = hs_cnt[i]; if (reset) hs_cnt[i] = 0; } }
+
+// the thread-scalar score-only global alignment the thread-per-read kernel uses for mem_patch_reg
+// (align_lanes.cuh): query against ref[t0, t0 + tlen) with band w; *target receives the bases read
+int hs_patch_global(void *h_, int qlen, const uint8_t *q, int64_t t0, int tstep, int tlen, int w, uint8_t *target, int64_t *cells)
+{
+	HostIndex *h = (HostIndex *)h_;
+	int err = 0;
+	unsigned long long c = 0;
+	ScalarPatchDP dp{h->d, &err, &c};
+	for (int i = 0; i < tlen; ++i) target[i] = (uint8_t)ref_base(h->d, t0 + (int64_t)i * tstep);
+	int sc = dp.global(q, 0, 1, qlen, t0, tstep, tlen, w, nullptr, nullptr);
+	if (cells) *cells = (int64_t)c;
+	return err ? -999999 : sc;
+}
 
 }  // extern "C"

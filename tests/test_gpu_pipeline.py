@@ -50,6 +50,22 @@ def test_candidates_golden(emab):
     assert got2 == got
 
 
+def test_candidates_golden_thread_per_read(emab):
+    """the same golden comparison with mem_align1_core run one thread per read (emab_set_sw_mode 2,
+    align_lanes.cuh) instead of one warp per read"""
+    ix = emab.Index(os.path.join(G, "tiny_rep", "ref.fa"))
+    ctx = emab.Context(ix)
+    emab.set_sw_mode(ctx, 2)
+    want = helpers.cands_from_golden(np.load(os.path.join(G, "cand_golden.npz")))
+    lines = helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x"))
+    got, res = pipeline_candidates(emab, ctx, lines)
+    bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert not bad, f"{len(bad)} of {len(want)} pairs differ; first {lines[bad[0]][1]}: {got[bad[0]]} vs {want[bad[0]]}"
+    ctx1 = emab.Context(ix)
+    got1, res1 = pipeline_candidates(emab, ctx1, lines)
+    assert res["stats"].extend_cells == res1["stats"].extend_cells, "both kernels must visit the reference's DP cells"
+
+
 def test_stage_regions_vs_hostsim(emab):
     """regions after mem_align1_core (stage 1) and after mate rescue (stage 2) against the host build of
     the same control logic driven by the oracle's scalar DP (itself pinned to the reference)."""

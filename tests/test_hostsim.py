@@ -90,6 +90,45 @@ def test_seeding_flat_equals_nested(hs):
         assert hs.hs_collect_intv_touches(hi, len(s), _p(s, C.c_uint8)) == tb.value
 
 
+def test_scalar_patch_global_vs_oracle(hs, port_lib):
+    """ScalarPatchDP::global (the score-only ksw_global2 the thread-per-read kernel runs inline for
+    mem_patch_reg) against the oracle: same score and same visited cells, both strands, assorted bands."""
+    hi = C.c_void_p(hs.hs_index_load(os.path.join(G, "tiny_rep", "ref.fa").encode()))
+    rng = np.random.default_rng(3)
+    l_pac = 120000
+    qs, ts, ws, got, gcells = [], [], [], [], []
+    for it in range(300):
+        tlen = int(rng.integers(1, 230))
+        rev = it % 2
+        t0 = int(rng.integers(1000, l_pac - 1000)) + (l_pac if rev else 0)
+        tstep = -1 if it % 3 == 0 else 1
+        w = int(rng.choice([0, 1, 3, 10, 50, 100, 400]))
+        tgt = np.zeros(tlen, np.uint8)
+        # query = noisy copy of the window (filled after the bases are known), or unrelated
+        probe = np.zeros(1, np.uint8)
+        hs.hs_patch_global(hi, 1, _p(probe, C.c_uint8), C.c_int64(t0), tstep, tlen, w, _p(tgt, C.c_uint8), None)
+        q = [int(b) for b in tgt]
+        if it % 5 == 0:
+            q = list(rng.integers(0, 4, size=int(rng.integers(1, 200))))
+        else:
+            for _ in range(int(rng.integers(0, 6))):
+                pos = int(rng.integers(0, max(1, len(q))))
+                r = rng.random()
+                if r < 0.4 and len(q) > 1:
+                    del q[pos]
+                elif r < 0.7:
+                    q.insert(pos, int(rng.integers(0, 4)))
+                elif q:
+                    q[pos] = int(rng.integers(0, 5))
+        q = np.array(q[:200] or [0], np.uint8)
+        cells = C.c_int64()
+        sc = hs.hs_patch_global(hi, len(q), _p(q, C.c_uint8), C.c_int64(t0), tstep, tlen, w, _p(tgt, C.c_uint8), C.byref(cells))
+        qs.append(q); ts.append(tgt.copy()); ws.append(w); got.append(sc); gcells.append(cells.value)
+    want, _, wcells = helpers.sw_global(port_lib, "orc", qs, ts, ws)
+    assert np.array_equal(np.array(got), want[:, 0])
+    assert sum(gcells) == wcells
+
+
 def _regs(lib, fn, idx, s, *extra):
     rg = np.zeros((4096, 18), np.int64)
     n = getattr(lib, fn)(idx, len(s), _p(s, C.c_uint8), _p(rg, C.c_int64), 4096, *extra)
