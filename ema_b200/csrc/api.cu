@@ -8,7 +8,7 @@
 #include "../../include/ema_b200.h"
 #include "runtime.cuh"
 #include "fmindex.cuh"
-#include "seed.cuh"
+#include "seed_launch.cuh"
 #include "ksw_warp.cuh"
 #include "ksw_lanes.cuh"
 
@@ -195,6 +195,8 @@ extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
 	c->n_sm = prop.multiProcessorCount;
+	if (const char *e = getenv("EMAB_SW_MODE")) c->sw_mode = atoi(e);  // tuning knob, see emab_set_sw_mode
+	if (const char *e = getenv("EMAB_PL_BPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->pl_bps = v; }  // persistent SW grids: blocks per SM
 	*out = c;
 	return EMAB_OK;
 }
@@ -570,31 +572,6 @@ __global__ void k_sa_batch(DevIndex ix, int n, const int64_t *k, int64_t *out, i
 	out[i] = mode == 0 ? (int64_t)bwt_sa_dense(ix, (uint64_t)k[i]) : (int64_t)bwt_sa_walk(fm, (uint64_t)k[i]);
 }
 
-__global__ void __launch_bounds__(128)
-k_smem_batch(DevIndex ix, int n, const uint8_t *seq, const int64_t *off, Intv *intv, int32_t *n_intv, int max_intv,
-             Intv *scratch, int32_t *overflow, unsigned long long *counters)
-{
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned touches = 0;
-	{   // every lane of the warp runs collect_intv (it votes); lanes past the end get an empty read
-		const bool valid = r < n;
-		const int rr = valid ? r : 0;
-		Fm fm{ix, 0};
-		const int len = valid ? (int)(off[rr + 1] - off[rr]) : 0;
-		Intv *buf0 = scratch + (size_t)rr * 2 * (EMAB_MAX_READ_LEN + 1);
-		int ovf = 0;
-		const int ni = collect_intv(fm, len, seq + off[rr], intv + (size_t)rr * max_intv, max_intv, buf0, buf0 + EMAB_MAX_READ_LEN + 1, &ovf);
-		if (valid) {
-			n_intv[r] = ni;
-			if (ovf) *overflow = 1;
-			touches = fm.touches;
-		}
-	}
-	// one atomic per warp
-	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(FULL_MASK, touches, d);
-	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(&counters[2], (unsigned long long)touches);
-}
-
 extern "C" int emab_sa_batch(emab_ctx_t *c, int n, const int64_t *k, int64_t *out, int mode)
 {
 	if (!c || !c->ix || n < 0) return EMAB_ERR_ARG;
@@ -626,14 +603,16 @@ extern "C" int emab_smem_batch(emab_ctx_t *c, int n, const uint8_t *seq, const i
 	TRY(upload(c, c->b[1], off, (size_t)(n + 1) * 8));
 	TRY(c->b[2].ensure((size_t)n * max_intv * sizeof(Intv)));
 	TRY(c->b[3].ensure((size_t)n * 4 + 4));
-	TRY(c->b[4].ensure((size_t)n * 2 * (EMAB_MAX_READ_LEN + 1) * sizeof(Intv)));
 	int32_t *d_ovf = c->b[3].as<int32_t>() + n;
 	CUDA_TRY(cudaMemsetAsync(d_ovf, 0, 4, c->stream));
 	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-	k_smem_batch<<<(n + 127) / 128, 128, 0, c->stream>>>(c->ix->d, n, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(),
-	                                                       max_intv, c->b[4].as<Intv>(), d_ovf, c->d_counters);
-	c->last_launches = 1;
+	int max_len = 1;
+	for (int i = 0; i < n; ++i) if (off[i + 1] - off[i] > max_len) max_len = (int)(off[i + 1] - off[i]);
+	int launches = 0;
+	TRY(launch_seed(c, n, max_len, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), max_intv, c->b[3].as<int32_t>(), nullptr, d_ovf,
+	                &c->d_counters[2], &launches));
+	c->last_launches = launches;
 	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(intervals, c->b[2].p, (size_t)n * max_intv * sizeof(Intv), cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(cudaMemcpyAsync(n_intv, c->b[3].p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));

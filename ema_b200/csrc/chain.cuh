@@ -9,7 +9,7 @@
 // per-read node pool.  Seeds of a chain form a linked list in the read's seed pool and are
 // compacted per chain once filtering is done.
 #pragma once
-#include "fmindex.cuh"
+#include "seed.cuh"
 #include "sort.cuh"
 
 #define BT_T 5
@@ -29,14 +29,6 @@ struct ChainWork {   // per-read working pools (capacity `cap` = number of SA oc
 };
 
 struct WIdx { int32_t w, idx; };  // chain weight + index: what ks_introsort(mem_flt) compares and moves
-
-// number of SA occurrences mem_chain enumerates for one interval (bwa/bwamem.c:304-305)
-EMAB_HD int intv_occ_count(uint64_t x2)
-{
-	uint64_t step = x2 > (uint64_t)opt::max_occ ? x2 / opt::max_occ : 1;
-	uint64_t cnt = (x2 + step - 1) / step;
-	return (int)(cnt < (uint64_t)opt::max_occ ? cnt : (uint64_t)opt::max_occ);
-}
 
 // __kb_getp_aux (bwa/kbtree.h:118-133): lower-bound probe inside one node
 EMAB_HD int bt_probe(const BNode &x, const Chain *chains, int64_t pos, int *r)

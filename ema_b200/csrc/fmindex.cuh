@@ -82,22 +82,30 @@ EMAB_HD void block_occ4(const OccBlock &o, int idx, uint64_t cnt[4])
 	cnt[3] = ((uint64_t)o.c1.w << 32 | o.c1.z) + nt;
 }
 
-// bwt_2occ4(k, l): two positions, one block load when they share a block (bwa/bwt.c:189-220).
-// *touches counts 64-byte block loads (the roofline unit of SURVEY.md §8d).
+// bwt_2occ4(k, l): two positions (bwa/bwt.c:189-220).  Branch-free: with one thread per read the lanes of a
+// warp disagree on "k and l share a block", and a branch here made the warp run both arms of the ~200-instruction
+// counting code every step (ncu, profiles/r1b_ncu_summary_c2.md).  Both blocks are always loaded — the second
+// load of a shared block coalesces with the first in L1 — and both positions always counted.
+// fm.touches counts 64-byte block loads as the reference would issue them (the roofline unit of
+// SURVEY.md §8d): one when k and l share a block, none for a position equal to (bwtint_t)-1.
 EMAB_HD void bwt_2occ4(Fm &fm, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t cl[4])
 {
 	const uint64_t NEG1 = ~0ull;
-	uint64_t _k = k - (k >= fm.ix.primary && k != NEG1), _l = l - (l >= fm.ix.primary && l != NEG1);
-	if (k == NEG1) { ck[0] = ck[1] = ck[2] = ck[3] = 0; }
-	if (l == NEG1) { cl[0] = cl[1] = cl[2] = cl[3] = 0; }
-	if (k != NEG1 && l != NEG1 && (_k >> 7) == (_l >> 7)) {
-		OccBlock o = load_block(fm, _k >> 7);
-		block_occ4(o, (int)(_k & 127), ck);
-		block_occ4(o, (int)(_l & 127), cl);
-		return;
+	const bool kv = k != NEG1, lv = l != NEG1;
+	const uint64_t _k = kv ? k - (k >= fm.ix.primary) : 0, _l = lv ? l - (l >= fm.ix.primary) : 0;
+	const uint64_t bk = _k >> 7, bl = _l >> 7;
+	const uint4 *pk = fm.ix.bwt + (bk << 2), *pl = fm.ix.bwt + (bl << 2);
+	OccBlock a, b;
+	a.c0 = ldg128(pk); a.c1 = ldg128(pk + 1); a.b0 = ldg128(pk + 2); a.b1 = ldg128(pk + 3);
+	b.c0 = ldg128(pl); b.c1 = ldg128(pl + 1); b.b0 = ldg128(pl + 2); b.b1 = ldg128(pl + 3);
+	fm.touches += (unsigned)kv + (unsigned)(lv && !(kv && bk == bl));
+	block_occ4(a, (int)(_k & 127), ck);
+	block_occ4(b, (int)(_l & 127), cl);
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		ck[i] = kv ? ck[i] : 0;
+		cl[i] = lv ? cl[i] : 0;
 	}
-	if (k != NEG1) { OccBlock o = load_block(fm, _k >> 7); block_occ4(o, (int)(_k & 127), ck); }
-	if (l != NEG1) { OccBlock o = load_block(fm, _l >> 7); block_occ4(o, (int)(_l & 127), cl); }
 }
 
 EMAB_HD void bwt_set_intv(const DevIndex &ix, int c, Intv &ik)

@@ -2,7 +2,8 @@
 // bwa_mem_mate_sw + bwa_smith_waterman + append_alignments (src/bwabridge.c:204-311,
 // src/align.c:986-1061).  One bucket (or any batch of read pairs) is one call:
 //
-//   k_seed      thread / read   mem_collect_intv                      -> SA intervals, #occurrences
+//   k_seed      persistent lanes, one read per lane at a time, pass-1/2 and pass-3 roles (seed.cuh)
+//   k_seed_finish thread / read  merge + sort of mem_collect_intv       -> SA intervals, #occurrences
 //   (scan)                      exclusive sum of #occurrences          -> per-read pool offsets
 //   k_chain     thread / read   mem_chain + mem_chain_flt (dense SA)   -> chains + seeds
 //   k_align1    warp   / read   mem_chain2aln + mem_sort_dedup_patch   -> regions
@@ -15,7 +16,7 @@
 #include <cub/device/device_scan.cuh>
 #include "../../include/ema_b200.h"
 #include "runtime.cuh"
-#include "seed.cuh"
+#include "seed_launch.cuh"
 #include "chain.cuh"
 #include "ksw_warp.cuh"
 #include "align.cuh"
@@ -92,35 +93,6 @@ __device__ __forceinline__ int next_item(unsigned long long *counter, int lane)
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_seed(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, Intv *intv, int32_t *n_intv, Intv *scratch,
-       int32_t *occ_cnt, int *err, unsigned long long *counters)
-{
-	const int r = blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned touches = 0;
-	{   // every lane of the warp runs collect_intv (it votes); lanes past the end get an empty read
-		const bool valid = r < n_reads;
-		const int rr = valid ? r : 0;
-		Fm fm{ix, 0};
-		const int len = valid ? (int)(off[rr + 1] - off[rr]) : 0;
-		Intv *buf0 = scratch + (size_t)rr * 2 * (EMAB_MAX_READ_LEN + 1);
-		Intv *mine = intv + (size_t)rr * EMAB_MAX_INTV;
-		int ovf = 0;
-		const int n = collect_intv(fm, len, seq + off[rr], mine, EMAB_MAX_INTV, buf0, buf0 + EMAB_MAX_READ_LEN + 1, &ovf);
-		if (valid) {
-			if (ovf) *err = 3;
-			n_intv[r] = n;
-			int occ = 0;
-			if (len >= opt::min_seed_len)
-				for (int i = 0; i < n; ++i) occ += intv_occ_count(mine[i].x2);
-			occ_cnt[r] = occ;
-			touches = fm.touches;
-		}
-	}
-	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(FULL_MASK, touches, d);
-	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(&counters[2], (unsigned long long)touches);
-}
-
 struct Pools {  // device pools sized by the total number of SA occurrences T and the number of reads R
 	Seed *w_seeds; Chain *w_chains; BNode *w_nodes; int32_t *w_ord;   // chaining work space
 	Seed *seeds; Chain *chains;                                       // surviving chains + seeds
@@ -295,7 +267,6 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	TRY(upload(c, c->b[1], off, (size_t)(R + 1) * 8));
 	TRY(c->b[2].ensure((size_t)R * EMAB_MAX_INTV * sizeof(Intv)));
 	TRY(c->b[3].ensure((size_t)R * 4));
-	TRY(c->b[4].ensure((size_t)R * 2 * (EMAB_MAX_READ_LEN + 1) * sizeof(Intv)));
 	TRY(c->b[5].ensure((size_t)(R + 1) * 4 * 2));
 	int32_t *d_occ_cnt = c->b[5].as<int32_t>(), *d_occ_off = d_occ_cnt + (R + 1);
 	TRY(c->b[22].ensure(16));
@@ -307,9 +278,8 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	if (!c->stage_ev[0]) for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&c->stage_ev[i]));
 	CUDA_TRY(cudaEventRecord(c->ev0, st));
 	CUDA_TRY(cudaEventRecord(c->stage_ev[0], st));
-	k_seed<<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(),
-	                                        c->b[4].as<Intv>(), d_occ_cnt, d_err, c->d_counters);
-	++launches;
+	TRY(launch_seed(c, R, max_len, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), EMAB_MAX_INTV, c->b[3].as<int32_t>(), d_occ_cnt, d_err,
+	                &c->d_counters[2], &launches));
 	CUDA_TRY(cudaEventRecord(c->stage_ev[1], st));
 	size_t tmp_bytes = 0;
 	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_occ_cnt, d_occ_off, R + 1, st);
@@ -334,7 +304,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	p.n_chains = c->b[15].as<int32_t>(); p.n_regs = p.n_chains + (R + 1);
 	int32_t *d_aln_off = p.n_regs + (R + 1);
 	CUDA_TRY(cudaMemsetAsync(p.n_chains, 0, (size_t)(R + 1) * 4 * 3, st));
-	const int grid = c->n_sm * 4, n_warps = grid * PL_WARPS;
+	const int grid = c->n_sm * c->pl_bps, n_warps = grid * PL_WARPS;
 	const size_t z_cap = (size_t)EMAB_MAX_READ_LEN * 1024;
 	TRY(c->b[16].ensure((size_t)n_warps * z_cap));
 	TRY(c->b[17].ensure((size_t)n_warps * EMAB_MAX_CIGAR * 4));

@@ -8,6 +8,14 @@
 #pragma once
 #include "fmindex.cuh"
 
+// number of SA occurrences mem_chain enumerates for one interval (bwa/bwamem.c:304-305)
+EMAB_HD int intv_occ_count(uint64_t x2)
+{
+	uint64_t step = x2 > (uint64_t)opt::max_occ ? x2 / opt::max_occ : 1;
+	uint64_t cnt = (x2 + step - 1) / step;
+	return (int)(cnt < (uint64_t)opt::max_occ ? cnt : (uint64_t)opt::max_occ);
+}
+
 struct SeedScratch {  // per read: two interval lists of (len+1) entries for bwt_smem1a's prev/curr
 	Intv *a;          // [n_slots][2][EMAB_MAX_READ_LEN + 1]
 };
@@ -165,155 +173,175 @@ EMAB_HD int collect_intv_nested(Fm &fm, int len, const uint8_t *seq, Intv *mem, 
 
 
 // ---------------------------------------------------------------------------------------------
-// mem_collect_intv flattened into ONE loop whose body performs exactly one bwt_extend.
+// mem_collect_intv for the device: flattened into loops whose body performs exactly ONE bwt_extend.
 //
 // Why: with one thread per read, the nested form above puts every lane of a warp in a different
-// loop nest (forward sweep, backward sweep, pass 3, ...), so the ~250-instruction bwt_extend is
-// issued once per distinct program point: ncu showed 8.9 of 32 lanes active per instruction.
-// Here every lane reaches the same bwt_extend call site each iteration; what differs between lanes
-// is only the cheap bookkeeping before ("which interval/base next") and after ("what to do with
-// the result").  Semantics are unchanged: tests/hostsim checks this against the nested form and
-// against the reference on every read of the fixtures.
+// loop nest (forward sweep, backward sweep, pass 3, ...), so the ~200-instruction bwt_extend is
+// issued once per distinct program point (ncu: 8.9 of 32 lanes active per instruction).  Here every
+// lane reaches the same bwt_extend call site each iteration; what differs between lanes is only the
+// cheap bookkeeping before ("which interval/base next") and after ("what to do with the result").
+//
+// The work of one read is split where the reference's data flow allows it:
+//   * passes 1+2 (bwt_smem1a from every x, then re-seeding inside long rare SMEMs) are one state
+//     machine (P12): pass 2 consumes pass 1's intervals;
+//   * pass 3 (bwt_seed_strategy1, bwa/bwamem.c:170-185) reads nothing the other passes write, so it is
+//     its own, perfectly uniform loop (P3) — on the device a different warp, which doubles the number
+//     of independent dependent-load chains in flight per read;
+//   * the final ks_introsort by info (bwa/bwamem.c:187) runs once both lists exist (finish_intv).
+// Because of that final sort — equal keys are identical intervals, so any comparison sort gives the
+// reference's byte-identical list — P12 neither reverses each call's intervals (bwa/bwt.c:349) nor
+// compacts them afterwards: an interval is tested against min_seed_len (bwa/bwamem.c:150-155,165-167)
+// when it is emitted, and the first backward round indexes the forward list back to front instead
+// of reversing it (bwa/bwt.c:322).
+//
+// Lanes are persistent: a lane that finishes a read takes the next one from its Feeder (an atomic
+// counter on the device), so a warp's lanes stay busy until the queue is empty instead of idling
+// until the warp's slowest read is done.  Semantics are unchanged: tests/hostsim checks the composed
+// form against the nested one and against the reference on every read of the fixtures, including the
+// count of Occ-block loads.
 // ---------------------------------------------------------------------------------------------
-enum { SD_NEXT = 0, SD_FWD = 1, SD_BWD = 2, SD_P3 = 3, SD_DONE = 4 };
+enum { SD_NEXT = 0, SD_FWD = 1, SD_BWD0 = 2, SD_BWD = 3, SD_DONE = 4 };
 
-EMAB_HD int collect_intv(Fm &fm, int len, const uint8_t *seq, Intv *mem, int mem_cap,
-                         Intv *buf0, Intv *buf1, int *overflow)
+struct SeedJob {  // one read as the seeding loops see it
+	const uint8_t *seq;
+	int len;
+	Intv *out;   // where this pass's intervals go
+	int cap;
+	int id;      // read index (feeder's business)
+};
+
+#ifdef __CUDA_ARCH__
+#define EMAB_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+#define EMAB_WARP_ANY(p) (p)
+#endif
+
+// Passes 1 and 2.  feed.next(job) hands out the next read (false = queue empty); feed.done(job, n, ovf)
+// receives the number of intervals written to job.out.  buf0/buf1: this lane's prev/curr lists,
+// (longest read + 1) entries each.  ALL 32 LANES OF A WARP MUST CALL (the loop votes).
+template <class Feeder>
+EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 {
-	int n = 0;            // intervals kept so far (all passes)
-	int pass = 1, x = 0;  // pass 1 / 3 cursor
-	int old_n = 0, k2 = 0;  // pass 2 cursor over the pass-1 intervals
-	int st = SD_NEXT;
+	SeedJob job;
+	job.seq = nullptr; job.len = 0; job.out = nullptr; job.cap = 0; job.id = -1;
+	int n = 0, ovf = 0;   // intervals kept so far for this read
+	int pass = 1, x = 0, old_n = 0, k2 = 0;
+	int st = SD_DONE;
+	bool have_job = false, drained = false;
 	// state of the bwt_smem1a call in progress
-	int i = 0, j = 0, n_prev = 0, n_curr = 0, m0 = 0, m = 0, sx = 0, ret = 0;
-	uint64_t min_intv = 1, last_start = 0, last_size = 0;
-	bool have_last = false, in_p2 = false;
+	int i = 0, j = 0, n_prev = 0, n_curr = 0, sx = 0, ret = 0, last_start = 0x7fffffff;
+	uint64_t min_intv = 1, last_size = 0;
+	bool in_p2 = false, rev = false;
 	Intv *prev = buf0, *curr = buf1;
 	Intv ik;
 	ik.x0 = ik.x1 = ik.x2 = ik.info = 0;
 	int c = 0, back = 0;
 	for (;;) {
-		// ---- bookkeeping until the next bwt_extend is known (or everything is done)
+		// ---- bookkeeping until the next bwt_extend is known (or the queue is empty)
 		bool req = false;
-		while (!req && st != SD_DONE) {
+		while (!req && !drained) {
+			if (st == SD_DONE) {  // take the next read
+				if (have_job) { feed.done(job, n, ovf); have_job = false; }
+				if (feed.next(job)) { have_job = true; n = 0; ovf = 0; pass = 1; x = 0; st = SD_NEXT; }
+				else drained = true;
+			}
+			if (st == SD_BWD && j == n_prev) {  // end of one backward round (bwa/bwt.c:346-348)
+				if (n_curr == 0) {  // the call is over
+					if (!in_p2) x = ret;
+					st = SD_NEXT;
+				} else {
+					{ Intv *t = curr; curr = prev; prev = t; }
+					n_prev = n_curr; n_curr = 0;
+					--i; rev = false;
+					st = SD_BWD0;
+				}
+			}
 			if (st == SD_NEXT) {
 				bool start_call = false;
 				if (pass == 1) {
-					while (x < len && seq[x] > 3) ++x;
-					if (x >= len) { pass = 2; old_n = n; k2 = 0; }
+					while (x < job.len && job.seq[x] > 3) ++x;
+					if (x >= job.len) { pass = 2; old_n = n; k2 = 0; }
 					else { sx = x; min_intv = 1; in_p2 = false; start_call = true; }
-				} else if (pass == 2) {  // bwa/bwamem.c:157-168
+				} else {  // pass 2: bwa/bwamem.c:157-168
 					while (k2 < old_n) {
-						const Intv p = mem[k2];
+						const Intv p = job.out[k2];
 						const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
 						if (end - start >= opt::split_len && p.x2 <= (uint64_t)opt::split_width) break;
 						++k2;
 					}
-					if (k2 >= old_n) { pass = 3; x = 0; }
+					if (k2 >= old_n) st = SD_DONE;
 					else {
-						const Intv p = mem[k2++];
+						const Intv p = job.out[k2++];
 						sx = ((int)(p.info >> 32) + (int)(uint32_t)p.info) >> 1;
 						min_intv = p.x2 + 1; in_p2 = true; start_call = true;
 					}
-				} else {  // pass 3: bwt_seed_strategy1 from x (bwa/bwamem.c:170-185)
-					while (x < len && seq[x] > 3) ++x;
-					if (x >= len) st = SD_DONE;
-					else { bwt_set_intv(fm.ix, seq[x], ik); i = x + 1; st = SD_P3; }
 				}
 				if (start_call) {  // bwt_smem1a(sx, min_intv): bwa/bwt.c:289-302
-					bwt_set_intv(fm.ix, seq[sx], ik);
+					bwt_set_intv(fm.ix, job.seq[sx], ik);
 					ik.info = sx + 1;
-					i = sx + 1; n_curr = 0; m0 = m = n; have_last = false;
+					i = sx + 1; n_curr = 0; last_start = 0x7fffffff;
 					st = SD_FWD;
 				}
-			} else if (st == SD_FWD) {
-				bool fwd_done = false;
-				if (i < len && seq[i] < 4) { c = 3 - seq[i]; back = 0; req = true; }
-				else { curr[n_curr++] = ik; fwd_done = true; }  // ambiguous base, or i == len (bwa/bwt.c:316-321)
-				if (fwd_done) {
-					reverse_intvs(curr, n_curr);
-					ret = (int)curr[0].info;
-					{ Intv *t = curr; curr = prev; prev = t; }
-					n_prev = n_curr; n_curr = 0; last_size = 0;
-					i = sx - 1; j = 0;
-					st = SD_BWD;
-				}
-			} else if (st == SD_BWD) {
-				if (j == n_prev) {  // end of one backward round (bwa/bwt.c:346-348)
-					if (n_curr == 0) {  // the call is over: reverse + keep seeds >= min_seed_len
-						if (m > mem_cap) m = mem_cap;
-						reverse_intvs(mem + m0, m - m0);
-						int k = m0;
-						for (int jj = m0; jj < m; ++jj) {
-							const Intv p = mem[jj];
-							const int slen = (int)(uint32_t)p.info - (int)(p.info >> 32);
-							if (slen >= opt::min_seed_len) mem[k++] = p;
-						}
-						n = k;
-						if (!in_p2) x = ret;
-						st = SD_NEXT;
-					} else {
-						{ Intv *t = curr; curr = prev; prev = t; }
-						n_prev = n_curr; n_curr = 0; last_size = 0;
-						--i; j = 0;
-					}
-				} else {
-					const int cc = i < 0 ? -1 : (seq[i] < 4 ? seq[i] : -1);
-					if (cc < 0) {  // nothing can extend: the first interval may be emitted (bwa/bwt.c:331-338)
-						Intv p = prev[j];
-						if (n_curr == 0 && (!have_last || (uint64_t)(i + 1) < last_start)) {
-							p.info |= (uint64_t)(i + 1) << 32;
-							if (m < mem_cap) mem[m] = p; else *overflow = 1;
-							++m;
-							last_start = (uint64_t)(i + 1); have_last = true;
-						}
-						++j;
-					} else { ik = prev[j]; c = cc; back = 1; req = true; }
-				}
-			} else {  // SD_P3
-				if (i < len && seq[i] < 4) { c = 3 - seq[i]; back = 0; req = true; }
-				else { x = i < len ? i + 1 : len; st = SD_NEXT; }  // bwa/bwt.c:376-378
 			}
+			if (st == SD_FWD) {
+				if (i < job.len && job.seq[i] < 4) { c = 3 - job.seq[i]; back = 0; req = true; }
+				else {  // ambiguous base, or i == len (bwa/bwt.c:316-321)
+					curr[n_curr++] = ik; ret = (int)ik.info;
+					{ Intv *t = curr; curr = prev; prev = t; }
+					n_prev = n_curr; n_curr = 0;
+					i = sx - 1; rev = true;
+					st = SD_BWD0;
+				}
+			}
+			if (st == SD_BWD0) {  // a backward round starts at query position i (bwa/bwt.c:324-326)
+				const int cc = i < 0 ? -1 : (job.seq[i] < 4 ? job.seq[i] : -1);
+				if (cc < 0) {
+					// nothing can extend: only the first (longest) interval may be emitted, after which the round
+					// leaves curr empty and the call is over (bwa/bwt.c:331-338,346)
+					Intv p = prev[rev ? n_prev - 1 : 0];
+					if (i + 1 < last_start) {
+						p.info |= (uint64_t)(i + 1) << 32;
+						if ((int)(uint32_t)p.info - (i + 1) >= opt::min_seed_len) {
+							if (n < job.cap) job.out[n++] = p; else ovf = 1;
+						}
+					}
+					if (!in_p2) x = ret;
+					st = SD_NEXT;
+				} else { c = cc; back = 1; j = 0; last_size = 0; st = SD_BWD; }
+			}
+			if (st == SD_BWD && j < n_prev) { ik = prev[rev ? n_prev - 1 - j : j]; req = true; }
 		}
 		// ---- the one convergent step.  On the device the warp votes here every iteration: the vote is
-		// the reconvergence point that brings all lanes to the bwt_extend below together (without it the
-		// lanes leave the bookkeeping loop one by one and each runs the extend code on its own), and
-		// lanes whose read is finished idle until the whole warp is.  ALL 32 LANES MUST CALL collect_intv.
-#ifdef __CUDA_ARCH__
-		if (!__any_sync(0xffffffffu, st != SD_DONE)) break;
-		if (st == SD_DONE) continue;
-#else
-		if (st == SD_DONE) break;
-#endif
-		const Intv ok0 = bwt_extend1(fm, ik, c, back);
-		Intv ok = ok0;
+		// the reconvergence point that brings all lanes to the bwt_extend below together.
+		if (!EMAB_WARP_ANY(req)) break;
+		if (!req) continue;
+		Intv ok = bwt_extend1(fm, ik, c, back);
 		// ---- consume
 		if (st == SD_FWD) {  // bwa/bwt.c:307-315
 			bool stop = false;
 			if (ok.x2 != ik.x2) {
-				curr[n_curr++] = ik;
-				if (ok.x2 < min_intv) stop = true;
+				curr[n_curr++] = ik; ret = (int)ik.info;
+				stop = ok.x2 < min_intv;
 			}
 			if (stop) {
-				reverse_intvs(curr, n_curr);
-				ret = (int)curr[0].info;
 				{ Intv *t = curr; curr = prev; prev = t; }
-				n_prev = n_curr; n_curr = 0; last_size = 0;
-				i = sx - 1; j = 0;
-				st = SD_BWD;
+				n_prev = n_curr; n_curr = 0;
+				i = sx - 1; rev = true;
+				st = SD_BWD0;
 			} else {
 				ok.info = i + 1;
 				ik = ok;
 				++i;
 			}
-		} else if (st == SD_BWD) {  // bwa/bwt.c:328-345
+		} else {  // SD_BWD: bwa/bwt.c:328-345
 			if (ok.x2 < min_intv) {
-				if (n_curr == 0 && (!have_last || (uint64_t)(i + 1) < last_start)) {
+				if (n_curr == 0 && i + 1 < last_start) {
 					Intv p = ik;
 					p.info |= (uint64_t)(i + 1) << 32;
-					if (m < mem_cap) mem[m] = p; else *overflow = 1;
-					++m;
-					last_start = (uint64_t)(i + 1); have_last = true;
+					if ((int)(uint32_t)p.info - (i + 1) >= opt::min_seed_len) {
+						if (n < job.cap) job.out[n++] = p; else ovf = 1;
+					}
+					last_start = i + 1;
 				}
 			} else if (n_curr == 0 || ok.x2 != last_size) {
 				ok.info = ik.info;
@@ -321,19 +349,60 @@ EMAB_HD int collect_intv(Fm &fm, int len, const uint8_t *seq, Intv *mem, int mem
 				last_size = ok.x2;
 			}
 			++j;
-		} else {  // SD_P3 (bwa/bwt.c:366-375)
-			if (ok.x2 < (uint64_t)opt::max_mem_intv && i - x >= opt::min_seed_len) {
-				if (ok.x2 > 0) {
-					ok.info = (uint64_t)x << 32 | (uint64_t)(i + 1);
-					if (n < mem_cap) mem[n++] = ok; else *overflow = 1;
-				}
-				x = i + 1;
-				st = SD_NEXT;
-			} else { ik = ok; ++i; }
 		}
 	}
-	// ks_introsort by info (bwa/bwamem.c:187): equal keys are identical intervals, so any
-	// comparison sort gives the reference's byte-identical result.
+}
+
+// Pass 3: bwt_seed_strategy1 from every restart point (bwa/bwt.c:358-379, bwa/bwamem.c:170-185).
+// At most len / (min_seed_len + 1) + 1 intervals per read.  ALL 32 LANES OF A WARP MUST CALL.
+template <class Feeder>
+EMAB_HD void seed_p3(Fm &fm, Feeder &feed)
+{
+	SeedJob job;
+	job.seq = nullptr; job.len = 0; job.out = nullptr; job.cap = 0; job.id = -1;
+	int n = 0, ovf = 0, x = 0, i = 0, c = 0;
+	bool have_job = false, drained = false, active = false;
+	Intv ik;
+	ik.x0 = ik.x1 = ik.x2 = ik.info = 0;
+	for (;;) {
+		bool req = false;
+		while (!req && !drained) {
+			if (!active) {
+				while (x < job.len && job.seq[x] > 3) ++x;
+				if (x >= job.len) {  // this read is finished (or there is none yet)
+					if (have_job) { feed.done(job, n, ovf); have_job = false; }
+					if (feed.next(job)) { have_job = true; n = 0; ovf = 0; x = 0; }
+					else drained = true;
+					continue;
+				}
+				bwt_set_intv(fm.ix, job.seq[x], ik);
+				i = x + 1; active = true;
+			}
+			if (i < job.len && job.seq[i] < 4) { c = 3 - job.seq[i]; req = true; }
+			else { x = i < job.len ? i + 1 : job.len; active = false; }  // bwa/bwt.c:376-378
+		}
+		if (!EMAB_WARP_ANY(req)) break;
+		if (!req) continue;
+		Intv ok = bwt_extend1(fm, ik, c, 0);
+		if (ok.x2 < (uint64_t)opt::max_mem_intv && i - x >= opt::min_seed_len) {  // bwa/bwt.c:366-375
+			if (ok.x2 > 0) {
+				ok.info = (uint64_t)x << 32 | (uint64_t)(i + 1);
+				if (n < job.cap) job.out[n++] = ok; else ovf = 1;
+			}
+			x = i + 1; active = false;
+		} else { ik = ok; ++i; }
+	}
+}
+
+#define EMAB_P3_CAP 16  // pass 3 emits at most EMAB_MAX_READ_LEN / (min_seed_len + 1) + 1 = 13 intervals
+
+// Appends the pass-3 intervals to the pass-1/2 list and sorts by info (bwa/bwamem.c:187).  Returns the
+// total, or -1 if it does not fit `cap`.
+EMAB_HD int finish_intv(Intv *mem, int n12, const Intv *p3, int n3, int cap)
+{
+	if (n12 + n3 > cap) return -1;
+	for (int k = 0; k < n3; ++k) mem[n12 + k] = p3[k];
+	const int n = n12 + n3;
 	for (int a = 1; a < n; ++a) {
 		Intv t = mem[a];
 		int b = a;
@@ -342,3 +411,77 @@ EMAB_HD int collect_intv(Fm &fm, int len, const uint8_t *seq, Intv *mem, int mem
 	}
 	return n;
 }
+
+// one read, all passes: the host-side composition (tests/hostsim) of what the device runs as three roles
+struct OneReadFeeder {
+	SeedJob j; bool given; int n, ovf;
+	EMAB_HD bool next(SeedJob &o) { if (given) return false; given = true; o = j; return true; }
+	EMAB_HD void done(const SeedJob &, int n_, int ovf_) { n = n_; ovf = ovf_; }
+};
+
+EMAB_HD int collect_intv(Fm &fm, int len, const uint8_t *seq, Intv *mem, int mem_cap,
+                         Intv *buf0, Intv *buf1, int *overflow)
+{
+	Intv p3[EMAB_P3_CAP];
+	OneReadFeeder f12{{seq, len, mem, mem_cap, 0}, false, 0, 0}, f3{{seq, len, p3, EMAB_P3_CAP, 0}, false, 0, 0};
+	seed_p12(fm, f12, buf0, buf1);
+	seed_p3(fm, f3);
+	const int n = finish_intv(mem, f12.n, p3, f3.n, mem_cap);
+	if (f12.ovf || f3.ovf || n < 0) { *overflow = 1; return f12.n; }
+	return n;
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// device roles.  A launch is a persistent grid of warps; warps with (warp index % 4 == 3) start on the
+// pass-3 queue and move to the pass-1/2 queue when it is empty, the others the other way round.
+// ---------------------------------------------------------------------------------------------
+struct SeedBatch {
+	int n_reads;
+	const uint8_t *seq;
+	const int64_t *off;
+	Intv *intv;        // [n_reads][max_intv]: pass 1/2 output, completed in place by seed_finish
+	int max_intv;
+	Intv *p3;          // [n_reads][EMAB_P3_CAP]
+	int32_t *n12, *n3; // [n_reads]
+	Intv *scratch;     // [n_lanes][2][scratch_len]: per-LANE prev/curr lists
+	int scratch_len;
+	int *err;          // set to 3 on overflow
+	unsigned long long *queue;  // [0] pass-1/2 read counter, [1] pass-3 read counter
+	unsigned long long *touches;
+};
+
+struct QueueFeeder {
+	const SeedBatch &b;
+	int which;  // 0: pass 1/2, 1: pass 3
+	__device__ bool next(SeedJob &o)
+	{
+		const unsigned long long r = atomicAdd(&b.queue[which], 1ull);
+		if (r >= (unsigned long long)b.n_reads) return false;
+		o.id = (int)r;
+		o.seq = b.seq + b.off[r];
+		o.len = (int)(b.off[r + 1] - b.off[r]);
+		if (which == 0) { o.out = b.intv + (size_t)r * b.max_intv; o.cap = b.max_intv; }
+		else { o.out = b.p3 + (size_t)r * EMAB_P3_CAP; o.cap = EMAB_P3_CAP; }
+		return true;
+	}
+	__device__ void done(const SeedJob &j, int n, int ovf)
+	{
+		(which == 0 ? b.n12 : b.n3)[j.id] = n;
+		if (ovf) *b.err = 3;
+	}
+};
+
+__device__ __forceinline__ void seed_warp(const DevIndex &ix, const SeedBatch &b)
+{
+	const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+	Fm fm{ix, 0};
+	Intv *buf0 = b.scratch + (size_t)gt * 2 * b.scratch_len;
+	QueueFeeder f12{b, 0}, f3{b, 1};
+	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(fm, f3); seed_p12(fm, f12, buf0, buf0 + b.scratch_len); }
+	else { seed_p12(fm, f12, buf0, buf0 + b.scratch_len); seed_p3(fm, f3); }
+	unsigned touches = fm.touches;
+	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
+	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(b.touches, (unsigned long long)touches);
+}
+#endif

@@ -1,0 +1,69 @@
+// Host-side launcher of the seeding stage (seed.cuh) shared by emab_align_pairs and emab_smem_batch:
+//   k_seed         persistent warps, pass-1/2 and pass-3 roles fed from two atomic read queues
+//   k_seed_finish  thread / read: merge + sort by info (bwa/bwamem.c:187), SA-occurrence count
+#pragma once
+#include <cstdlib>
+#include "runtime.cuh"
+#include "seed.cuh"
+
+#define SEED_BLOCK 128
+
+static __global__ void __launch_bounds__(SEED_BLOCK)
+k_seed(DevIndex ix, SeedBatch b)
+{
+	seed_warp(ix, b);
+}
+
+static __global__ void __launch_bounds__(128)
+k_seed_finish(SeedBatch b, int32_t *n_intv, int32_t *occ_cnt)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= b.n_reads) return;
+	Intv *mem = b.intv + (size_t)r * b.max_intv;
+	int n = finish_intv(mem, b.n12[r], b.p3 + (size_t)r * EMAB_P3_CAP, b.n3[r], b.max_intv);
+	if (n < 0) { *b.err = 3; n = b.n12[r]; }
+	n_intv[r] = n;
+	if (occ_cnt) {
+		int occ = 0;
+		if ((int)(b.off[r + 1] - b.off[r]) >= opt::min_seed_len)
+			for (int i = 0; i < n; ++i) occ += intv_occ_count(mem[i].x2);
+		occ_cnt[r] = occ;
+	}
+}
+
+// EMAB_SEED_BPS: resident 128-thread blocks per SM of the persistent seeding grid (tuning knob)
+static inline int seed_blocks_per_sm()
+{
+	static int v = 0;
+	if (!v) { const char *e = getenv("EMAB_SEED_BPS"); v = e ? atoi(e) : 0; if (v < 1 || v > 16) v = 6; }
+	return v;
+}
+
+// Device buffers: d_intv [R][max_intv], d_n_intv [R], d_occ_cnt [R] or null, *d_err int, *d_touches u64 (zeroed by the caller).
+// Uses ctx slots 4 (lane scratch), 25 (pass-3 lists), 26 (per-pass counts + the two queue counters).
+static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, const int64_t *d_off, Intv *d_intv, int max_intv,
+                       int32_t *d_n_intv, int32_t *d_occ_cnt, int *d_err, unsigned long long *d_touches, int *launches)
+{
+	cudaStream_t st = c->stream;
+	int grid = c->n_sm * seed_blocks_per_sm();
+	const int want = (2 * R + SEED_BLOCK - 1) / SEED_BLOCK;  // never more lanes than (read, role) items
+	if (grid > want) grid = want;
+	if (grid < 1) grid = 1;
+	const size_t lanes = (size_t)grid * SEED_BLOCK;
+	SeedBatch b;
+	b.n_reads = R; b.seq = d_seq; b.off = d_off; b.intv = d_intv; b.max_intv = max_intv;
+	b.scratch_len = max_len + 1;
+	if (int rc = c->b[4].ensure(lanes * 2 * b.scratch_len * sizeof(Intv))) return rc;
+	if (int rc = c->b[25].ensure((size_t)R * EMAB_P3_CAP * sizeof(Intv))) return rc;
+	if (int rc = c->b[26].ensure((size_t)R * 8 + 16)) return rc;
+	b.scratch = c->b[4].as<Intv>();
+	b.p3 = c->b[25].as<Intv>();
+	b.queue = c->b[26].as<unsigned long long>();
+	b.n12 = (int32_t *)(b.queue + 2); b.n3 = b.n12 + R;
+	b.err = d_err; b.touches = d_touches;
+	CUDA_TRY(cudaMemsetAsync(b.queue, 0, 16, st));
+	k_seed<<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
+	k_seed_finish<<<(R + 127) / 128, 128, 0, st>>>(b, d_n_intv, d_occ_cnt);
+	*launches += 2;
+	return EMAB_OK;
+}
