@@ -253,6 +253,7 @@ struct Barcode {
 	std::vector<Entry> entries;            // insertion order; the reference walks them newest first
 	std::unordered_map<std::pair<std::string_view, int>, int, KeyHash> dict;
 	std::vector<int> final_;               // records_final
+	std::vector<std::vector<int>> opt_jobs; // -d: name-sorted records of each bad cloud, in cloud order (see process_pairs)
 	std::string sam;
 	std::string bc_str;                    // decode_bc(bc), printed in every BX tag of this barcode
 
@@ -474,7 +475,10 @@ void Barcode::build_clouds(const Session *s, const std::vector<Pair> &pairs)
 				if (cmp != 0) return cmp < 0;
 				return recs[a].mate < recs[b].mate;
 			});
-			if (s->apply_opt) mark_optimal(s, recs, split);
+			// -d: mark_optimal only writes the records' `active` bits, which nothing reads before the EM is
+			// flattened, so it is deferred to a serial pass in (barcode, cloud) order: the reference draws from ONE
+			// libc rand() stream in that order (src/split.c:229-306), which concurrent barcodes would scramble
+			if (s->apply_opt) opt_jobs.push_back(split);
 			for (size_t k = 0; k < cov; ++k) dict_add(split[k], c, true, many);
 		}
 		i = r + 1;
@@ -761,6 +765,11 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 		}
 		B.build_clouds(s, pairs);
 	}
+	if (s->apply_opt)
+		for (int b = 0; b < nb; ++b) {
+			for (const std::vector<int> &job : bcs[b].opt_jobs) mark_optimal(s, bcs[b].recs, job);
+			bcs[b].opt_jobs.clear();
+		}
 	const double t3 = now_ms();
 	// ---- flatten for the device EM
 	std::vector<int32_t> bc_entry_off(nb + 1, 0), bc_cloud_off(nb + 1, 0), bc_group_off(nb + 1, 0), bc_unit_off(nb + 1, 0), bc_full(nb, 0);
@@ -1064,6 +1073,7 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 	// buckets are in flight: bucket i's SAM text is written while i+1 runs on the GPU and i+2 is parsed.
 	int caps[PH_COUNT] = {3, 3, 3};
 	if (const char *e = getenv("EMAB_GATE_CAPS")) sscanf(e, "%d,%d,%d", &caps[0], &caps[1], &caps[2]);  // tuning knob
+	if (s->apply_opt) caps[PH_POST] = 1;  // -d consumes one rand() stream in bucket order (see process_pairs)
 	for (int k = 0; k < PH_COUNT; ++k) s->gate[k].cap = W > 1 ? std::max(1, std::min(caps[k], W)) : 1;
 	const int cap = W > 1 ? std::max(s->gate[PH_PARSE].cap, s->gate[PH_POST].cap) : 1;
 	const int per = std::max(1, s->n_threads / cap);

@@ -1,0 +1,86 @@
+"""GPU parity tests (-m gpu): BASELINE config 4 (platform sweep: -p haplotag / dbs on bucket input, -p tru /
+tellseq / 10x on interleaved FASTQ through -1) and the -d density optimiser, SAM bytes against the reference
+binary run on the same files with -t 1.  -d seeds libc rand() from time() in both programs
+(src/split.c:54-58), so both run under tests/shims/faketime.c (LD_PRELOAD) for that case."""
+import os
+import subprocess
+
+import pytest
+
+import helpers
+from test_gpu_sam import CLI, diff_msg, split_sam
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(cfg, platform):
+    from tools import synth
+    if not os.path.exists(helpers.ref_bin("ema")):
+        pytest.skip("oracle/_ref/ema missing")
+    return synth.build_config(cfg, helpers.DATA_ROOT, helpers.ref_bin("bwa"), platform=platform)
+
+
+def _run_both(p, platform, in_flag, tmp_path, extra=(), env=None, threads="6"):
+    ref_sam, our_sam = tmp_path / "ref.sam", tmp_path / "ours.sam"
+    common = ["align", in_flag, p["bucket"], "-r", p["fasta"], "-p", platform] + list(extra)
+    subprocess.run([helpers.ref_bin("ema")] + common + ["-t", "1", "-o", str(ref_sam)], check=True, stderr=subprocess.DEVNULL, env=env)
+    subprocess.run([CLI] + common + ["-t", threads, "-o", str(our_sam)], check=True, env=env)
+    h1, b1 = split_sam(our_sam.read_bytes())
+    h2, b2 = split_sam(ref_sam.read_bytes())
+    assert h1 == h2
+    assert len(b2) > 500
+    assert b1 == b2, diff_msg(b1, b2)
+    return b1
+
+
+@pytest.mark.parametrize("platform,in_flag", [("haplotag", "-s"), ("dbs", "-s"), ("tru", "-1"), ("tellseq", "-1")])
+def test_platform_sweep(platform, in_flag, tmp_path):
+    cfg = "c1_rep"
+    p = _data(cfg, platform)
+    body = _run_both(p, platform, in_flag, tmp_path)
+    assert any(b"\tBX:Z:" in l for l in body[:50])
+
+
+def test_10x_interleaved_fastq(tmp_path):
+    """-p 10x through -1 (extract_bc_10x on interleaved FASTQ ids, src/techs.c:19-30) on the tiny fixture's reference."""
+    from tools import synth
+    p = _data("tiny_rep", "10x")
+    n_contigs, clen, rseed, dup, nbc, ppb, indel = synth.CONFIGS["tiny_rep"]
+    contigs = synth.make_reference(n_contigs, clen, rseed, dup)
+    sim = synth.simulate_pairs(contigs, 40, 40, rseed + 2000, indel=indel)
+    fq = tmp_path / "reads.fq"
+    synth.write_interleaved_fastq(str(fq), sim, platform="10x")
+    q = dict(p)
+    q["bucket"] = str(fq)
+    _run_both(q, "10x", "-1", tmp_path)
+
+
+def test_read_group_and_bx_index(tmp_path):
+    """-R (read group header + RG tags) and -i (BX index suffix) reach the header and every record."""
+    p = _data("tiny_rep", "10x")
+    body = _run_both(p, "10x", "-s", tmp_path, extra=["-R", "@RG\\tID:rg1\\tSM:sample", "-i", "7"])
+    assert all(b"RG:Z:rg1" in l for l in body[:100])
+
+
+def _faketime_env(tmp_path):
+    so = tmp_path / "faketime.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-O2", os.path.join(helpers.ROOT, "tests", "shims", "faketime.c"), "-o", str(so)], check=True)
+    env = dict(os.environ)
+    env["LD_PRELOAD"] = str(so)
+    return env
+
+
+@pytest.mark.parametrize("platform,in_flag,cfg", [("10x", "-s", "c1_rep"), ("tru", "-1", "c1_rep")])
+def test_density_optimiser(platform, in_flag, cfg, tmp_path):
+    """-d (mark_optimal_alignments_in_cloud, src/split.c:38-338) under a pinned clock.  The duplicated
+    reference makes reads collide inside clouds, so the annealing actually runs; the test also checks that
+    -d changes the output, i.e. that the code path was exercised."""
+    p = _data(cfg, platform)
+    env = _faketime_env(tmp_path)
+    d_on = tmp_path / "on"; d_on.mkdir()
+    body_d = _run_both(p, platform, in_flag, d_on, extra=["-d"], env=env)
+    d_off = tmp_path / "off"; d_off.mkdir()
+    body = _run_both(p, platform, in_flag, d_off, env=env)
+    assert len(body) == len(body_d)
+    if body == body_d:
+        pytest.xfail("this data set has no bad cloud that -d re-decides: -d parity holds but the optimiser did not change the output")
