@@ -24,7 +24,7 @@
 //   * rows are synchronous across the warp: cells below the narrowest live band of the 32 lanes run
 //     unpredicated, 8 per iteration with the loads of the next group in flight (lanes whose task is over
 //     run along as zombies on their own dead columns); the few cells between the narrowest and the widest
-//     band are predicated per lane; the per-row scalar work (band shrink, z-drop, end-of-query score) is
+//     band run four at a time with their effects predicated per lane; the per-row scalar work (band shrink, z-drop, end-of-query score) is
 //     the reference's code per lane.
 //
 // Used by emab_extend_batch (config 5 of BASELINE.json) and by the pipeline's extension stage.
@@ -53,6 +53,16 @@ __device__ __forceinline__ int mul1024(int x)
 {
 	int r;
 	asm("mul.lo.s32 %0, %1, 1024;" : "=r"(r) : "r"(x));
+	return r;
+}
+
+// The key of the row maximum, "last j wins ties" (bwa/ksw.c:473): (h*16) * KEY_MUL + j as ONE IMAD on the FMA
+// pipe.  KEY_MUL is deliberately not a power of two: ptxas turns a shift-and-add into ALU-pipe instructions.
+constexpr int KEY_MUL = 4097;    // > any column index; 4000*16*4097 < 2^31
+__device__ __forceinline__ int row_key(int h, int j)
+{
+	int r;
+	asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(h), "n"(KEY_MUL), "r"(j));
 	return r;
 }
 
@@ -102,30 +112,38 @@ __device__ __forceinline__ ExtResult extend(uint32_t *eh, bool valid, int qlen, 
 	}
 	bool alive = valid;
 	unsigned long long cells = 0;
+	const int one = __popc(__activemask()) - 31;   // 1 (all lanes call), but not to the compiler: `x * one - c` stays an IMAD (FMA pipe)
+	int tb_next = valid && tlen > 0 ? tf(0) : 0;   // the target base is fetched one row ahead of its use
 	for (int i = 0;; ++i) {
 		alive = alive && i < tlen;
 		if (!__any_sync(FULL_MASK, alive)) break;
 		int width = 0, h1 = 0, f = 0, mkey = -1, j = 0;   // h1, f are SCALEd
 		uint32_t rlo = 0;
 		uint32_t *p = eh;
+		const int tb = tb_next;
+		if (alive && i + 1 < tlen) tb_next = tf(i + 1);
 		if (alive) {
 			if (s.beg < i - w) s.beg = i - w;
 			if (s.end > i + w + 1) s.end = i + w + 1;
 			if (s.end > qlen) s.end = qlen;
 			if (s.beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); h1 = h1 > 0 ? h1 * SCALE : 0; }
 			width = s.end > s.beg ? s.end - s.beg : 0;
-			rlo = row_scores(tf(i));
+			rlo = row_scores(tb);
 			p = eh + s.beg * 32;
 			j = s.beg;
 			cells += width;
 		}
+		// the first group's words are requested before the warp-wide reductions below (nfast >= 4 implies width >= 4
+		// on every live lane; the dead lanes compute on zeros)
+		uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+		if (width >= 4) { a0 = p[0]; a1 = p[32]; a2 = p[64]; a3 = p[96]; }
 		// Lanes whose task is over (or that never had one) run along as zombies on their own, now dead,
 		// columns, so that the cells up to the narrowest LIVE band need no predicate at all.
 		const int maxw = (int)__reduce_max_sync(FULL_MASK, (unsigned)width);
 		const int minw = (int)__reduce_min_sync(FULL_MASK, alive ? (unsigned)width : 0x7fffffffu);
 		const int nfast = minw < maxw ? minw : maxw;
 		const uint32_t rhi = (uint32_t)(uint8_t)(-SCALE);
-#define EMAB_LANES_CELL(WV, JJ)                                                                                  \
+#define EMAB_LANES_CELL(WV, JJ, KN)                                                                                \
 		{                                                                                                        \
 			const uint32_t wv = (WV);                                                                            \
 			const int diag = (int)(wv & 0xfff0u), e = (int)__umulhi(wv, 65536u);       /* h*16, e*16 */          \
@@ -133,8 +151,8 @@ __device__ __forceinline__ ExtResult extend(uint32_t *eh, bool valid, int qlen, 
 			const int sc = (int)prmt(sb, 0u, 0x8880u);       /* sign-extend byte 0 */                            \
 			const int M = __viaddmin_s32(diag, sc, mul1024(diag));  /* diag ? diag + sc : <= 0  (ksw.c:469) */   \
 			const int h = __vimax3_s32(M, e, f);                                                                 \
-			mkey = max(mkey, h * (65536 / SCALE) + (j + (JJ)));   /* last j wins ties (ksw.c:473) */             \
-			const int mo = M - oe_del * SCALE;                                                                   \
+			key##KN = row_key(h, KN);    /* position inside the group; last j wins ties (ksw.c:473) */             \
+			const int mo = M * one - oe_del * SCALE;              /* IMAD: keeps the subtraction off the ALU pipe */ \
 			const int en = __vimax_s32_relu(e - e_del * SCALE, mo);   /* E(i+1, j), opened from M only */        \
 			f = __vimax_s32_relu(f - e_ins * SCALE, mo);              /* F(i, j+1) */                            \
 			p[(JJ) * 32] = (uint32_t)(en * 65536 + (int)((wv & 0xfu) | (uint32_t)h1));  /* {base, H(i,j-1), E} */ \
@@ -142,53 +160,91 @@ __device__ __forceinline__ ExtResult extend(uint32_t *eh, bool valid, int qlen, 
 		}
 		int jj = 0;
 		{   // cells below the narrowest live band: no predicates; loads run one 4-cell group ahead of the math
-			uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0, b1, b2, b3;
-			if (nfast >= 4) { a0 = p[0]; a1 = p[32]; a2 = p[64]; a3 = p[96]; }
+			int key0, key1, key2, key3, key4, key5, key6, key7;
+			uint32_t b0, b1, b2, b3;
 #pragma unroll 1
 			for (; jj + 8 <= nfast; jj += 8) {
 				b0 = p[(jj + 4) * 32]; b1 = p[(jj + 5) * 32]; b2 = p[(jj + 6) * 32]; b3 = p[(jj + 7) * 32];
-				EMAB_LANES_CELL(a0, jj) EMAB_LANES_CELL(a1, jj + 1) EMAB_LANES_CELL(a2, jj + 2) EMAB_LANES_CELL(a3, jj + 3)
+				EMAB_LANES_CELL(a0, jj, 0) EMAB_LANES_CELL(a1, jj + 1, 1) EMAB_LANES_CELL(a2, jj + 2, 2) EMAB_LANES_CELL(a3, jj + 3, 3)
 				if (jj + 12 <= nfast) { a0 = p[(jj + 8) * 32]; a1 = p[(jj + 9) * 32]; a2 = p[(jj + 10) * 32]; a3 = p[(jj + 11) * 32]; }
-				EMAB_LANES_CELL(b0, jj + 4) EMAB_LANES_CELL(b1, jj + 5) EMAB_LANES_CELL(b2, jj + 6) EMAB_LANES_CELL(b3, jj + 7)
+				EMAB_LANES_CELL(b0, jj + 4, 4) EMAB_LANES_CELL(b1, jj + 5, 5) EMAB_LANES_CELL(b2, jj + 6, 6) EMAB_LANES_CELL(b3, jj + 7, 7)
+				/* row maximum: the group's best key (one ALU-pipe max per two cells), then its offset in the row */
+				mkey = max(mkey, __vimax3_s32(__vimax3_s32(key0, key1, key2), __vimax3_s32(key3, key4, key5), max(key6, key7)) + (j + jj));
 			}
 			if (jj + 4 <= nfast) {
-				EMAB_LANES_CELL(a0, jj) EMAB_LANES_CELL(a1, jj + 1) EMAB_LANES_CELL(a2, jj + 2) EMAB_LANES_CELL(a3, jj + 3)
+				EMAB_LANES_CELL(a0, jj, 0) EMAB_LANES_CELL(a1, jj + 1, 1) EMAB_LANES_CELL(a2, jj + 2, 2) EMAB_LANES_CELL(a3, jj + 3, 3)
+				mkey = max(mkey, __vimax3_s32(__vimax3_s32(key0, key1, key2), key3, -1) + (j + jj));
 				jj += 4;
 			}
 		}
-#pragma unroll 1
-		for (; jj < maxw; ++jj) {
-			if (jj < width || !alive) EMAB_LANES_CELL(p[jj * 32], jj)
-		}
 #undef EMAB_LANES_CELL
-		h1 /= SCALE;
+		// cells between the narrowest and the widest band of the warp: four at a time, branch-free.  A lane whose
+		// band is over computes on a zero word and its effects (store, row maximum, H carried to the next column)
+		// are predicated off, so the four cells of a group still overlap in the pipes; the band is contiguous,
+		// so a garbage f past a lane's last cell is never consumed.
+#define EMAB_LANES_TAIL(PK, WV, JJ)                                                                              \
+		{                                                                                                        \
+			const uint32_t wv = (WV);                                                                            \
+			const int diag = (int)(wv & 0xfff0u), e = (int)__umulhi(wv, 65536u);                                 \
+			const uint32_t sb = prmt(rlo, rhi, wv);                                                              \
+			const int sc = (int)prmt(sb, 0u, 0x8880u);                                                           \
+			const int M = __viaddmin_s32(diag, sc, mul1024(diag));                                               \
+			const int h = __vimax3_s32(M, e, f);                                                                 \
+			const int key = row_key(h, j + (JJ));                                                                \
+			mkey = max(mkey, (PK) ? key : -1);                                                                   \
+			const int mo = M * one - oe_del * SCALE;              /* IMAD: keeps the subtraction off the ALU pipe */ \
+			const int en = __vimax_s32_relu(e - e_del * SCALE, mo);                                              \
+			f = __vimax_s32_relu(f - e_ins * SCALE, mo);                                                         \
+			if (PK) p[(JJ) * 32] = (uint32_t)(en * 65536 + (int)((wv & 0xfu) | (uint32_t)h1));                   \
+			h1 = (PK) ? h : h1;                                                                                  \
+		}
+#pragma unroll 1
+		for (; jj < maxw; jj += 4) {
+			const bool p0 = jj < width, p1 = jj + 1 < width, p2 = jj + 2 < width, p3 = jj + 3 < width;
+			uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+			if (p0) c0 = p[jj * 32];
+			if (p1) c1 = p[(jj + 1) * 32];
+			if (p2) c2 = p[(jj + 2) * 32];
+			if (p3) c3 = p[(jj + 3) * 32];
+			EMAB_LANES_TAIL(p0, c0, jj) EMAB_LANES_TAIL(p1, c1, jj + 1) EMAB_LANES_TAIL(p2, c2, jj + 2) EMAB_LANES_TAIL(p3, c3, jj + 3)
+		}
+#undef EMAB_LANES_TAIL
 		if (alive) {
-			eh[s.end * 32] = (eh[s.end * 32] & 0xfu) | (uint32_t)(h1 * SCALE);   // eh[end] = {h1, 0}  (bwa/ksw.c:485); the base stays
+			// eh[end] = {h1, 0} (bwa/ksw.c:485); the base of that column stays.  The first word of the band is
+			// fetched right behind the store (beg may equal end) so that it is there when the band is trimmed.
+			uint32_t *pe = eh + s.end * 32;
+			*pe = (*pe & 0xfu) | (uint32_t)h1;
+			const uint32_t wb = eh[s.beg * 32];
+			const int h1u = h1 / SCALE;
 			const int jfin = width > 0 ? s.end : s.beg;
 			if (jfin == qlen) {                                            // later rows win ties (bwa/ksw.c:486-489)
-				if (!(s.g > h1)) s.g_i = i;
-				s.g = s.g > h1 ? s.g : h1;
+				if (!(s.g > h1u)) s.g_i = i;
+				s.g = s.g > h1u ? s.g : h1u;
 			}
-			const int m = mkey < 0 ? 0 : mkey >> 16, mj = mkey < 0 ? -1 : (mkey & 0xffff);
-			if (m == 0) alive = false;
-			else {
-				if (m > s.best) {
-					s.best = m; s.best_i = i; s.best_j = mj;
-					int d = mj - i; d = d < 0 ? -d : d;
-					s.max_off = s.max_off > d ? s.max_off : d;
-				} else if (zdrop > 0) {                                    // bwa/ksw.c:494-500
-					const int di = i - s.best_i, dj = mj - s.best_j;
-					if (di > dj) { if (s.best - m - (di - dj) * e_del > zdrop) alive = false; }
-					else { if (s.best - m - (dj - di) * e_ins > zdrop) alive = false; }
-				}
-				if (alive) {                                               // bwa/ksw.c:502-505
-					int a = s.beg;
+			const int m16 = mkey < 0 ? 0 : mkey / KEY_MUL, m = m16 / SCALE, mj = mkey < 0 ? -1 : mkey - m16 * KEY_MUL;
+			// best cell / z-drop (bwa/ksw.c:490-500) without branches; e_del == e_ins (asserted above)
+			const bool better = m > s.best;
+			int gap = (i - s.best_i) - (mj - s.best_j); gap = gap < 0 ? -gap : gap;
+			const bool drop = !better && zdrop > 0 && s.best - m - gap * e_del > zdrop;
+			int d = mj - i; d = d < 0 ? -d : d;
+			s.max_off = better && d > s.max_off ? d : s.max_off;
+			s.best_i = better ? i : s.best_i;
+			s.best_j = better ? mj : s.best_j;
+			s.best = better ? m : s.best;
+			alive = m != 0 && !drop;
+			if (alive) {                                                   // bwa/ksw.c:502-505
+				int a = s.beg;
+				if (a < s.end && (wb & 0xfffffff0u) == 0) {
+					++a;
 					while (a < s.end && (eh[a * 32] & 0xfffffff0u) == 0) ++a;
-					s.beg = a;
-					a = s.end;
-					while (a >= s.beg && (eh[a * 32] & 0xfffffff0u) == 0) --a;
-					s.end = a + 2 < qlen ? a + 2 : qlen;
 				}
+				s.beg = a;
+				a = s.end;
+				if (h1 == 0) {   // eh[end] was just written: {h1, 0}
+					--a;
+					while (a >= s.beg && (eh[a * 32] & 0xfffffff0u) == 0) --a;
+				}
+				s.end = a + 2 < qlen ? a + 2 : qlen;
 			}
 		}
 	}
