@@ -219,7 +219,7 @@ class Stats(C.Structure):
     _fields_ = [("extend_cells", C.c_int64), ("global_cells", C.c_int64), ("local_cells", C.c_int64), ("occ_touches", C.c_int64),
                 ("n_occ", C.c_int64), ("n_regs", C.c_int64), ("kernel_ms", C.c_double), ("ms_seed", C.c_double), ("ms_chain", C.c_double),
                 ("ms_align1", C.c_double), ("ms_rescue", C.c_double), ("ms_finalize", C.c_double), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("launches", C.c_int32), ("pad", C.c_int32)]
+                ("d2h_bytes", C.c_int64), ("launches", C.c_int32), ("pad", C.c_int32), ("rescue_planned_cells", C.c_int64), ("rescue_unplanned", C.c_int64)]
 
 
 class PairsResult(C.Structure):

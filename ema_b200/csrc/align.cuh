@@ -409,18 +409,19 @@ EMAB_HD int infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist)
 
 // mem_matesw with EMA's pes[] (src/bwabridge.c:216-229): only orientation 1 (FR) is live, low = -35,
 // high = 500.  `a` is a hit of the anchor read, ms the mate's sequence; ma the mate's region list.
-template <class DP>
-EMAB_HD int matesw(const DevIndex &ix, DP &dp, const Reg &a, int l_ms, const uint8_t *ms, Reg *ma, int *n_ma)
+// The part of mem_matesw that decides whether a local SW runs and on which window (bwa/bwamem_pair.c:143-172):
+// false when a hit of the mate already pairs with the anchor, or the clamped window leaves the anchor's contig
+// or is shorter than a seed.  The window depends on the anchor and the mate's length only — not on `ma` — so
+// the SW result for an (anchor, mate) is a pure function the pipeline may compute ahead of time.
+EMAB_HD bool matesw_window(const DevIndex &ix, const Reg &a, int l_ms, const Reg *ma, int n_ma, int64_t *rb_, int64_t *re_)
 {
 	const int64_t l_pac = ix.l_pac;
 	const int low = -35, high = 500;
-	int skip1 = 0;
-	for (int i = 0; i < *n_ma; ++i) {
+	for (int i = 0; i < n_ma; ++i) {
 		int64_t dist;
 		int r = infer_dir(l_pac, a.rb, ma[i].rb, &dist);
-		if (r == 1 && dist >= low && dist <= high) skip1 = 1;
+		if (r == 1 && dist >= low && dist <= high) return false;  // a consistent pair exists
 	}
-	if (skip1) return 0;  // a consistent pair exists
 	// r = 1: is_rev = 1, is_larger = 1
 	int64_t rb = (a.rb + low) - l_ms;
 	int64_t re = a.rb + high;
@@ -428,8 +429,18 @@ EMAB_HD int matesw(const DevIndex &ix, DP &dp, const Reg &a, int l_ms, const uin
 	if (re > l_pac << 1) re = l_pac << 1;
 	int rid = -1;
 	if (rb < re) bns_clamp(ix, &rb, (rb + re) >> 1, &re, &rid);
+	*rb_ = rb; *re_ = re;
+	return a.rid == rid && re - rb >= opt::min_seed_len;
+}
+
+template <class DP>
+EMAB_HD int matesw(const DevIndex &ix, DP &dp, const Reg &a, int l_ms, const uint8_t *ms, Reg *ma, int *n_ma)
+{
+	const int64_t l_pac = ix.l_pac;
+	int64_t rb, re;
+	const bool run = matesw_window(ix, a, l_ms, ma, *n_ma, &rb, &re);
 	int n = 0;
-	if (a.rid == rid && re - rb >= opt::min_seed_len) {
+	if (run) {
 		// query = reverse complement of ms; target = ref[rb, re)
 		LocResult aln = dp.local(ms, l_ms, rb, (int)(re - rb));
 		if (aln.score >= opt::min_seed_len && aln.qb >= 0) {

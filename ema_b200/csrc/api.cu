@@ -125,7 +125,10 @@ extern "C" int emab_index_load(const char *prefix, int device, emab_index_t **ou
 	ix->d.ann_offset = (const int64_t *)ix->d_ann_off;
 	ix->d.ann_len = (const int32_t *)ix->d_ann_len;
 	// dense SA
-	const bool small = ix->d.seq_len < 0xffffffffull;
+	// EMAB_SA64=1 forces the u64 table of an hg38-sized index (2*l_pac >= 2^32) on a small one, so the tests
+	// can walk that branch without a 3.1 Gbp reference
+	const char *force64 = getenv("EMAB_SA64");
+	const bool small = ix->d.seq_len < 0xffffffffull && !(force64 && atoi(force64) == 1);
 	size_t dense_bytes = (ix->d.seq_len + 1) * (small ? 4 : 8);
 	CUDA_TRY(cudaMalloc(&ix->d_sa_dense, dense_bytes));
 	cudaEvent_t e0, e1;
@@ -191,11 +194,12 @@ extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaEventCreate(&c->ev0));
 	CUDA_TRY(cudaEventCreate(&c->ev1));
-	CUDA_TRY(cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)));
+	CUDA_TRY(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
 	c->n_sm = prop.multiProcessorCount;
 	if (const char *e = getenv("EMAB_SW_MODE")) c->sw_mode = atoi(e);  // tuning knob, see emab_set_sw_mode
+	if (const char *e = getenv("EMAB_RESCUE_PLAN")) c->rescue_plan = atoi(e) != 0;  // tuning knob: 0 = one warp-per-pair rescue kernel
 	if (const char *e = getenv("EMAB_PL_BPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->pl_bps = v; }  // persistent SW grids: blocks per SM
 	*out = c;
 	return EMAB_OK;

@@ -158,11 +158,8 @@ EMAB_HD Intv bwt_extend1(Fm &fm, const Intv &ik, int c, int is_back)
 // (bwt_sa is a pure function of the index; SURVEY.md §7 hard part 6).
 EMAB_HD uint64_t bwt_sa_dense(const DevIndex &ix, uint64_t k)
 {
-	if (ix.sa32) {
-		uint32_t v = ix.sa32[k];
-		return k == 0 ? ~0ull : (uint64_t)v;  // SA[0] = (u64)-1 by construction (bwa/bwt.c:83,437)
-	}
-	return ix.sa64[k];
+	if (k == 0) return ~0ull;  // SA[0] = (u64)-1 by construction (bwa/bwt.c:83,437)
+	return ix.sa32 ? (uint64_t)ix.sa32[k] : ix.sa64[k];
 }
 
 // bwt_invPsi (bwa/bwt.c:53-59): LF-mapping step, used by the dense-SA builder and the walking bwt_sa.

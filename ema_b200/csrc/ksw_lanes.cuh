@@ -112,7 +112,10 @@ __device__ __forceinline__ ExtResult extend(uint32_t *eh, bool valid, int qlen, 
 	}
 	bool alive = valid;
 	unsigned long long cells = 0;
-	const int one = __popc(__activemask()) - 31;   // 1 (all lanes call), but not to the compiler: `x * one - c` stays an IMAD (FMA pipe)
+	// 1, but not to the compiler: `x * one - c` stays an IMAD (FMA pipe).  A *_sync vote over the full mask (all lanes
+	// must call anyway) — __activemask() is NOT the same thing: after the divergent set-up above the warp need not
+	// have reconverged, and a partial mask here silently corrupts every gap-open term.
+	const int one = __popc(__ballot_sync(FULL_MASK, true)) - 31;
 	int tb_next = valid && tlen > 0 ? tf(0) : 0;   // the target base is fetched one row ahead of its use
 	for (int i = 0;; ++i) {
 		alive = alive && i < tlen;

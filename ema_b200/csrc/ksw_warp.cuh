@@ -277,58 +277,90 @@ __device__ inline int global_backtrack(const uint8_t *z, int qlen, int tlen, int
 // ---------------------------------------------------------------------------------------------
 struct PassResult { int score, te, qe, score2, te2; };
 
-template <class TF>
+// per-row substitution bytes of bwa_fill_scmat(1,4) (bwa/bwa.c:136-146) for a byte permute: byte q of the pair
+// (lo, hi) is the score of target base t against query code q = A,C,G,T, N (-1) and 5 = the zero-scoring
+// padding of the striped query profile (bwa/ksw.c:95-113)
+__device__ __forceinline__ uint32_t local_row_scores(int t)
+{
+	const uint32_t mis = (uint32_t)(uint8_t)(-opt::b) * 0x01010101u;
+	const uint32_t flip = (uint32_t)(uint8_t)(-opt::b) ^ (uint32_t)(uint8_t)opt::a;
+	return t < 4 ? mis ^ (flip << (t << 3)) : 0xffffffffu;
+}
+__device__ __forceinline__ int local_score(uint32_t lo, int q)
+{
+	uint32_t b, r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(b) : "r"(lo), "r"(0x000000ffu), "r"((uint32_t)q));   // byte 4 = -1 (N), byte 5 = 0 (padding)
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(0u), "r"(0x8880u));                 // sign-extend byte 0
+	return (int)r;
+}
+
+// One ksw_u8 / ksw_i16 pass (bwa/ksw.c:122-253,255-370) with the query laid out in STRIPS: lane l owns the S
+// consecutive columns [l*S, l*S+S) and keeps their H(i-1,.) and E(i,.) in registers.  A row is then
+//   1 shuffle   H(i-1, l*S-1) from the lane below,
+//   S cells     H' = max(0, diag+s, E) and the gap-open term tI = max(H'-oe, 0)            (registers only)
+//   1 scan      exclusive max-plus prefix of the lanes' max(tI_j + j*e): F entering each strip (5 shuffles)
+//   S cells     F(j) = max_{k<j}(tI_k + k*e) - (j-1)*e, H = max(H', F), E for the next row   (registers only)
+//   1 REDUX     the row maximum,
+// i.e. 7 shuffles per row whatever the query length, where 32-column chunks need 8 per chunk and a shared-memory
+// round trip per cell.  Same values as the chunked form: F opened from an F-derived H never wins (oe > e), see
+// the header.  Columns >= qpad are computed but never stored nor counted.
+template <int S, class TF>
 __device__ PassResult warp_local_pass(WarpDP &sm, int qlen, int qpad, const TF &tf, int tlen, bool is_u8, int minsc, int endsc,
                                       bool want_sub, unsigned long long *cells)
 {
 	const int lane = threadIdx.x & 31;
-	const int e_del = opt::e_del, e_ins = opt::e_ins, oe_del = opt::oe_del, oe_ins = opt::oe_ins;
+	constexpr int e_del = opt::e_del, e_ins = opt::e_ins, oe_del = opt::oe_del, oe_ins = opt::oe_ins;
 	const int shift = opt::b;  // -(min score) = 4 with bwa_fill_scmat(1,4)  (bwa/ksw.c:85-91)
-	// H[j+1] = H(i-1, j) ; E[j] = E(i, j)
-	for (int j = lane; j <= qpad; j += 32) { sm.H[j] = 0; sm.E[j] = 0; }
-	__syncwarp();
+	const int j0 = lane * S;
+	int H[S], E[S], Q[S];      // H(i-1, j0+k), E(i, j0+k), query code
+#pragma unroll
+	for (int k = 0; k < S; ++k) { H[k] = 0; E[k] = 0; Q[k] = j0 + k < qpad ? sm.q[j0 + k] : 5; }
 	int gmax = 0, te = -1, qe = 0;
 	int tchunk = 0;
 	int i;
 	for (i = 0; i < tlen; ++i) {
 		if ((i & 31) == 0) tchunk = (i + lane < tlen) ? tf(i + lane) : 4;
-		const int tb = __shfl_sync(FULL_MASK, tchunk, i & 31);
-		int carry_diag = 0;  // H(i-1, j0-1)
-		int carry_f = 0;     // F(i, j0)
+		const uint32_t rlo = local_row_scores(__shfl_sync(FULL_MASK, tchunk, i & 31));
+		int dl = __shfl_up_sync(FULL_MASK, H[S - 1], 1);   // H(i-1, j0-1)
+		if (lane == 0) dl = 0;
+		int hq[S], tI[S];
+		int top = KSW_NEG_INF;
+#pragma unroll
+		for (int k = 0; k < S; ++k) {
+			const int diag = k ? H[k - 1] : dl;
+			int v = diag + local_score(rlo, Q[k]);
+			v = v > 0 ? v : 0;
+			v = v > E[k] ? v : E[k];                       // H' = max(0, diag+s, E)
+			hq[k] = v;
+			int t = v - oe_ins; t = t > 0 ? t : 0;
+			tI[k] = t;
+			top = max(top, t + (j0 + k) * e_ins);
+		}
+		const int incl = warp_scan_max(top, lane);
+		int run = __shfl_up_sync(FULL_MASK, incl, 1);      // max_{j < j0} (tI_j + j*e)
+		if (lane == 0) run = KSW_NEG_INF;
 		int m = 0;
-		for (int j0 = 0; j0 < qpad; j0 += 32) {
-			const int j = j0 + lane;
-			const bool act = j < qpad;
-			int hp = 0, e = 0, qb = 5;
-			if (act) { hp = sm.H[j + 1]; e = sm.E[j]; qb = sm.q[j]; }
-			int diag = __shfl_up_sync(FULL_MASK, hp, 1);
-			if (lane == 0) diag = carry_diag;
-			carry_diag = __shfl_sync(FULL_MASK, hp, 31);
-			const int s = qb > 4 ? 0 : sc_mat(tb, qb);
-			int hq = diag + s; hq = hq > 0 ? hq : 0;
-			hq = hq > e ? hq : e;                          // H' = max(0, diag+s, E)
-			int tI = hq - oe_ins; tI = tI > 0 ? tI : 0;
-			const int p = warp_scan_max(tI + j * e_ins, lane);
-			const int px = __shfl_up_sync(FULL_MASK, p, 1);
-			int f = carry_f - lane * e_ins;
-			if (lane) f = max(f, px - (j - 1) * e_ins);
-			f = f > 0 ? f : 0;
-			const int h = hq > f ? hq : f;
-			if (act) {
+#pragma unroll
+		for (int k = 0; k < S; ++k) {
+			const int j = j0 + k;
+			int f = run - (j - 1) * e_ins; f = f > 0 ? f : 0;
+			const int h = hq[k] > f ? hq[k] : f;
+			run = max(run, tI[k] + j * e_ins);
+			if (j < qpad) {
 				int t = h - oe_del; t = t > 0 ? t : 0;
-				int en = e - e_del; en = en > t ? en : t;   // gaps open from H here (bwa/ksw.c:189-196)
-				sm.E[j] = en;
-				sm.H[j + 1] = h;
+				int en = E[k] - e_del; en = en > t ? en : t;   // gaps open from H here (bwa/ksw.c:189-196)
+				E[k] = en;
+				H[k] = h;
 				m = max(m, h);
 			}
-			carry_f = __shfl_sync(FULL_MASK, max(f - e_ins, tI), 31);   // F(i, j0+32)
 		}
 		const int imax = warp_max(m);
 		if (want_sub && lane == 0 && i < KSW_MAX_TLEN) sm.rowmax[i] = (uint16_t)imax;
 		if (imax > gmax) {  // bwa/ksw.c:224-229
 			gmax = imax; te = i;
 			int c = 0x7fffffff;   // qe = smallest query index holding the row maximum (bwa/ksw.c:235-239)
-			for (int j = lane; j < qpad; j += 32) if (sm.H[j + 1] == imax) { c = j; break; }
+#pragma unroll
+			for (int k = S - 1; k >= 0; --k) if (j0 + k < qpad && H[k] == imax) c = j0 + k;
 			qe = -warp_max(-c);
 			if ((is_u8 && gmax + shift >= 255) || gmax >= endsc) { ++i; break; }
 		}
@@ -358,6 +390,18 @@ __device__ PassResult warp_local_pass(WarpDP &sm, int qlen, int qpad, const TF &
 		if (run_val >= 0 && (run_row < lo || run_row > hi) && run_val > r.score2) { r.score2 = run_val; r.te2 = run_row; }
 	}
 	return r;
+}
+
+// strip width by query length: the smallest instantiated S with 32*S >= qpad (qpad <= EMAB_MAX_READ_LEN + 16)
+template <class TF>
+__device__ __forceinline__ PassResult warp_local_pass(WarpDP &sm, int qlen, int qpad, const TF &tf, int tlen, bool is_u8, int minsc, int endsc,
+                                                      bool want_sub, unsigned long long *cells)
+{
+	static_assert(EMAB_MAX_READ_LEN + 16 <= 32 * 9, "widest strip");
+	if (qpad <= 32 * 4) return warp_local_pass<4>(sm, qlen, qpad, tf, tlen, is_u8, minsc, endsc, want_sub, cells);
+	if (qpad <= 32 * 5) return warp_local_pass<5>(sm, qlen, qpad, tf, tlen, is_u8, minsc, endsc, want_sub, cells);
+	if (qpad <= 32 * 7) return warp_local_pass<7>(sm, qlen, qpad, tf, tlen, is_u8, minsc, endsc, want_sub, cells);
+	return warp_local_pass<9>(sm, qlen, qpad, tf, tlen, is_u8, minsc, endsc, want_sub, cells);
 }
 
 template <class TF>

@@ -31,14 +31,29 @@ static_assert(sizeof(emab_cand_t) == 56, "emab_cand_t is a 56-byte wire record")
 // ---------------------------------------------------------------------------------------------
 // device DP policy: the warp-cooperative kernels of ksw_warp.cuh
 // ---------------------------------------------------------------------------------------------
+// One mem_matesw local alignment computed ahead of the rescue replay (see k_rescue_plan): the key is what
+// ksw_align2 is a pure function of — the mate's sequence and the reference window — the value its result.
+struct RescueTask {
+	const uint8_t *ms;             // the mate's nt4 sequence (null: slot not filled)
+	int64_t rb;
+	int32_t l_ms, tlen;
+	LocResult res;
+	int32_t pad;
+	unsigned long long cells;      // DP cells of this call (added to the pipeline's count when the replay consumes it)
+};
+static_assert(sizeof(RescueTask) == 64, "RescueTask is one 64-byte record");
+#define RESCUE_PLAN_MAX 24         // tasks planned per pair; anything beyond is aligned inline by the replay
+
 struct WarpPolicy {
 	const DevIndex &ix;
 	WarpDP &sm;
-	unsigned long long *counters;  // [0] extend cells, [3] global cells, [4] local cells
+	unsigned long long *counters;  // [0] extend cells, [3] global cells, [4] local cells, [11] rescue SWs not planned ahead
 	uint8_t *z;                    // this warp's backtrack scratch
 	size_t z_cap;
 	uint32_t *tmp;                 // this warp's cigar scratch [EMAB_MAX_CIGAR]
 	int *err;
+	const RescueTask *cache = nullptr;  // this pair's precomputed local alignments
+	int n_cache = 0;
 
 	__device__ ExtResult extend(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, int end_bonus, int h0)
 	{
@@ -81,6 +96,27 @@ struct WarpPolicy {
 		__syncwarp();
 		return r;
 	}
+	// the same call during the rescue replay: answered from the pair's planned tasks when it is there
+	__device__ LocResult local_cached(const uint8_t *ms, int l_ms, int64_t rb, int tlen)
+	{
+		for (int t = 0; t < n_cache; ++t) {
+			const RescueTask &k = cache[t];
+			if (k.ms == ms && k.rb == rb && k.tlen == tlen && k.l_ms == l_ms) {
+				if ((threadIdx.x & 31) == 0) atomicAdd(&counters[4], k.cells);
+				return k.res;
+			}
+		}
+		if ((threadIdx.x & 31) == 0) atomicAdd(&counters[11], 1ull);
+		return local_unplanned(ms, l_ms, rb, tlen);
+	}
+	// rare: kept out of line so that the replay kernel does not carry the DP's registers
+	__device__ __noinline__ LocResult local_unplanned(const uint8_t *ms, int l_ms, int64_t rb, int tlen) { return local(ms, l_ms, rb, tlen); }
+};
+
+// the replay's policy: mem_matesw's ksw_align2 goes through the cache, everything else is WarpPolicy
+struct ReplayPolicy : WarpPolicy {
+	__device__ ReplayPolicy(const WarpPolicy &b) : WarpPolicy(b) {}
+	__device__ LocResult local(const uint8_t *ms, int l_ms, int64_t rb, int tlen) { return local_cached(ms, l_ms, rb, tlen); }
 };
 
 __device__ __forceinline__ int next_item(unsigned long long *counter, int lane)
@@ -142,19 +178,104 @@ k_align1_lanes(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off,
 	lanes::align1_warp(ix, n_reads, seq, off, occ_off, p, RESCUE_ROOM, lanes_smem + threadIdx.x, &counters[5], err, &counters[0], &counters[3]);
 }
 
+// Mate rescue in three kernels.  bwa_mem_mate_sw's rescue half is sequential per pair (every mem_matesw sees the
+// regions the previous ones added), and a pair in a repeat runs up to 100 local alignments of ~90 k cells
+// back to back while most pairs run none: as ONE warp-per-pair kernel the bucket waits for its slowest pair.
+// But the alignment itself is a pure function of (mate sequence, window), and the window of the anchor only:
+//   k_rescue_plan  thread / pair  the anchors of both directions tested against the regions as they stand
+//                                 BEFORE any rescue; every mem_matesw that would align becomes a task
+//   k_rescue_sw    warp / task    ksw_align2 of all tasks of the bucket, evenly spread over the GPU
+//   k_rescue       warp / pair    the reference's sequential loop, its ksw_align2 calls answered from the
+//                                 pair's tasks.  An alignment the plan did not foresee (a region added or dropped
+//                                 by an earlier rescue changed the decision) is computed inline, so the result
+//                                 is the reference's whatever the plan guessed; a planned one that the replay
+//                                 never asks for is wasted work and nothing else.
+__global__ void __launch_bounds__(128)
+k_rescue_plan(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p,
+              RescueTask *tasks, int task_cap, int32_t *task_beg, int32_t *task_n, unsigned long long *counters)
+{
+	const int pr = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pr >= n_pairs) return;
+	const int score_delta = 25;
+	int64_t t_rb[RESCUE_PLAN_MAX];
+	int32_t t_len[RESCUE_PLAN_MAX];
+	uint32_t t_dir = 0;
+	int n = 0;
+	const int rd[2] = {2 * pr, 2 * pr + 1};
+	const Reg *g[2]; int ng[2], best[2], len[2];
+	for (int m = 0; m < 2; ++m) {
+		g[m] = p.regs + (occ_off[rd[m]] + (size_t)RESCUE_ROOM * rd[m]);
+		ng[m] = p.n_regs[rd[m]];
+		len[m] = (int)(off[rd[m] + 1] - off[rd[m]]);
+		best[m] = 0;
+		for (int i = 0; i < ng[m]; ++i) if (g[m][i].score > best[m]) best[m] = g[m][i].score;
+	}
+	// direction 0: hits of read 2 rescue read 1 (src/bwabridge.c:239-259); direction 1: the other way round
+	for (int d = 0; d < 2; ++d) {
+		const int an = d == 0 ? 1 : 0, mt = 1 - an;
+		int num = 0;
+		for (int i = 0; i < ng[an] && num < opt::max_matesw; ++i) {
+			if (g[an][i].score < best[an] - score_delta) continue;
+			++num;
+			int64_t rb, re;
+			if (!matesw_window(ix, g[an][i], len[mt], g[mt], ng[mt], &rb, &re)) continue;
+			if (re - rb > KSW_MAX_TLEN || n >= RESCUE_PLAN_MAX) continue;
+			t_rb[n] = rb; t_len[n] = (int)(re - rb); t_dir |= (uint32_t)d << n; ++n;
+		}
+	}
+	int beg = 0;
+	if (n) {
+		beg = (int)atomicAdd(&counters[8], (unsigned long long)n);
+		if (beg + n > task_cap) {  // out of room: these alignments run inline in the replay
+			for (int t = beg; t < task_cap; ++t) tasks[t].ms = nullptr;
+			n = 0;
+		}
+	}
+	task_beg[pr] = beg; task_n[pr] = n;
+	for (int t = 0; t < n; ++t) {
+		const int mt = (t_dir >> t & 1) ? 1 : 0;   // direction 0 aligns read 1 (index 0), direction 1 read 2
+		RescueTask &k = tasks[beg + t];
+		k.ms = seq + off[rd[mt]]; k.rb = t_rb[t]; k.l_ms = len[mt]; k.tlen = t_len[t]; k.cells = 0; k.pad = 0;
+	}
+}
+
+__global__ void __launch_bounds__(PL_WARPS * 32, 3)
+k_rescue_sw(DevIndex ix, RescueTask *tasks, int task_cap, int *err, unsigned long long *counters)
+{
+	__shared__ WarpDP sm_all[PL_WARPS];
+	const int lane = threadIdx.x & 31;
+	WarpPolicy dp{ix, sm_all[threadIdx.x >> 5], counters, nullptr, 0, nullptr, err};
+	const unsigned long long planned = counters[8];
+	const int n_tasks = planned < (unsigned long long)task_cap ? (int)planned : task_cap;
+	for (;;) {
+		const int t = next_item(&counters[9], lane);
+		if (t >= n_tasks) break;
+		RescueTask &k = tasks[t];
+		if (k.ms == nullptr) continue;
+		dp.counters = &k.cells - 4;   // WarpPolicy::local counts into counters[4]: this task's own cell count
+		const LocResult r = dp.local(k.ms, k.l_ms, k.rb, k.tlen);
+		__syncwarp();
+		if (lane == 0) { k.res = r; atomicAdd(&counters[10], k.cells); }
+		__syncwarp();
+	}
+}
+
 __global__ void __launch_bounds__(PL_WARPS * 32)
 k_rescue(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p,
-         uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
+         uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters,
+         const RescueTask *tasks, const int32_t *task_beg, const int32_t *task_n)
 {
 	__shared__ WarpDP sm_all[PL_WARPS];
 	const int lane = threadIdx.x & 31, gw = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
-	WarpPolicy dp{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err};
+	ReplayPolicy dp(WarpPolicy{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err});
 	for (;;) {
 		const int pr = next_item(&counters[6], lane);
 		if (pr >= n_pairs) break;
 		const int r1 = 2 * pr, r2 = r1 + 1;
 		Reg *g1 = p.regs + (occ_off[r1] + (size_t)RESCUE_ROOM * r1), *g2 = p.regs + (occ_off[r2] + (size_t)RESCUE_ROOM * r2);
 		int n1 = p.n_regs[r1], n2 = p.n_regs[r2];
+		dp.cache = tasks ? tasks + task_beg[pr] : nullptr;
+		dp.n_cache = tasks ? task_n[pr] : 0;
 		mate_sw_pair(ix, dp, (int)(off[r1 + 1] - off[r1]), seq + off[r1], (int)(off[r2 + 1] - off[r2]), seq + off[r2], g1, &n1, g2, &n2);
 		p.n_regs[r1] = n1; p.n_regs[r2] = n2;
 		__syncwarp();
@@ -272,7 +393,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	TRY(c->b[22].ensure(16));
 	int *d_err = c->b[22].as<int>();
 	CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
-	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, st));
+	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 128, st));
 	CUDA_TRY(cudaMemsetAsync(d_occ_cnt, 0, (size_t)(R + 1) * 4, st));
 	int launches = 0;
 	if (!c->stage_ev[0]) for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&c->stage_ev[i]));
@@ -326,8 +447,20 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	launches += 2;
 	CUDA_TRY(cudaEventRecord(c->stage_ev[4], st));
 	if (stage >= 2) {
+		RescueTask *tasks = nullptr;
+		int32_t *task_beg = nullptr, *task_n = nullptr;
+		if (c->rescue_plan) {
+			const int task_cap = 4 * n_pairs + 4096;
+			TRY(c->b[25].ensure((size_t)task_cap * sizeof(RescueTask)));
+			TRY(c->b[26].ensure((size_t)n_pairs * 4 * 2));
+			tasks = c->b[25].as<RescueTask>(); task_beg = c->b[26].as<int32_t>(); task_n = task_beg + n_pairs;
+			k_rescue_plan<<<(n_pairs + 127) / 128, 128, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p,
+			                                                    tasks, task_cap, task_beg, task_n, c->d_counters);
+			k_rescue_sw<<<grid, PL_WARPS * 32, 0, st>>>(ix, tasks, task_cap, d_err, c->d_counters);
+			launches += 2;
+		}
 		k_rescue<<<grid, PL_WARPS * 32, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
-		                                          c->b[17].as<uint32_t>(), d_err, c->d_counters);
+		                                          c->b[17].as<uint32_t>(), d_err, c->d_counters, tasks, task_beg, task_n);
 		++launches;
 	}
 	CUDA_TRY(cudaEventRecord(c->stage_ev[5], st));
@@ -375,12 +508,12 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		k_export_regs<<<(R + 127) / 128, 128, 0, st>>>(R, d_occ_off, d_aln_off, p, c->b[24].as<int64_t>());
 		CUDA_TRY(cudaMemcpyAsync(c->h[3].p, c->b[24].p, (size_t)A * 18 * 8, cudaMemcpyDeviceToHost, st));
 	}
-	TRY(c->h[0].ensure((size_t)R * 4 + 128));
+	TRY(c->h[0].ensure((size_t)R * 4 + 256));
 	CUDA_TRY(cudaMemcpyAsync(c->h[0].p, p.n_regs, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
 	int *h_err = (int *)((char *)c->h[0].p + (size_t)R * 4);
 	unsigned long long *cnt = (unsigned long long *)((char *)c->h[0].p + (((size_t)R * 4 + 16 + 7) & ~(size_t)7));
 	CUDA_TRY(cudaMemcpyAsync(h_err, d_err, 16, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 64, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 128, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaGetLastError());
 	res->n_cands = A; res->n_cigar_ops = NC; res->n_regs = (const int32_t *)c->h[0].p;
@@ -391,6 +524,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	c->last_ms = ms; c->last_launches = launches;
 	if (stats) {
 		stats->extend_cells = (int64_t)cnt[0]; stats->occ_touches = (int64_t)cnt[2]; stats->global_cells = (int64_t)cnt[3];
+		stats->rescue_planned_cells = (int64_t)cnt[10]; stats->rescue_unplanned = (int64_t)cnt[11];
 		stats->local_cells = (int64_t)cnt[4]; stats->n_occ = T; stats->n_regs = A; stats->kernel_ms = ms; stats->launches = launches;
 		float t;
 		cudaEventElapsedTime(&t, c->stage_ev[0], c->stage_ev[1]); stats->ms_seed = t;

@@ -70,11 +70,12 @@ struct emab_ctx {
 	int last_launches = 0;
 	DevBuf b[28];            // device scratch slots, meaning assigned by each entry point
 	HostBuf h[8];            // pinned host result buffers, owned by the ctx and valid until its next call
-	unsigned long long *d_counters = nullptr;  // 8 x u64 instrumentation counters
+	unsigned long long *d_counters = nullptr;  // 16 x u64 instrumentation / work counters
 	int n_sm = 148;
 	int pl_bps = 4;          // blocks per SM of the persistent warp-per-read kernels (EMAB_PL_BPS)
 	// resident SW microbench inputs
 	int res_n = 0, res_qcap = 0;
 	int sw_mode = 0;         // see emab_set_sw_mode (include/ema_b200.h)
+	bool rescue_plan = true; // mate-rescue alignments planned and run as one balanced batch (pipeline.cu, k_rescue_plan)
 	bool consts_ready = false;
 };

@@ -141,6 +141,8 @@ typedef struct {
 	int64_t h2d_bytes, d2h_bytes;                     /* bytes copied inside the call */
 	int32_t launches;
 	int32_t pad;
+	int64_t rescue_planned_cells;                     /* local-SW cells computed ahead of the rescue replay (>= local_cells' share of them) */
+	int64_t rescue_unplanned;                         /* mem_matesw alignments the plan did not foresee (computed inline by the replay) */
 } emab_stats_t;
 
 int emab_set_error_rate(emab_ctx_t *ctx, double eps);  /* platform error_rate (src/techs.c:71-127); default 0.001 */

@@ -29,7 +29,7 @@ def test_wire_struct_sizes():
     from ema_b200 import _lib
     assert _lib.CAND_DTYPE.itemsize == 56
     assert C.sizeof(_lib.RunStats) == 16 * 8 + 11 * 8 + 8
-    assert C.sizeof(_lib.Stats) == 6 * 8 + 6 * 8 + 2 * 8 + 8
+    assert C.sizeof(_lib.Stats) == 6 * 8 + 6 * 8 + 2 * 8 + 8 + 2 * 8
 
 
 def test_no_cpu_fallback():

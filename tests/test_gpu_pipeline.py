@@ -139,3 +139,45 @@ def test_edge_cases(emab):
     assert res["n_regs"][1] == 0 and res["n_regs"][2] == 0 and res["n_regs"][0] >= 1
     with pytest.raises(emab.EmabError):
         emab.align_pairs(ctx, [np.zeros(400, np.uint8), r])
+
+
+def test_wide_dense_sa_branch(emab, monkeypatch):
+    """hg38-sized indexes (2*l_pac >= 2^32, BASELINE configs[2]) keep the dense SA as u64; EMAB_SA64=1 forces
+    that table on the small golden index: every SA slot and the golden candidates must be unchanged."""
+    monkeypatch.setenv("EMAB_SA64", "1")
+    ix = emab.Index(os.path.join(G, "tiny_rep", "ref.fa"))
+    monkeypatch.delenv("EMAB_SA64")
+    ctx = emab.Context(ix)
+    allk = np.arange(0, ix.seq_len + 1, dtype=np.int64)
+    assert np.array_equal(emab.sa_batch(ctx, allk, mode=0), emab.sa_batch(ctx, allk, mode=1)), "every SA slot (u64 table)"
+    want = helpers.cands_from_golden(np.load(os.path.join(G, "cand_golden.npz")))
+    lines = helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x"))
+    got, _ = pipeline_candidates(emab, ctx, lines)
+    assert got == want
+
+
+def test_rescue_plan_is_transparent(emab, monkeypatch):
+    """mate rescue as plan + batched ksw_align2 + replay (pipeline.cu) must return what the single sequential
+    warp-per-pair kernel returns — candidates, regions per read and the DP cells the reference's loop visits —
+    on the golden bucket and on the repeat/indel variant of BASELINE configs[0] (where rescues chain)."""
+    from tools import synth
+    cases = [(os.path.join(G, "tiny_rep", "ref.fa"), helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x")))]
+    if os.path.exists(helpers.ref_bin("bwa")):
+        p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+        cases.append((p["fasta"], helpers.read_bucket(p["bucket"])))
+    for pre, lines in cases:
+        ix = emab.Index(pre)
+        monkeypatch.setenv("EMAB_RESCUE_PLAN", "0")
+        ctx0 = emab.Context(ix)
+        monkeypatch.delenv("EMAB_RESCUE_PLAN")
+        ctx1 = emab.Context(ix)
+        a, ra = pipeline_candidates(emab, ctx0, lines)
+        b, rb = pipeline_candidates(emab, ctx1, lines)
+        assert a == b
+        assert np.array_equal(ra["n_regs"], rb["n_regs"])
+        sa, sb = ra["stats"], rb["stats"]
+        assert sa.local_cells == sb.local_cells and sa.local_cells > 0
+        assert sa.rescue_planned_cells == 0 and sb.rescue_planned_cells > 0
+        n_sw = max(1, sb.local_cells // 60000)  # ~ number of ksw_align2 calls
+        assert sb.rescue_unplanned * 10 <= n_sw, f"the plan should foresee nearly every alignment ({sb.rescue_unplanned} of ~{n_sw} were not)"
+        print(f"rescue plan: {sb.rescue_planned_cells} cells planned, {sb.local_cells} consumed, {sb.rescue_unplanned} alignments unplanned")
