@@ -245,6 +245,21 @@ EMAB_HD void chain2aln(const DevIndex &ix, DP &dp, int l_query, const uint8_t *q
 	}
 }
 
+// n bases aligned without gaps: substitution score and number of mismatches (the gap-free path of
+// bwa_gen_cigar2, bwa/bwa.c:168-176, and its NM count over M runs, :203-210).  The scalar form; a DP policy's
+// ungapped() may spread the bases over the lanes of a warp.
+EMAB_HD int ungapped_scalar(const DevIndex &ix, const uint8_t *query, int q0, int qstep, int n, int64_t t0, int tstep, int *score)
+{
+	int sc = 0, mm = 0;
+	for (int i = 0; i < n; ++i) {
+		const int qc = query[q0 + i * qstep], tc = ref_base(ix, t0 + (int64_t)i * tstep);
+		sc += sc_mat(tc, qc);
+		mm += qc != tc;
+	}
+	*score = sc;
+	return mm;
+}
+
 // ---------------------------------------------------------------------------------------------
 // bwa_gen_cigar2's global alignment set-up (bwa/bwa.c:148-234): orientation, band, fast path.
 // Returns the score; if cigar != nullptr also the CIGAR (BAM encoding) and NM.
@@ -268,13 +283,7 @@ EMAB_HD int gen_cigar(const DevIndex &ix, DP &dp, int w_, int l_query, const uin
 	*ok = true;
 	int score;
 	if (l_query == rlen && w_ == 0) {  // no gap: no DP
-		score = 0;
-		int mm = 0;
-		for (int i = 0; i < l_query; ++i) {
-			int qc = query[q0 + i * qstep], tc = ref_base(ix, t0 + (int64_t)i * tstep);
-			score += sc_mat(tc, qc);
-			mm += qc != tc;
-		}
+		const int mm = dp.ungapped(query, q0, qstep, l_query, t0, tstep, &score);
 		if (cigar) { cigar[0] = (uint32_t)l_query << 4; *n_cigar = 1; if (NM) *NM = mm; }
 		return score;
 	}
@@ -295,8 +304,8 @@ EMAB_HD int gen_cigar(const DevIndex &ix, DP &dp, int w_, int l_query, const uin
 		for (int k = 0; k < nc; ++k) {
 			int op = cigar[k] & 0xf, len = (int)(cigar[k] >> 4);
 			if (op == 0) {
-				for (int i = 0; i < len; ++i)
-					n_mm += query[q0 + (x + i) * qstep] != ref_base(ix, t0 + (int64_t)(y + i) * tstep);
+				int sc_unused;
+				n_mm += dp.ungapped(query, q0 + x * qstep, qstep, len, t0 + (int64_t)y * tstep, tstep, &sc_unused);
 				x += len; y += len;
 			} else if (op == 2) {
 				if (k > 0 && k < *n_cigar - 1) n_gap += len;

@@ -32,6 +32,10 @@ struct ScalarPatchDP {
 		*err = 4;
 		return LocResult{};
 	}
+	EMAB_HD int ungapped(const uint8_t *query, int q0, int qstep, int n, int64_t t0, int tstep, int *score)
+	{
+		return ungapped_scalar(ix, query, q0, qstep, n, t0, tstep, score);
+	}
 	EMAB_HD int global(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, uint32_t *cigar, int *n_cigar)
 	{
 		const int NEG = -0x40000000;

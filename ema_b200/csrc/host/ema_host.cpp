@@ -55,6 +55,34 @@ static double now_ms()
 	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// EMAB_HOST_PROFILE=1: CPU time (per-thread clocks, so waiting on a gate or a full machine does not count) of
+// the host stages, summed over threads and buckets and printed when the session closes.
+enum { HP_SPLIT, HP_SORT, HP_TOKENS, HP_ENCODE, HP_RECS, HP_CLOUDS, HP_FLATTEN, HP_CHOOSE, HP_PRINT, HP_COPY, HP_N };
+static const char *const g_hp_name[HP_N] = {"parse:split", "parse:sort", "parse:tokens", "encode", "records", "clouds", "flatten", "choose", "print", "copy"};
+static std::atomic<long long> g_hp_ns[HP_N];
+static const bool g_hp_on = getenv("EMAB_HOST_PROFILE") && atoi(getenv("EMAB_HOST_PROFILE")) != 0;
+static inline long long thread_cpu_ns()
+{
+	timespec ts;
+	clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+	return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+struct HostProf {
+	int k; long long t0;
+	explicit HostProf(int k_) : k(k_), t0(g_hp_on ? thread_cpu_ns() : 0) {}
+	void next(int k2) { if (g_hp_on) { const long long t = thread_cpu_ns(); g_hp_ns[k] += t - t0; t0 = t; } k = k2; }
+	~HostProf() { if (g_hp_on) g_hp_ns[k] += thread_cpu_ns() - t0; }
+};
+static void host_profile_report()
+{
+	if (!g_hp_on) return;
+	long long tot = 0;
+	for (int k = 0; k < HP_N; ++k) tot += g_hp_ns[k];
+	fprintf(stderr, "[emab host profile] thread-CPU ms by stage (total %.1f):", tot * 1e-6);
+	for (int k = 0; k < HP_N; ++k) fprintf(stderr, " %s %.1f", g_hp_name[k], g_hp_ns[k] * 1e-6);
+	fprintf(stderr, "\n");
+}
+
 // ---------------------------------------------------------------------------------------------
 // barcodes (src/util.c:41-95)
 // ---------------------------------------------------------------------------------------------
@@ -179,6 +207,7 @@ int session_open(const char *ref_path, const char *platform, int device, Session
 void session_close(Session *s)
 {
 	if (!s) return;
+	host_profile_report();
 	for (Worker &w : s->workers) emab_ctx_free(w.ctx);
 	s->workers.clear();
 	emab_index_free(s->ix);
@@ -701,13 +730,17 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	}
 	if (wk.seq.ensure((size_t)off[2 * np] + 1)) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
 	uint8_t *seq = (uint8_t *)wk.seq.p;
-	#pragma omp parallel for num_threads(nthr) schedule(static)
+	#pragma omp parallel num_threads(nthr)
+	{
+	HostProf hp(HP_ENCODE);
+	#pragma omp for schedule(static)
 	for (size_t i = 0; i < np; ++i)
 		for (int m = 0; m < 2; ++m) {
 			uint8_t *d = seq + off[2 * i + m];
 			const std::string_view r = pairs[i].read[m];
 			for (size_t k = 0; k < r.size(); ++k) d[k] = tab[(uint8_t)r[k]];
 		}
+	}
 	emab_stats_t ds;
 	emab_pairs_result_t res;
 	const double t1 = now_ms();
@@ -743,6 +776,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	// ---- records + clouds per barcode
 	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 1)
 	for (int b = 0; b < nb; ++b) {
+		HostProf hp(HP_RECS);
 		Barcode &B = bcs[b];
 		for (int pi = 0; pi < B.n_pairs; ++pi) {  // append_alignments' bookkeeping (src/align.c:1010-1060)
 			const size_t gp = (size_t)B.first_pair + pi;
@@ -763,6 +797,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 				if (added == 1) B.recs.back().unique = 1;
 			}
 		}
+		hp.next(HP_CLOUDS);
 		B.build_clouds(s, pairs);
 	}
 	if (s->apply_opt)
@@ -797,6 +832,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	std::vector<uint8_t> cand_flags(K);
 	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 1)
 	for (int b = 0; b < nb; ++b) {
+		HostProf hp(HP_FLATTEN);
 		const Barcode &B = bcs[b];
 		const int ne = (int)B.entries.size(), e0 = bc_entry_off[b], c0 = bc_cloud_off[b];
 		// entries in the reference's walk order: newest first (sd->head, src/samdict.c:131-132)
@@ -869,6 +905,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	for (int b = 0; b < nb; ++b) cloud_base[b + 1] = cloud_base[b] + (int)bcs[b].clouds.size();
 	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 1)
 	for (int b = 0; b < nb; ++b) {
+		HostProf hp(HP_CHOOSE);
 		Barcode &B = bcs[b];
 		const int ne = (int)B.entries.size(), e0 = bc_entry_off[b];
 		for (int ei = 0; ei < ne; ++ei) {
@@ -879,6 +916,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 		B.choose(s);
 		B.bc_str.clear();
 		decode_bc(s, B.bc, &B.bc_str);
+		hp.next(HP_PRINT);
 		B.sam.reserve(B.final_.size() * 520);
 		for (int ri : B.final_) {
 			Rec &best = B.recs[ri];
@@ -906,7 +944,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	char *buf = (char *)malloc(total + 1);
 	if (!buf) { s->err = "out of memory"; return EMAB_ERR_NOMEM; }
 	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 4)
-	for (int b = 0; b < nb; ++b) memcpy(buf + soff[b], bcs[b].sam.data(), bcs[b].sam.size());
+	for (int b = 0; b < nb; ++b) { HostProf hp(HP_COPY); memcpy(buf + soff[b], bcs[b].sam.data(), bcs[b].sam.size()); }
 	buf[total] = 0;
 	*out_buf = buf; *out_len = total;
 	const double t6 = now_ms();
@@ -947,6 +985,7 @@ static int parse_bucket(Session *s, int nthr, const char *data, size_t len, std:
 		std::vector<std::vector<size_t>> nl(nt);
 		#pragma omp parallel num_threads(nt)
 		{
+			HostProf hp(HP_SPLIT);
 			const int t = omp_get_thread_num(), T = omp_get_num_threads();
 			const size_t lo = len * (size_t)t / (size_t)T, hi = len * (size_t)(t + 1) / (size_t)T;
 			std::vector<size_t> &v = nl[t];
@@ -958,6 +997,7 @@ static int parse_bucket(Session *s, int nthr, const char *data, size_t len, std:
 				p = q + 1;
 			}
 		}
+		HostProf hp(HP_SPLIT);
 		size_t total = 0;
 		for (auto &v : nl) total += v.size();
 		lines.reserve(total + 1);
@@ -984,7 +1024,10 @@ static int parse_bucket(Session *s, int nthr, const char *data, size_t len, std:
 	} else {
 		struct Key { uint64_t hi, lo; uint32_t idx; };
 		std::vector<Key> keys(n);
-		#pragma omp parallel for num_threads(nthr) schedule(static)
+		#pragma omp parallel num_threads(nthr)
+		{
+		HostProf hp(HP_SORT);
+		#pragma omp for schedule(static)
 		for (size_t i = 0; i < n; ++i) {
 			uint64_t hi = 0, lo = 0;
 			const unsigned char *c = (const unsigned char *)lines[i].data();
@@ -994,29 +1037,36 @@ static int parse_bucket(Session *s, int nthr, const char *data, size_t len, std:
 			}
 			keys[i] = Key{hi, lo, (uint32_t)i};
 		}
+		}
 		auto less = [](const Key &a, const Key &b) { return a.hi != b.hi ? a.hi < b.hi : (a.lo != b.lo ? a.lo < b.lo : a.idx < b.idx); };
 		// sort slices in parallel, then merge pairwise (idx in the key makes the order total, hence stable)
 		const int nt = std::max(1, std::min(nthr, 16));
 		std::vector<size_t> cut(nt + 1);
 		for (int t = 0; t <= nt; ++t) cut[t] = n * (size_t)t / (size_t)nt;
 		#pragma omp parallel for num_threads(nt) schedule(static, 1)
-		for (int t = 0; t < nt; ++t) std::sort(keys.begin() + cut[t], keys.begin() + cut[t + 1], less);
+		for (int t = 0; t < nt; ++t) { HostProf hp(HP_SORT); std::sort(keys.begin() + cut[t], keys.begin() + cut[t + 1], less); }
 		for (int step = 1; step < nt; step <<= 1) {
 			#pragma omp parallel for num_threads(nt) schedule(static, 1)
 			for (int t = 0; t < nt; t += 2 * step) {
 				const int mid = std::min(t + step, nt), hi = std::min(t + 2 * step, nt);
+				HostProf hp(HP_SORT);
 				if (mid < hi) std::inplace_merge(keys.begin() + cut[t], keys.begin() + cut[mid], keys.begin() + cut[hi], less);
 			}
 		}
 		std::vector<std::string_view> sorted(n);
-		#pragma omp parallel for num_threads(nthr) schedule(static)
-		for (size_t i = 0; i < n; ++i) sorted[i] = lines[keys[i].idx];
+		{
+			HostProf hp(HP_SORT);
+			for (size_t i = 0; i < n; ++i) sorted[i] = lines[keys[i].idx];
+		}
 		lines.swap(sorted);
 	}
 	pairs.resize(lines.size());
 	ws_table();
 	int bad = 0;
-	#pragma omp parallel for num_threads(nthr) schedule(static) reduction(max : bad)
+	#pragma omp parallel num_threads(nthr) reduction(max : bad)
+	{
+	HostProf hp(HP_TOKENS);
+	#pragma omp for schedule(static)
 	for (size_t i = 0; i < lines.size(); ++i) {
 		const char *p = lines[i].data(), *end = p + lines[i].size();
 		std::string_view bc = token(p, end);
@@ -1027,6 +1077,7 @@ static int parse_bucket(Session *s, int nthr, const char *data, size_t len, std:
 		P.id1 = P.id2 = id;
 		P.read[0] = token(p, end); P.qual[0] = token(p, end); P.read[1] = token(p, end); P.qual[1] = token(p, end);
 		if (P.read[0].size() > 200 || P.read[1].size() > 200) bad = std::max(bad, 2);
+	}
 	}
 	if (bad == 1) { *err = "error: malformed barcode in the input bucket"; return EMAB_ERR_ARG; }
 	if (bad == 2) { *err = "error: read longer than MAX_READ_LEN (200)"; return EMAB_ERR_ARG; }

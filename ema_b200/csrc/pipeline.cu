@@ -82,6 +82,18 @@ struct WarpPolicy {
 		__syncwarp();
 		return score;
 	}
+	// gap-free stretch: the bases are spread over the lanes, two REDUX put the sums back on every lane
+	__device__ int ungapped(const uint8_t *query, int q0, int qstep, int n, int64_t t0, int tstep, int *score)
+	{
+		int sc = 0, mm = 0;
+		for (int i = threadIdx.x & 31; i < n; i += 32) {
+			const int qc = query[q0 + i * qstep], tc = ref_base(ix, t0 + (int64_t)i * tstep);
+			sc += sc_mat(tc, qc);
+			mm += qc != tc;
+		}
+		*score = __reduce_add_sync(FULL_MASK, sc);
+		return __reduce_add_sync(FULL_MASK, mm);
+	}
 	// query = reverse complement of ms (bwa/bwamem_pair.c:150-153), target = ref[rb, rb+tlen)
 	__device__ LocResult local(const uint8_t *ms, int l_ms, int64_t rb, int tlen)
 	{

@@ -56,6 +56,10 @@ struct HostDP {  // scalar stand-in for WarpPolicy (pipeline.cu)
 		++hs_cnt[1]; hs_cnt[4] += cells;
 		return sc;
 	}
+	int ungapped(const uint8_t *query, int q0, int qstep, int n, int64_t t0, int tstep, int *score)
+	{
+		return ungapped_scalar(ix, query, q0, qstep, n, t0, tstep, score);
+	}
 	LocResult local(const uint8_t *ms, int l_ms, int64_t rb, int tlen)
 	{
 		std::vector<uint8_t> q(l_ms + 1), t(tlen + 1);
