@@ -277,6 +277,12 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None   # dram bytes per k_seed launch from the committed `ncu --set full` capture of this workload
+        try:
+            if args.workload == "c2":
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_seed"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         seed_bytes = agg["occ_touches"] * 64.0 / K
         seed_ms = agg["ms_seed"] / K
         achieved = seed_bytes / (seed_ms * 1e-3) / 1e9 if seed_ms > 0 else 0.0
@@ -291,7 +297,7 @@ def main():
             "gpu_launches": launches + launches_e2e,
             "clocks": clocks,
             "roofline": {"kernel": "k_seed (SMEM seeding, mem_collect_intv)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": seed_bytes, "ms_per_launch": seed_ms},
             "device_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain", "ms_align1", "ms_rescue", "ms_finalize", "em_kernel_ms")},

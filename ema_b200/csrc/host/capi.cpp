@@ -17,7 +17,7 @@ static int fail(int rc, const std::string &msg)
 
 static int give(const std::string &text, char **out, uint64_t *len)
 {
-	char *p = (char *)malloc(text.size() + 1);
+	char *p = emab::text_alloc(text.size() + 1);
 	if (!p) return fail(EMAB_ERR_NOMEM, "out of memory");
 	memcpy(p, text.data(), text.size());
 	p[text.size()] = 0;
@@ -122,6 +122,6 @@ int emab_session_dump_posteriors(emab_session_t *h, const char *path)
 }
 
 emab_ctx_t *emab_session_ctx(emab_session_t *h) { return h ? h->s->workers[0].ctx : nullptr; }
-void emab_free(void *p) { free(p); }
+void emab_free(void *p) { emab::text_free(p); }
 
 }  // extern "C"

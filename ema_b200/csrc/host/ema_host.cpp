@@ -25,11 +25,71 @@
 #include <cstring>
 #include <ctime>
 #include <atomic>
+#include <emmintrin.h>
+#include <malloc.h>
+#include <mutex>
 #include <string_view>
 #include <thread>
 #include <unordered_map>
 
 namespace emab {
+
+// ---------------------------------------------------------------------------------------------
+// output blocks
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct BlockHdr { size_t cap; uint64_t magic; };
+constexpr uint64_t BLOCK_MAGIC = 0x656d6162424c4b31ull;
+constexpr size_t POOL_MIN = 1u << 20;
+std::mutex g_pool_mu;
+std::vector<BlockHdr *> g_pool;
+}
+
+char *text_alloc(size_t n)
+{
+	BlockHdr *h = nullptr;
+	if (n >= POOL_MIN) {
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		size_t best = g_pool.size();
+		for (size_t i = 0; i < g_pool.size(); ++i)
+			if (g_pool[i]->cap >= n && g_pool[i]->cap <= 2 * n && (best == g_pool.size() || g_pool[i]->cap < g_pool[best]->cap)) best = i;
+		if (best < g_pool.size()) { h = g_pool[best]; g_pool[best] = g_pool.back(); g_pool.pop_back(); }
+	}
+	if (!h) {
+		const size_t cap = n >= POOL_MIN ? n + n / 8 : n;
+		h = (BlockHdr *)malloc(sizeof(BlockHdr) + cap + 1);
+		if (!h) return nullptr;
+		h->cap = cap; h->magic = BLOCK_MAGIC;
+	}
+	return (char *)(h + 1);
+}
+
+void text_free(void *p)
+{
+	if (!p) return;
+	BlockHdr *h = (BlockHdr *)p - 1;
+	if (h->magic != BLOCK_MAGIC) { fprintf(stderr, "emab_free: not a block returned by this library\n"); return; }
+	if (h->cap >= POOL_MIN) {
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		if (g_pool.size() < 32) { g_pool.push_back(h); return; }
+	}
+	h->magic = 0;
+	free(h);
+}
+
+// glibc serves blocks above its mmap threshold (128 KB, growing to at most 32 MB) straight from mmap and gives them
+// back on free: every per-barcode record vector and text buffer of every bucket would page-fault its way in again.
+// Keep them in the heap arenas instead.
+static void tune_malloc()
+{
+	static std::once_flag once;
+	std::call_once(once, [] {
+		if (const char *e = getenv("EMAB_MALLOC_TUNE")) if (atoi(e) == 0) return;
+		mallopt(M_MMAP_THRESHOLD, 32 << 20);
+		mallopt(M_TRIM_THRESHOLD, 1 << 30);
+		mallopt(M_TOP_PAD, 64 << 20);
+	});
+}
 
 // ---------------------------------------------------------------------------------------------
 // platforms (src/techs.c:71-127)
@@ -163,6 +223,7 @@ int session_set_workers(Session *s, int n_workers)
 int session_open(const char *ref_path, const char *platform, int device, Session **out, std::string *err)
 {
 	*out = nullptr;
+	tune_malloc();
 	const Platform *tech = platform_by_name(platform);
 	if (!tech) { *err = std::string("error: invalid platform name: '") + platform + "'"; return EMAB_ERR_ARG; }
 	Session *s = new Session();
@@ -274,6 +335,27 @@ static inline bool is_pair(const Rec &a, const Rec &b)
 	return -35 <= d && d <= 750;
 }
 
+struct TextBuf {  // grow-only text buffer written through a raw cursor (see print_sam_record)
+	char *p = nullptr;
+	size_t n = 0, cap = 0;
+	TextBuf() = default;
+	TextBuf(const TextBuf &) = delete;
+	TextBuf &operator=(const TextBuf &) = delete;
+	TextBuf(TextBuf &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+	TextBuf &operator=(TextBuf &&o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
+	~TextBuf() { free(p); }
+	void reserve(size_t c)
+	{
+		if (c <= cap) return;
+		char *q = (char *)realloc(p, c);
+		if (!q) throw std::bad_alloc();
+		p = q; cap = c;
+	}
+	char *room(size_t k) { if (n + k > cap) reserve(std::max(2 * cap, n + k + 4096)); return p + n; }
+	size_t size() const { return n; }
+	const char *data() const { return p; }
+};
+
 struct Barcode {
 	uint64_t bc = 0;
 	int first_pair = 0, n_pairs = 0;       // range in the bucket's (barcode-sorted) pair list
@@ -283,7 +365,7 @@ struct Barcode {
 	std::unordered_map<std::pair<std::string_view, int>, int, KeyHash> dict;
 	std::vector<int> final_;               // records_final
 	std::vector<std::vector<int>> opt_jobs; // -d: name-sorted records of each bad cloud, in cloud order (see process_pairs)
-	std::string sam;
+	TextBuf sam;
 	std::string bc_str;                    // decode_bc(bc), printed in every BX tag of this barcode
 
 	int find(const Rec &k) const
@@ -587,39 +669,52 @@ static inline int get_rlen(const emab_cand_t *a, const uint32_t *cig)
 	return l;
 }
 
-static inline void put_int(std::string *o, long long v)
+// SAM text goes through a raw cursor into a buffer whose room was checked once per record: the formatter is the
+// largest single consumer of host CPU on this path, and a bounds check per character was most of it.
+static inline char *put_int(char *w, long long v)
 {
 	char buf[24];
 	int n = 0;
-	bool neg = v < 0;
+	const bool neg = v < 0;
 	unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
 	do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
-	if (neg) o->push_back('-');
-	while (n) o->push_back(buf[--n]);
+	if (neg) *w++ = '-';
+	while (n) *w++ = buf[--n];
+	return w;
 }
+static inline char *put_sv(char *w, std::string_view v) { memcpy(w, v.data(), v.size()); return w + v.size(); }
+template <size_t N> static inline char *put_lit(char *w, const char (&lit)[N]) { memcpy(w, lit, N - 1); return w + (N - 1); }
 
-static inline void put_cigar(std::string *o, const emab_cand_t *a, const uint32_t *cig)
+static inline char *put_cigar(char *w, const emab_cand_t *a, const uint32_t *cig)
 {
-	for (int i = 0; i < a->n_cigar; ++i) { put_int(o, cig[i] >> 4); o->push_back("MIDSS"[cig[i] & 0xf]); }
+	for (int i = 0; i < a->n_cigar; ++i) { w = put_int(w, cig[i] >> 4); *w++ = "MIDSS"[cig[i] & 0xf]; }
+	return w;
 }
 
-static inline char rc(char c)
+static const char *rc_table()
 {
-	switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; }
+	static char tab[256];
+	static bool init = false;
+	if (!init) {
+		memset(tab, 'N', sizeof tab);
+		tab[(unsigned char)'A'] = 'T'; tab[(unsigned char)'C'] = 'G'; tab[(unsigned char)'G'] = 'C'; tab[(unsigned char)'T'] = 'A';
+		init = true;
+	}
+	return tab;
 }
 
-static void print_sam_record(const Session *s, const Barcode &b, const std::vector<Pair> &pairs, int ri, int mi, int cloud_base, std::string *o)
+static void print_sam_record(const Session *s, const Barcode &b, const std::vector<Pair> &pairs, int ri, int mi, int cloud_base, TextBuf *o)
 {
 	const Rec *rec = ri >= 0 ? &b.recs[ri] : nullptr, *mate = mi >= 0 ? &b.recs[mi] : nullptr;
 	int flag = 1;
 	std::string_view ident, read, qual;
-	const char *chrom = "*";
+	std::string_view chrom("*");
 	uint32_t pos = 0;
 	int mapq = 0;
 	if (rec) {
 		const Pair &p = pairs[b.first_pair + rec->pair];
 		ident = rec->ident;
-		chrom = s->fai_names[rec->chrom].c_str();
+		chrom = s->fai_names[rec->chrom];
 		pos = rec->pos;
 		read = p.read[rec->mate]; qual = p.qual[rec->mate];
 		const double gamma = rec->gamma;
@@ -642,56 +737,60 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 		if (rec && is_pair(*rec, *mate)) flag |= 2;
 		if (mate->rev) flag |= 32;
 	} else flag |= 8;
-	o->append(ident); o->push_back('\t'); put_int(o, flag); o->push_back('\t'); o->append(chrom); o->push_back('\t');
-	put_int(o, pos); o->push_back('\t'); put_int(o, mapq); o->push_back('\t');
-	if (rec) put_cigar(o, rec->aln, rec->cig); else o->push_back('*');
+	const Rec *alt = rec && rec->alt >= 0 ? &b.recs[rec->alt] : nullptr;
+	const std::string &bc_str = b.bc_str;
+	// everything of variable length, plus room for the fixed tags, every integer and two full CIGARs
+	const size_t bound = ident.size() + read.size() + qual.size() + chrom.size() + bc_str.size() + s->bx_index.size() + s->rg_id.size() +
+	                     (mate ? s->fai_names[mate->chrom].size() : 0) + (alt ? s->fai_names[alt->chrom].size() : 0) + 2 * 64 * 12 + 512;  // 64 = the most CIGAR ops a candidate carries (include/align.h:41)
+	char *w = o->room(bound);
+	w = put_sv(w, ident); *w++ = '\t'; w = put_int(w, flag); *w++ = '\t'; w = put_sv(w, chrom); *w++ = '\t';
+	w = put_int(w, pos); *w++ = '\t'; w = put_int(w, mapq); *w++ = '\t';
+	if (rec) w = put_cigar(w, rec->aln, rec->cig); else *w++ = '*';
 	if (mate) {
 		const bool same = rec && mate->chrom == rec->chrom;
-		o->push_back('\t');
-		if (same) o->push_back('='); else o->append(s->fai_names[mate->chrom]);
-		o->push_back('\t'); put_int(o, (int)mate->pos);
+		*w++ = '\t';
+		if (same) *w++ = '='; else w = put_sv(w, s->fai_names[mate->chrom]);
+		*w++ = '\t'; w = put_int(w, (int)mate->pos);
 		if (same) {
 			const emab_cand_t *r = rec->aln, *m = mate->aln;
 			const int64_t p0 = r->pos + (r->is_rev ? get_rlen(r, rec->cig) - 1 : 0), p1 = m->pos + (m->is_rev ? get_rlen(m, mate->cig) - 1 : 0);
-			o->push_back('\t');
-			if (m->n_cigar == 0 || r->n_cigar == 0) o->push_back('0');
-			else put_int(o, -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
-		} else o->append("\t0");
-	} else o->append("\t*\t0\t0");
-	o->push_back('\t');
+			*w++ = '\t';
+			if (m->n_cigar == 0 || r->n_cigar == 0) *w++ = '0';
+			else w = put_int(w, -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
+		} else w = put_lit(w, "\t0");
+	} else w = put_lit(w, "\t*\t0\t0");
+	*w++ = '\t';
 	if (rec && rec->rev) {
-		const size_t at = o->size(), nr = read.size(), nq = qual.size();
-		o->resize(at + nr + 1 + nq);
-		char *d = &(*o)[at];
-		for (size_t i = 0; i < nr; ++i) d[i] = rc(read[nr - 1 - i]);
-		d[nr] = '\t';
-		for (size_t i = 0; i < nq; ++i) d[nr + 1 + i] = qual[nq - 1 - i];
-	} else { o->append(read); o->push_back('\t'); o->append(qual); }
-	const std::string &bc_str = b.bc_str;
+		const char *rct = rc_table();
+		const size_t nr = read.size(), nq = qual.size();
+		for (size_t i = 0; i < nr; ++i) w[i] = rct[(unsigned char)read[nr - 1 - i]];
+		w[nr] = '\t';
+		for (size_t i = 0; i < nq; ++i) w[nr + 1 + i] = qual[nq - 1 - i];
+		w += nr + 1 + nq;
+	} else { w = put_sv(w, read); *w++ = '\t'; w = put_sv(w, qual); }
 	if (rec) {
-		char buf[64];
-		o->append("\tNM:i:"); put_int(o, rec->aln->NM);
-		o->append("\tBX:Z:"); o->append(bc_str);
-		if (!s->is_haplotag) { o->push_back('-'); o->append(s->bx_index); }
-		if (rec->gamma == 1.0) o->append("\tXG:f:1");  // what %.5g prints for 1.0: the common case skips snprintf
-		else { snprintf(buf, sizeof buf, "\tXG:f:%.5g", rec->gamma); o->append(buf); }
-		o->append("\tMI:i:"); put_int(o, cloud_base + rec->cloud);
-		o->append("\tXF:i:"); put_int(o, b.clouds[rec->cloud].bad ? 1 : 0);
+		w = put_lit(w, "\tNM:i:"); w = put_int(w, rec->aln->NM);
+		w = put_lit(w, "\tBX:Z:"); w = put_sv(w, bc_str);
+		if (!s->is_haplotag) { *w++ = '-'; w = put_sv(w, s->bx_index); }
+		if (rec->gamma == 1.0) w = put_lit(w, "\tXG:f:1");  // what %.5g prints for 1.0: the common case skips snprintf
+		else w += snprintf(w, 64, "\tXG:f:%.5g", rec->gamma);
+		w = put_lit(w, "\tMI:i:"); w = put_int(w, cloud_base + rec->cloud);
+		w = put_lit(w, "\tXF:i:"); *w++ = b.clouds[rec->cloud].bad ? '1' : '0';
 	} else {
-		o->append("\tBX:Z:"); o->append(bc_str);
-		if (!s->is_haplotag) o->append("-1");
+		w = put_lit(w, "\tBX:Z:"); w = put_sv(w, bc_str);
+		if (!s->is_haplotag) w = put_lit(w, "-1");
 	}
 	if (s->has_rg) {
-		o->append("\tRG:Z:");
-		o->append(s->rg_id);
+		w = put_lit(w, "\tRG:Z:");
+		w = put_sv(w, s->rg_id);
 	}
-	if (rec && rec->alt >= 0) {
-		const Rec &a = b.recs[rec->alt];
-		o->append("\tXA:Z:"); o->append(s->fai_names[a.chrom]); o->push_back(','); o->push_back(a.rev ? '-' : '+'); put_int(o, (int)a.pos); o->push_back(',');
-		put_cigar(o, a.aln, a.cig);
-		o->push_back(','); put_int(o, a.aln->NM); o->push_back(';');
+	if (alt) {
+		w = put_lit(w, "\tXA:Z:"); w = put_sv(w, s->fai_names[alt->chrom]); *w++ = ','; *w++ = alt->rev ? '-' : '+'; w = put_int(w, (int)alt->pos); *w++ = ',';
+		w = put_cigar(w, alt->aln, alt->cig);
+		*w++ = ','; w = put_int(w, alt->aln->NM); *w++ = ';';
 	}
-	o->push_back('\n');
+	*w++ = '\n';
+	o->n = (size_t)(w - o->p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -718,7 +817,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	memset(&st, 0, sizeof st);
 	st.n_pairs = (int64_t)np;
 	*out_buf = nullptr; *out_len = 0;
-	if (np == 0) { s->take_cloud_base(ticket, 0); *out_buf = (char *)malloc(1); return EMAB_OK; }
+	if (np == 0) { s->take_cloud_base(ticket, 0); *out_buf = text_alloc(1); return EMAB_OK; }
 	// ---- encode and align the whole batch on the device
 	const uint8_t *tab = nt4_table();
 	if (wk.off.ensure((2 * np + 1) * 8)) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
@@ -917,7 +1016,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 		B.bc_str.clear();
 		decode_bc(s, B.bc, &B.bc_str);
 		hp.next(HP_PRINT);
-		B.sam.reserve(B.final_.size() * 520);
+		B.sam.reserve(B.final_.size() * 1100 + 4096);
 		for (int ri : B.final_) {
 			Rec &best = B.recs[ri];
 			if (best.visited) continue;
@@ -941,7 +1040,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	std::vector<size_t> soff(nb + 1, 0);
 	for (int b = 0; b < nb; ++b) soff[b + 1] = soff[b] + bcs[b].sam.size();
 	const size_t total = soff[nb];
-	char *buf = (char *)malloc(total + 1);
+	char *buf = text_alloc(total + 1);
 	if (!buf) { s->err = "out of memory"; return EMAB_ERR_NOMEM; }
 	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 4)
 	for (int b = 0; b < nb; ++b) { HostProf hp(HP_COPY); memcpy(buf + soff[b], bcs[b].sam.data(), bcs[b].sam.size()); }
@@ -968,7 +1067,17 @@ static inline std::string_view token(const char *&p, const char *end)
 {  // copy_until_space (src/util.c:11-20): up to the next whitespace, then skip one character
 	static const bool *ws = ws_table();
 	const char *b = p;
+	{  // 16 bytes at a time: c == ' ' or c in ['\t', '\r'] (SSE2 is part of x86-64)
+		const __m128i sp = _mm_set1_epi8(' '), nine = _mm_set1_epi8(9), four = _mm_set1_epi8(4);
+		while (p + 16 <= end) {
+			const __m128i v = _mm_loadu_si128((const __m128i *)p), d = _mm_sub_epi8(v, nine);
+			const int m = _mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(v, sp), _mm_cmpeq_epi8(_mm_min_epu8(d, four), d)));
+			if (m) { p += __builtin_ctz((unsigned)m); goto found; }
+			p += 16;
+		}
+	}
 	while (p < end && !ws[(uint8_t)*p]) ++p;
+found:;
 	std::string_view t(b, (size_t)(p - b));
 	if (p < end) ++p;
 	return t;
@@ -1167,7 +1276,7 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 	s->last.total_ms = now_ms() - t0;
 	if (first_err.load()) {
 		for (int w = 0; w < W; ++w) if (!errs[w].empty()) { s->err = errs[w]; break; }
-		for (int i = 0; i < n; ++i) { free(out[i]); out[i] = nullptr; }
+		for (int i = 0; i < n; ++i) { text_free(out[i]); out[i] = nullptr; }
 		return first_err.load();
 	}
 	return EMAB_OK;

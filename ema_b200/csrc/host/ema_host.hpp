@@ -130,6 +130,12 @@ struct GatePass {
 	GatePass &operator=(const GatePass &) = delete;
 };
 
+// Output text blocks (what emab_free releases).  Blocks of a megabyte or more are recycled through a small pool:
+// a bucket's SAM text is ~30 MB, and a fresh malloc of that size is an mmap whose 8 k first-touch page faults
+// (serialised on the process's mm lock) cost more CPU than formatting the text.
+char *text_alloc(size_t n);
+void text_free(void *p);
+
 int session_open(const char *ref_path, const char *platform, int device, Session **out, std::string *err);
 void session_close(Session *s);
 void sam_header(const Session *s, int argc, const char *const *argv, std::string *out);

@@ -5,7 +5,7 @@ OUT=gpurun_out; mkdir -p $OUT
 i=0
 for combo in "$@"; do
   i=$((i+1))
-  env $(echo $combo | tr '+' ' ') timeout 600 python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline 2>/dev/null > $OUT/knob_$i.json
+  env $(echo $combo | tr '+' ' ') timeout 600 python bench.py --steps ${STEPS:-10} --warmup 3 --workers ${WORKERS:-8} --threads ${THREADS:-0} --no-cpu-baseline 2> $OUT/knob_$i.err > $OUT/knob_$i.json; grep "host profile" $OUT/knob_$i.err
   python - <<PY
 import json
 d=json.load(open("$OUT/knob_$i.json"))
