@@ -191,6 +191,7 @@ extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
 	CUDA_TRY(cudaSetDevice(dev));
 	emab_ctx *c = new emab_ctx();
 	c->ix = ix;
+	c->device = dev;
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaEventCreate(&c->ev0));
 	CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -205,9 +206,17 @@ extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
 	return EMAB_OK;
 }
 
+extern "C" int emab_ctx_make_current(emab_ctx_t *c)
+{
+	if (!c) return EMAB_ERR_ARG;
+	CTX_ENTER(c);
+	return EMAB_OK;
+}
+
 extern "C" void emab_ctx_free(emab_ctx_t *c)
 {
 	if (!c) return;
+	cudaSetDevice(c->device);
 	for (auto &b : c->b) b.release();
 	for (auto &b : c->h) b.release();
 	cudaFree(c->d_counters);
@@ -392,6 +401,7 @@ static int upload_sw_inputs(emab_ctx *c, int n, const uint8_t *q, const int64_t 
 
 extern "C" int emab_set_sw_mode(emab_ctx_t *c, int mode)
 {
+	CTX_ENTER(c);
 	if (!c || mode < 0 || mode > 2) return EMAB_ERR_ARG;
 	c->sw_mode = mode;
 	return EMAB_OK;
@@ -438,6 +448,7 @@ static int launch_extend_lanes(emab_ctx *c, int n, int qcap, int w, int end_bonu
 extern "C" int emab_extend_batch(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
                                  const int32_t *h0, int w, int end_bonus, int zdrop, int32_t *out, int64_t *cells)
 {
+	CTX_ENTER(c);
 	if (!c || n < 0) return EMAB_ERR_ARG;
 	if (n == 0) { if (cells) *cells = 0; return EMAB_OK; }
 	TRY(check_lengths(n, qoff, toff, 0));
@@ -467,6 +478,7 @@ extern "C" int emab_extend_batch(emab_ctx_t *c, int n, const uint8_t *q, const i
 
 extern "C" int emab_extend_resident_load(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff, const int32_t *h0)
 {
+	CTX_ENTER(c);
 	if (!c || n <= 0) return EMAB_ERR_ARG;
 	TRY(check_lengths(n, qoff, toff, 0));
 	TRY(upload_sw_inputs(c, n, q, qoff, t, toff));
@@ -480,6 +492,7 @@ extern "C" int emab_extend_resident_load(emab_ctx_t *c, int n, const uint8_t *q,
 
 extern "C" int emab_extend_resident_run(emab_ctx_t *c, int w, int end_bonus, int zdrop, int reps, int32_t *out, int64_t *cells)
 {
+	CTX_ENTER(c);
 	if (!c || c->res_n <= 0 || reps <= 0) return EMAB_ERR_ARG;
 	const int n = c->res_n;
 	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
@@ -503,6 +516,7 @@ extern "C" int emab_extend_resident_run(emab_ctx_t *c, int w, int end_bonus, int
 extern "C" int emab_global_batch(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
                                  const int32_t *w, int32_t *out, uint32_t *cigar, int max_cigar, int64_t *cells)
 {
+	CTX_ENTER(c);
 	if (!c || n < 0 || max_cigar <= 0) return EMAB_ERR_ARG;
 	if (n == 0) { if (cells) *cells = 0; return EMAB_OK; }
 	TRY(check_lengths(n, qoff, toff, 0));
@@ -544,6 +558,7 @@ extern "C" int emab_global_batch(emab_ctx_t *c, int n, const uint8_t *q, const i
 extern "C" int emab_local_batch(emab_ctx_t *c, int n, const uint8_t *q, const int64_t *qoff, const uint8_t *t, const int64_t *toff,
                                 int32_t *out, int64_t *cells)
 {
+	CTX_ENTER(c);
 	if (!c || n < 0) return EMAB_ERR_ARG;
 	if (n == 0) { if (cells) *cells = 0; return EMAB_OK; }
 	TRY(check_lengths(n, qoff, toff, KSW_MAX_TLEN));
@@ -578,6 +593,7 @@ __global__ void k_sa_batch(DevIndex ix, int n, const int64_t *k, int64_t *out, i
 
 extern "C" int emab_sa_batch(emab_ctx_t *c, int n, const int64_t *k, int64_t *out, int mode)
 {
+	CTX_ENTER(c);
 	if (!c || !c->ix || n < 0) return EMAB_ERR_ARG;
 	if (n == 0) return EMAB_OK;
 	for (int i = 0; i < n; ++i) if (k[i] < 0 || (uint64_t)k[i] > c->ix->d.seq_len) { snprintf(emab_errbuf, sizeof emab_errbuf, "SA index out of range"); return EMAB_ERR_ARG; }
@@ -597,6 +613,7 @@ extern "C" int emab_sa_batch(emab_ctx_t *c, int n, const int64_t *k, int64_t *ou
 extern "C" int emab_smem_batch(emab_ctx_t *c, int n, const uint8_t *seq, const int64_t *off, int64_t *intervals, int32_t *n_intv,
                                int max_intv, int64_t *touches)
 {
+	CTX_ENTER(c);
 	if (!c || !c->ix || n < 0 || max_intv <= 0) return EMAB_ERR_ARG;
 	if (n == 0) { if (touches) *touches = 0; return EMAB_OK; }
 	for (int i = 0; i < n; ++i) {

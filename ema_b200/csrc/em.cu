@@ -155,6 +155,7 @@ static int up(emab_ctx *c, DevBuf &b, const void *src, size_t bytes)
 
 extern "C" int emab_em_batch(emab_ctx_t *c, const emab_em_problem_t *h, double *gamma_out)
 {
+	CTX_ENTER(c);
 	if (!c || !h || h->n_bc < 0) return EMAB_ERR_ARG;
 	if (h->n_bc == 0 || h->n_cands == 0) return EMAB_OK;
 	const int nb = h->n_bc, E = h->n_entries, K = h->n_cands, C = h->n_clouds, G = h->n_groups, U = h->n_units;

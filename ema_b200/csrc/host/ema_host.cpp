@@ -1246,6 +1246,7 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 	const double t0 = now_ms();
 	auto body = [&](int w) {
 		Worker &wk = s->workers[w];
+		emab_ctx_make_current(wk.ctx);   // worker threads start on device 0
 		wk.n_threads = per;
 		for (;;) {
 			const int i = next.fetch_add(1);

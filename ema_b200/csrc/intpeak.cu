@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) k_intpeak(int iters, int *sink, int seed)
 
 extern "C" int emab_int_peak(emab_ctx_t *c, int kind, int iters, double *gops_per_s, double *ms_out)
 {
+	CTX_ENTER(c);
 	if (!c || kind < 0 || kind > 19 || iters <= 0 || !gops_per_s) return EMAB_ERR_ARG;
 	if (c->b[27].ensure(64)) return EMAB_ERR_NOMEM;
 	const int grid = c->n_sm * 8, block = 256;

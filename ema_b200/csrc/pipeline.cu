@@ -369,6 +369,7 @@ static int upload(emab_ctx *c, DevBuf &b, const void *src, size_t bytes)
 
 extern "C" int emab_set_error_rate(emab_ctx_t *c, double eps)
 {
+	CTX_ENTER(c);
 	if (!c || !(eps > 0 && eps < 1)) return EMAB_ERR_ARG;
 	ScoreConsts sc;
 	fill_consts(sc, eps);
@@ -381,6 +382,7 @@ extern "C" int emab_set_error_rate(emab_ctx_t *c, double eps)
 extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, const int64_t *off, int stage, int want_regs,
                                 emab_pairs_result_t *res, emab_stats_t *stats)
 {
+	CTX_ENTER(c);
 	if (!c || !c->ix || !res || n_pairs < 0 || stage < 1 || stage > 3) return EMAB_ERR_ARG;
 	const int R = 2 * n_pairs;
 	memset(res, 0, sizeof *res);

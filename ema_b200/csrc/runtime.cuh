@@ -63,6 +63,7 @@ struct emab_index {
 
 struct emab_ctx {
 	emab_index *ix = nullptr;
+	int device = 0;          // every entry point makes it current first: callers may be threads that never chose a device
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaEvent_t stage_ev[8] = {};
@@ -79,3 +80,7 @@ struct emab_ctx {
 	bool rescue_plan = true; // mate-rescue alignments planned and run as one balanced batch (pipeline.cu, k_rescue_plan)
 	bool consts_ready = false;
 };
+
+// first statement of every entry point that takes a ctx: a worker thread of the host pipeline (or any caller's
+// thread) starts on device 0, and a stream or buffer of another device is an invalid argument there
+#define CTX_ENTER(c) do { if (c) CUDA_TRY(cudaSetDevice((c)->device)); } while (0)

@@ -48,6 +48,9 @@ double emab_index_build_ms(const emab_index_t *ix); /* device time spent densify
 
 int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out);  /* ix may be NULL for the sequence-only SW calls */
 void emab_ctx_free(emab_ctx_t *ctx);
+/* Makes the ctx's device current on the calling thread.  Every entry point that takes a ctx does this itself; a
+ * thread that allocates pinned memory before its first ctx call uses it to stay off device 0. */
+int emab_ctx_make_current(emab_ctx_t *ctx);
 /* device time (ms, CUDA events on the ctx stream) of the kernels launched by the last call, and
  * the number of kernel launches it made */
 double emab_last_kernel_ms(const emab_ctx_t *ctx);
