@@ -315,16 +315,50 @@ struct Rec {  // SAMRecord (include/samrecord.h:22-58), fields on the path only
 
 struct Cloud { double exp_cov = 0, weight = 0; int parent = -1, child = -1, id = 0; bool bad = false; };
 
+// A read has one or two candidates nearly always: the candidate lists of a SAMDict entry live inside the entry and
+// only spill to the heap beyond N (a malloc per list per read was a fifth of the cloud-building time).
+template <class T, int N>
+struct SmallVec {
+	T inl[N];
+	T *p = inl;
+	uint32_t n = 0, cap = N;
+	SmallVec() = default;
+	SmallVec(const SmallVec &) = delete;
+	SmallVec &operator=(const SmallVec &) = delete;
+	SmallVec(SmallVec &&o) noexcept { take(o); }
+	SmallVec &operator=(SmallVec &&o) noexcept { if (this != &o) { if (p != inl) free(p); take(o); } return *this; }
+	~SmallVec() { if (p != inl) free(p); }
+	void take(SmallVec &o) noexcept
+	{
+		n = o.n; cap = o.cap;
+		if (o.p == o.inl) { memcpy(inl, o.inl, sizeof(T) * o.n); p = inl; cap = N; }
+		else { p = o.p; o.p = o.inl; }
+		o.n = 0; o.cap = N;
+	}
+	void push_back(T v)
+	{
+		if (n == cap) {
+			const uint32_t c = cap * 2;
+			T *q = (T *)malloc(sizeof(T) * c);
+			if (!q) throw std::bad_alloc();
+			memcpy(q, p, sizeof(T) * n);
+			if (p != inl) free(p);
+			p = q; cap = c;
+		}
+		p[n++] = v;
+	}
+	void pop_back() { --n; }
+	size_t size() const { return n; }
+	T &operator[](size_t i) { return p[i]; }
+	const T &operator[](size_t i) const { return p[i]; }
+};
+
 struct Entry {  // SAMDictEnt (include/samdict.h:15-28)
 	int key;                       // record index
 	int mate = -1;                 // entry index
-	std::vector<int> cand_rec, cand_cloud;
-	std::vector<double> gamma;
+	SmallVec<int, 4> cand_rec, cand_cloud;
+	const double *gamma = nullptr; // posteriors of the candidates (into the batch's EM result), set before choose()
 	bool visited = false;
-};
-
-struct KeyHash {
-	size_t operator()(const std::pair<std::string_view, int> &k) const { return std::hash<std::string_view>()(k.first) * 2 + k.second; }
 };
 
 static inline bool is_pair(const Rec &a, const Rec &b)
@@ -362,17 +396,37 @@ struct Barcode {
 	std::vector<Rec> recs;                 // after sort: (chrom&0xff, pos, ident) order
 	std::vector<Cloud> clouds;
 	std::vector<Entry> entries;            // insertion order; the reference walks them newest first
-	std::unordered_map<std::pair<std::string_view, int>, int, KeyHash> dict;
+	std::vector<int32_t> slots;            // SAMDict: open-addressing table of entry indices keyed by (ident, mate)
+	uint32_t slot_mask = 0;
 	std::vector<int> final_;               // records_final
 	std::vector<std::vector<int>> opt_jobs; // -d: name-sorted records of each bad cloud, in cloud order (see process_pairs)
 	TextBuf sam;
 	std::string bc_str;                    // decode_bc(bc), printed in every BX tag of this barcode
 
-	int find(const Rec &k) const
+	void dict_init(size_t n_keys)
 	{
-		auto it = dict.find({k.ident, (int)k.mate});
-		return it == dict.end() ? -1 : it->second;
+		size_t c = 16;
+		while (c < 4 * n_keys) c <<= 1;
+		slots.assign(c, -1);
+		slot_mask = (uint32_t)(c - 1);
 	}
+	static uint32_t key_hash(std::string_view ident, int mate) { return (uint32_t)(std::hash<std::string_view>()(ident) * 2 + (size_t)mate); }
+	int find_key(std::string_view ident, int mate) const
+	{
+		for (uint32_t i = key_hash(ident, mate) & slot_mask;; i = (i + 1) & slot_mask) {
+			const int e = slots[i];
+			if (e < 0) return -1;
+			const Rec &k = recs[entries[e].key];
+			if ((int)k.mate == mate && k.ident == ident) return e;
+		}
+	}
+	void dict_insert(std::string_view ident, int mate, int ei)
+	{
+		uint32_t i = key_hash(ident, mate) & slot_mask;
+		while (slots[i] >= 0) i = (i + 1) & slot_mask;
+		slots[i] = ei;
+	}
+	int find(const Rec &k) const { return find_key(k.ident, (int)k.mate); }
 	int dict_add(int ri, int cloud, bool force, bool many_clouds);
 	void dict_del(int ri) { int e = find(recs[ri]); if (e >= 0) { entries[e].cand_rec.pop_back(); entries[e].cand_cloud.pop_back(); } }
 	void build_clouds(const Session *s, const std::vector<Pair> &pairs);
@@ -411,10 +465,10 @@ int Barcode::dict_add(int ri, int v, bool force, bool many_clouds)
 	e.cand_rec.push_back(ri);
 	e.cand_cloud.push_back(v);
 	ei = (int)entries.size();
-	auto it = dict.find({k.ident, 1 - (int)k.mate});  // find_mate_for_key
-	if (it != dict.end()) { e.mate = it->second; entries[it->second].mate = ei; }
+	const int me = find_key(k.ident, 1 - (int)k.mate);  // find_mate_for_key
+	if (me >= 0) { e.mate = me; entries[me].mate = ei; }
 	entries.push_back(std::move(e));
-	dict.emplace(std::make_pair(k.ident, (int)k.mate), ei);
+	dict_insert(recs[ri].ident, (int)recs[ri].mate, ei);
 	return 0;
 }
 
@@ -561,7 +615,8 @@ void Barcode::build_clouds(const Session *s, const std::vector<Pair> &pairs)
 	});
 	const bool many = s->tech->many_clouds != 0;
 	const size_t n = recs.size();
-	dict.reserve(2 * (size_t)n_pairs + 8);
+	dict_init(2 * (size_t)n_pairs + 8);
+	entries.reserve(2 * (size_t)n_pairs);
 	size_t i = 0;
 	while (i < n) {
 		const int c = (int)clouds.size();
@@ -1010,7 +1065,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 		for (int ei = 0; ei < ne; ++ei) {
 			Entry &e = B.entries[ei];
 			const int p = e0 + (ne - 1 - ei);
-			e.gamma.assign(gamma.begin() + entry_cand_off[p], gamma.begin() + entry_cand_off[p] + (int64_t)e.cand_rec.size());
+			e.gamma = gamma.data() + entry_cand_off[p];
 		}
 		B.choose(s);
 		B.bc_str.clear();

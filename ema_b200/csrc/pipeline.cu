@@ -163,7 +163,7 @@ k_chain(DevIndex ix, int n_reads, const int64_t *off, const Intv *intv, const in
 	p.n_chains[r] = chain_read(ix, (int)(off[r + 1] - off[r]), intv + (size_t)r * EMAB_MAX_INTV, n_intv[r], wk, cap, p.chains + o, p.seeds + o);
 }
 
-__global__ void __launch_bounds__(PL_WARPS * 32)
+__global__ void __launch_bounds__(PL_WARPS * 32, 3)
 k_align1(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p,
          uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
 {
