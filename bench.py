@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
     ap.add_argument("--workers", type=int, default=8, help="buckets in flight per GPU in the end-to-end pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-only", action="store_true",
+                    help="profiling aid (ncu captures): one bucket at a time only, no multi-bucket warm-up and an e2e pass of one bucket in flight")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -233,7 +235,10 @@ def main():
     for i in range(args.warmup):
         sess.align_bucket(bucket_bytes(i))
     # warm every worker context (device scratch and pinned buffers are grow-only and allocated on first use)
-    sess.align_buckets([bucket_bytes(i % (args.warmup + args.steps)) for i in range(max(args.warmup, 2 * args.workers))], keep_text=False)
+    if args.single_only:
+        sess.set_workers(1)
+    else:
+        sess.align_buckets([bucket_bytes(i % (args.warmup + args.steps)) for i in range(max(args.warmup, 2 * args.workers))], keep_text=False)
     sampler = ClockSampler(local_rank)
     # ---- pass A: one bucket at a time; device time of the kernel sequence (inputs resident when the
     #      CUDA-event region starts) gives `value`, the per-kernel times give the roofline

@@ -159,9 +159,12 @@ extern "C" int emab_em_batch(emab_ctx_t *c, const emab_em_problem_t *h, double *
 	if (!c || !h || h->n_bc < 0) return EMAB_ERR_ARG;
 	if (h->n_bc == 0 || h->n_cands == 0) return EMAB_OK;
 	const int nb = h->n_bc, E = h->n_entries, K = h->n_cands, C = h->n_clouds, G = h->n_groups, U = h->n_units;
-	static double log_n[5001];
-	static bool init = false;
-	if (!init) { log_n[0] = 0; for (int i = 1; i <= 5000; ++i) log_n[i] = log((double)i); init = true; }  // glibc, as src/util.c:138
+	struct LogTable {  // ln(n) from glibc, as src/util.c:138; a class-type static: initialised once, thread-safely (workers call concurrently)
+		double v[5001];
+		LogTable() { v[0] = 0; for (int i = 1; i <= 5000; ++i) v[i] = log((double)i); }
+	};
+	static const LogTable log_table;
+	const double *log_n = log_table.v;
 	EmProblem P;
 	P.n_bc = nb; P.many_clouds = h->many_clouds; P.log_eps = log(1e-50);
 	DevBuf *b = c->b;
@@ -183,7 +186,7 @@ extern "C" int emab_em_batch(emab_ctx_t *c, const emab_em_problem_t *h, double *
 	TRY(up(c, b[15], h->cloud_contrib, (size_t)K * 4));        P.cloud_contrib = b[15].as<int32_t>();
 	TRY(up(c, b[16], h->unit_first, (size_t)U * 4));           P.unit_first = b[16].as<int32_t>();
 	TRY(up(c, b[17], h->unit_second, (size_t)U * 4));          P.unit_second = b[17].as<int32_t>();
-	TRY(up(c, b[18], log_n, sizeof log_n));                    P.log_n = b[18].as<double>();
+	TRY(up(c, b[18], log_n, sizeof log_table.v));                    P.log_n = b[18].as<double>();
 	TRY(b[19].ensure((size_t)K * 8));                          P.gamma = b[19].as<double>();
 	TRY(b[20].ensure((size_t)K * 8));                          P.cw = b[20].as<double>();
 	TRY(b[21].ensure((size_t)C * 16 + 16));                    P.exp_cov = b[21].as<double>(); P.weight = P.exp_cov + C;

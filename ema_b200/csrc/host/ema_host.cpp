@@ -746,16 +746,20 @@ static inline char *put_cigar(char *w, const emab_cand_t *a, const uint32_t *cig
 	return w;
 }
 
+// Lookup tables are function-local statics of class type: C++11 initialises them once, thread-safely (several
+// buckets' teams reach them at the same time; a hand-rolled `static bool init` flag is a data race).
+struct RcTable {
+	char t[256];
+	RcTable()
+	{
+		memset(t, 'N', sizeof t);
+		t[(unsigned char)'A'] = 'T'; t[(unsigned char)'C'] = 'G'; t[(unsigned char)'G'] = 'C'; t[(unsigned char)'T'] = 'A';
+	}
+};
 static const char *rc_table()
 {
-	static char tab[256];
-	static bool init = false;
-	if (!init) {
-		memset(tab, 'N', sizeof tab);
-		tab[(unsigned char)'A'] = 'T'; tab[(unsigned char)'C'] = 'G'; tab[(unsigned char)'G'] = 'C'; tab[(unsigned char)'T'] = 'A';
-		init = true;
-	}
-	return tab;
+	static const RcTable tab;
+	return tab.t;
 }
 
 static void print_sam_record(const Session *s, const Barcode &b, const std::vector<Pair> &pairs, int ri, int mi, int cloud_base, TextBuf *o)
@@ -851,16 +855,18 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 // ---------------------------------------------------------------------------------------------
 // one batch of barcode-sorted pairs: device alignment, clouds, EM, choice, SAM
 // ---------------------------------------------------------------------------------------------
-static const uint8_t *nt4_table()
-{
-	static uint8_t t[256];
-	static bool init = false;
-	if (!init) {
+struct Nt4Table {
+	uint8_t t[256];
+	Nt4Table()
+	{
 		memset(t, 4, sizeof t);
 		t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
-		init = true;
 	}
-	return t;
+};
+static const uint8_t *nt4_table()
+{
+	static const Nt4Table tab;
+	return tab.t;
 }
 
 static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector<Pair> &pairs, char **out_buf, size_t *out_len, emab_run_stats_t &st)
@@ -1110,12 +1116,14 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 // ---------------------------------------------------------------------------------------------
 // inputs
 // ---------------------------------------------------------------------------------------------
+struct WsTable {  // isspace() in the C locale, as a table (the tail loop of the bucket parser)
+	bool t[256];
+	WsTable() { for (int c = 0; c < 256; ++c) t[c] = c == ' ' || (c >= '\t' && c <= '\r'); }
+};
 static const bool *ws_table()
-{  // isspace() in the C locale, as a table (the hot loop of the bucket parser)
-	static bool t[256];
-	static bool init = false;
-	if (!init) { for (int c = 0; c < 256; ++c) t[c] = c == ' ' || (c >= '\t' && c <= '\r'); init = true; }
-	return t;
+{
+	static const WsTable tab;
+	return tab.t;
 }
 
 static inline std::string_view token(const char *&p, const char *end)

@@ -60,33 +60,18 @@ __device__ __forceinline__ int warp_scan_max(int v, int lane)
 // ---------------------------------------------------------------------------------------------
 // ksw_extend2.  sm.q[0..qlen) must hold the query in extension order (and be visible: callers
 // __syncwarp() after filling it).  All arguments and the result are warp-uniform.
-//
-// The DP state eh[0..qlen] (bwa/ksw.c:412-414) lives in REGISTERS, in strips: lane l owns the S consecutive
-// columns [l*S, l*S+S), S = ceil((qlen+1)/32), whatever the adaptive band [beg,end) is doing; columns outside
-// the band are left alone, as in the reference.  A row is
-//   S cells   M = H(i-1,j-1) ? H(i-1,j-1)+s : 0, the gap-open term tI = max(M-oe_ins, 0)          (registers only)
-//   1 scan    exclusive max-plus prefix over the lanes' max(tI_j + j*e_ins): F entering each strip   (6 shuffles)
-//   S cells   F, H = max(M, E, F), E for the next row; row maximum with "last j wins"                (registers only)
-//   1 shuffle H(i, l*S-1) from the lane below: eh[j].h holds H of the column to its LEFT (bwa/ksw.c:471)
-//   4 REDUX   row maximum+argmax (one packed key), H(i,end-1), first / last non-zero column
-// against 10 shuffles, 4 REDUX and a shared-memory round trip per cell for every 32 columns of band before.
 // ---------------------------------------------------------------------------------------------
-template <int S, class TF>
-__device__ ExtResult warp_extend_strips(WarpDP &sm, int qlen, const TF &tf, int tlen, int w, int end_bonus, int zdrop, int h0,
-                                        unsigned long long *cells)
+template <class TF>
+__device__ ExtResult warp_extend(WarpDP &sm, int qlen, const TF &tf, int tlen, int w, int end_bonus, int zdrop, int h0,
+                                 unsigned long long *cells)
 {
 	const int lane = threadIdx.x & 31;
-	constexpr int o_del = opt::o_del, e_del = opt::e_del, e_ins = opt::e_ins, oe_del = opt::oe_del, oe_ins = opt::oe_ins;
-	const int j0 = lane * S;
-	int Hs[S], Es[S], Q[S];   // eh[j].h = H(i-1, j-1), eh[j].e = E(i, j), query base of column j
-	// first row (bwa/ksw.c:431-433): eh[0].h = h0, eh[j].h = max(h0 - oe_ins - (j-1)*e_ins, 0), e = 0
-#pragma unroll
-	for (int k = 0; k < S; ++k) {
-		const int j = j0 + k;
+	const int o_del = opt::o_del, e_del = opt::e_del, e_ins = opt::e_ins, oe_del = opt::oe_del, oe_ins = opt::oe_ins;
+	// first row (bwa/ksw.c:431-433): H(-1,j) = max(h0 - oe_ins - (j-1)*e_ins, 0), E = 0
+	for (int j = lane; j <= qlen; j += 32) {
 		int v = j == 0 ? h0 : h0 - oe_ins - (j - 1) * e_ins;
-		Hs[k] = (j <= qlen && v > 0) ? v : 0;
-		Es[k] = 0;
-		Q[k] = j < qlen ? sm.q[j] : 4;
+		sm.H[j] = v > 0 ? v : 0;
+		sm.E[j] = 0;
 	}
 	{  // band clamp (bwa/ksw.c:435-443); max(mat) = a
 		int max_ins = (int)((double)(qlen * opt::a + end_bonus - opt::o_ins) / e_ins + 1.);
@@ -96,6 +81,7 @@ __device__ ExtResult warp_extend_strips(WarpDP &sm, int qlen, const TF &tf, int 
 		w = w < max_ins ? w : max_ins;
 		w = w < max_del ? w : max_del;
 	}
+	__syncwarp();
 	int best = h0, best_i = -1, best_j = -1, g_i = -1, g = -1, max_off = 0;
 	int beg = 0, end = qlen;
 	unsigned long long visited = 0;
@@ -106,62 +92,51 @@ __device__ ExtResult warp_extend_strips(WarpDP &sm, int qlen, const TF &tf, int 
 		if (beg < i - w) beg = i - w;
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
-		int h_first = 0;  // H(i, beg-1)
-		if (beg == 0) { h_first = h0 - (o_del + e_del * (i + 1)); if (h_first < 0) h_first = 0; }
+		int carry_h = 0;  // H(i, beg-1)
+		if (beg == 0) { carry_h = h0 - (o_del + e_del * (i + 1)); if (carry_h < 0) carry_h = 0; }
+		int carry_f = 0;  // F(i, j0)
+		int m = 0, mj = -1;           // lane-local row max / argmax (last j wins ties)
+		int nz_first = 0x7fffffff, nz_last = -1;  // first / last j in [beg,end] whose new (h,e) is non-zero
+		const int h_first = carry_h;
 		if (end > beg) visited += end - beg;
-		// ---- phase 1: M and the gap-open terms of this lane's cells inside the band
-		int Ms[S], tI[S];
-		int top = KSW_NEG_INF;
-#pragma unroll
-		for (int k = 0; k < S; ++k) {
-			const int j = j0 + k;
-			const bool in = j >= beg && j < end;
-			const int diag = Hs[k];
-			const int M = (in && diag) ? diag + sc_mat(tb, Q[k]) : 0;   // bwa/ksw.c:469
-			Ms[k] = M;
-			int t = M - oe_ins; t = t > 0 ? t : 0;                         // opens F(i, j+1)
-			tI[k] = t;
-			if (in) top = max(top, t + j * e_ins);
-		}
-		const int incl = warp_scan_max(top, lane);
-		int run = __shfl_up_sync(FULL_MASK, incl, 1);                      // max over band columns left of this strip
-		if (lane == 0) run = KSW_NEG_INF;
-		// ---- phase 2: F, H, E; row maximum (last j wins ties, bwa/ksw.c:473); H(i, end-1)
-		int hs[S];
-		int key = -1, h_last = 0;
-#pragma unroll
-		for (int k = 0; k < S; ++k) {
-			const int j = j0 + k;
-			const bool in = j >= beg && j < end;
-			int f = run - (j - 1) * e_ins; f = f > 0 ? f : 0;            // F(i,j) = max_{beg<=c<j}(tI_c - (j-1-c)*e_ins), 0 at beg
-			const int e = Es[k], M = Ms[k];
-			int h = M > e ? M : e; h = h > f ? h : f;
-			hs[k] = h;
-			if (in) {
-				run = max(run, tI[k] + j * e_ins);
+		for (int j0 = beg; j0 < end; j0 += 32) {
+			const int j = j0 + lane;
+			const bool act = j < end;
+			int diag = 0, e = 0, M = 0;
+			if (act) {
+				diag = sm.H[j]; e = sm.E[j];
+				M = diag ? diag + sc_mat(tb, sm.q[j]) : 0;   // bwa/ksw.c:469
+			}
+			int tI = M - oe_ins; tI = tI > 0 ? tI : 0;       // opens F(i, j+1)
+			// F(i,j) = max(carry_f - (j-j0)*e_ins, max_{j0<=k<j} (tI_k - (j-1-k)*e_ins))
+			int v = tI + j * e_ins;
+			int p = warp_scan_max(v, lane);
+			int px = __shfl_up_sync(FULL_MASK, p, 1);
+			int f = carry_f - lane * e_ins;
+			if (lane) f = max(f, px - (j - 1) * e_ins);
+			int h = max(max(M, e), f);
+			int hl = __shfl_up_sync(FULL_MASK, h, 1);        // H(i, j-1)
+			if (lane == 0) hl = carry_h;
+			if (act) {
 				int t = M - oe_del; t = t > 0 ? t : 0;
-				const int en = e - e_del;
-				Es[k] = en > t ? en : t;                                   // E(i+1, j), opened from M only
-				key = max(key, (h << 12) | j);
-				if (j == end - 1) h_last = h;
+				int en = max(e - e_del, t);                   // E(i+1, j)
+				sm.H[j] = hl;
+				sm.E[j] = en;
+				if (h >= m) { m = h; mj = j; }
+				if (hl | en) { nz_first = min(nz_first, j); nz_last = j; }
 			}
+			const int last = min(31, end - 1 - j0);
+			carry_h = __shfl_sync(FULL_MASK, h, last);
+			carry_f = __shfl_sync(FULL_MASK, max(f - e_ins, tI), 31);
 		}
-		// ---- eh[j].h <- H(i, j-1) for j in [beg, end]; eh[end].e <- 0  (bwa/ksw.c:471,485)
-		int left = __shfl_up_sync(FULL_MASK, hs[S - 1], 1);
-		int nz_first = 0x7fffffff, nz_last = -1;  // first / last j in [beg,end) whose new (h,e) is non-zero
-#pragma unroll
-		for (int k = 0; k < S; ++k) {
-			const int j = j0 + k;
-			if (j >= beg && j <= end) {
-				const int hl = j == beg ? h_first : (k ? hs[k - 1] : left);
-				Hs[k] = hl;
-				if (j == end) Es[k] = 0;
-				else if (hl | Es[k]) { nz_first = min(nz_first, j); nz_last = j; }
-			}
-		}
-		const int rkey = warp_max(key);
-		const int rm = rkey < 0 ? 0 : rkey >> 12, rj = rkey < 0 ? -1 : (rkey & 4095);
-		const int h1 = (end > beg) ? warp_max(h_last) : h_first;
+		// eh[end] = {h1, 0}  (bwa/ksw.c:485)
+		if (lane == 0) { sm.H[end] = carry_h; sm.E[end] = 0; }
+		const int h1 = (end > beg) ? carry_h : h_first;
+		if (end <= beg && lane == 0) sm.H[end] = h_first;
+		// row max with "last j wins ties"
+		const int rm = warp_max(m);
+		int cand = (m == rm) ? mj : -1;
+		const int rj = warp_max(cand);
 		const int jfin = end > beg ? end : beg;
 		if (jfin == qlen) {  // bwa/ksw.c:486-489: later rows win ties
 			if (!(g > h1)) g_i = i;
@@ -185,24 +160,12 @@ __device__ ExtResult warp_extend_strips(WarpDP &sm, int qlen, const TF &tf, int 
 		int jl = nl >= nbeg ? nl : nbeg - 1;        // downward scan stops below beg
 		beg = nbeg;
 		end = jl + 2 < qlen ? jl + 2 : qlen;
+		__syncwarp();
 	}
 	if (cells && lane == 0) atomicAdd(cells, visited);
 	ExtResult r;
 	r.score = best; r.qle = best_j + 1; r.tle = best_i + 1; r.gtle = g_i + 1; r.gscore = g; r.max_off = max_off;
 	return r;
-}
-
-// strip width by query length: the smallest instantiated S with 32*S > qlen (columns 0..qlen)
-template <class TF>
-__device__ __forceinline__ ExtResult warp_extend(WarpDP &sm, int qlen, const TF &tf, int tlen, int w, int end_bonus, int zdrop, int h0,
-                                                 unsigned long long *cells)
-{
-	static_assert(EMAB_MAX_READ_LEN < 32 * 9, "widest strip");
-	if (qlen < 32 * 1) return warp_extend_strips<1>(sm, qlen, tf, tlen, w, end_bonus, zdrop, h0, cells);
-	if (qlen < 32 * 2) return warp_extend_strips<2>(sm, qlen, tf, tlen, w, end_bonus, zdrop, h0, cells);
-	if (qlen < 32 * 4) return warp_extend_strips<4>(sm, qlen, tf, tlen, w, end_bonus, zdrop, h0, cells);
-	if (qlen < 32 * 6) return warp_extend_strips<6>(sm, qlen, tf, tlen, w, end_bonus, zdrop, h0, cells);
-	return warp_extend_strips<9>(sm, qlen, tf, tlen, w, end_bonus, zdrop, h0, cells);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -163,7 +163,7 @@ k_chain(DevIndex ix, int n_reads, const int64_t *off, const Intv *intv, const in
 	p.n_chains[r] = chain_read(ix, (int)(off[r + 1] - off[r]), intv + (size_t)r * EMAB_MAX_INTV, n_intv[r], wk, cap, p.chains + o, p.seeds + o);
 }
 
-__global__ void __launch_bounds__(PL_WARPS * 32, 3)
+__global__ void __launch_bounds__(PL_WARPS * 32)
 k_align1(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p,
          uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
 {
@@ -448,8 +448,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	CUDA_TRY(cudaEventRecord(c->stage_ev[3], st));
 	if (c->sw_mode == 2) {  // thread-per-read mem_align1_core: wins only when a batch holds many more reads than the GPU has lanes
 		const size_t smem = lanes::smem_per_warp(max_len);
-		static bool configured = false;
-		if (!configured) { CUDA_TRY(cudaFuncSetAttribute(k_align1_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); configured = true; }
+		CUDA_TRY(cudaFuncSetAttribute(k_align1_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  // per device, cheap: no once-flag
 		int per_sm = (int)((227 * 1024) / (smem + 1024));
 		per_sm = per_sm > 32 ? 32 : (per_sm < 1 ? 1 : per_sm);
 		int lgrid = c->n_sm * per_sm;

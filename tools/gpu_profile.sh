@@ -19,8 +19,9 @@ kill $SMI
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_${WL}.csv \
     python bench.py --workload $WL --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
 tail -2 $OUT/${TAG}_ncu_bench.log
-# full capture of the pipeline kernels of one warm bucket
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_seed|k_chain|k_align1|k_rescue|k_finalize|k_em' -s 14 -c 7 \
-    -f -o $OUT/${TAG}_prof_${WL} python bench.py --workload $WL --steps 1 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
-tail -2 $OUT/${TAG}_ncu_full.log
+# full capture of the pipeline kernels of one warm bucket: buckets one at a time (--single-only), two warm-up buckets
+# = 18 launches of these kernels skipped, then the 9 of the next bucket
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_seed|k_chain|k_align1|k_rescue|k_finalize|k_em' -s 18 -c 9 \
+    -f -o $OUT/${TAG}_prof_${WL} python bench.py --workload $WL --steps 1 --warmup 2 --single-only --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
+tail -2 $OUT/${TAG}_ncu_full.log | cut -c1-300
 ls -la $OUT
