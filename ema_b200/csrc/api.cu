@@ -195,6 +195,8 @@ extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CUDA_TRY(cudaEventCreate(&c->ev0));
 	CUDA_TRY(cudaEventCreate(&c->ev1));
+	CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+	if (const char *e = getenv("EMAB_SYNC")) c->spin_wait = strcmp(e, "block") != 0;
 	CUDA_TRY(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
@@ -220,7 +222,7 @@ extern "C" void emab_ctx_free(emab_ctx_t *c)
 	for (auto &b : c->b) b.release();
 	for (auto &b : c->h) b.release();
 	cudaFree(c->d_counters);
-	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->ev_wait) cudaEventDestroy(c->ev_wait);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }

@@ -423,7 +423,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	++launches;
 	int32_t T = 0;
 	CUDA_TRY(cudaMemcpyAsync(&T, d_occ_off + R, 4, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(ctx_wait(c));
 	if (T < 0) { snprintf(emab_errbuf, sizeof emab_errbuf, "seed occurrence count overflow"); return EMAB_ERR_OVERFLOW; }
 	const size_t Tn = (size_t)T + 1, NR = (size_t)T + (size_t)RESCUE_ROOM * R + 1;
 	Pools p;
@@ -483,7 +483,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	++launches;
 	int32_t A = 0;
 	CUDA_TRY(cudaMemcpyAsync(&A, d_aln_off + R, 4, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(ctx_wait(c));
 	CUDA_TRY(cudaGetLastError());
 	int32_t NC = 0;
 	CUDA_TRY(cudaEventRecord(c->stage_ev[6], st));
@@ -506,7 +506,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		CUDA_TRY(cudaEventRecord(c->ev1, st));
 		CUDA_TRY(cudaEventRecord(c->stage_ev[7], st));
 		CUDA_TRY(cudaMemcpyAsync(&NC, d_cig_off + A, 4, cudaMemcpyDeviceToHost, st));
-		CUDA_TRY(cudaStreamSynchronize(st));
+		CUDA_TRY(ctx_wait(c));
 		TRY(c->h[1].ensure(((size_t)A + 1) * sizeof(emab_cand_t)));
 		TRY(c->h[2].ensure(((size_t)NC + 1) * 4));
 		if (A) CUDA_TRY(cudaMemcpyAsync(c->h[1].p, c->b[21].p, (size_t)A * sizeof(emab_cand_t), cudaMemcpyDeviceToHost, st));
@@ -527,7 +527,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	unsigned long long *cnt = (unsigned long long *)((char *)c->h[0].p + (((size_t)R * 4 + 16 + 7) & ~(size_t)7));
 	CUDA_TRY(cudaMemcpyAsync(h_err, d_err, 16, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaMemcpyAsync(cnt, c->d_counters, 128, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(ctx_wait(c));
 	CUDA_TRY(cudaGetLastError());
 	res->n_cands = A; res->n_cigar_ops = NC; res->n_regs = (const int32_t *)c->h[0].p;
 	res->cands = stage >= 3 ? (const emab_cand_t *)c->h[1].p : nullptr;
