@@ -123,5 +123,6 @@ int emab_session_dump_posteriors(emab_session_t *h, const char *path)
 
 emab_ctx_t *emab_session_ctx(emab_session_t *h) { return h ? h->s->workers[0].ctx : nullptr; }
 void emab_free(void *p) { emab::text_free(p); }
+int emab_host_selftest(void) { return emab::host_selftest(); }
 
 }  // extern "C"

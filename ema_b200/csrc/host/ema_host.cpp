@@ -25,7 +25,7 @@
 #include <cstring>
 #include <ctime>
 #include <atomic>
-#include <emmintrin.h>
+#include <immintrin.h>
 #include <malloc.h>
 #include <mutex>
 #include <string_view>
@@ -724,6 +724,98 @@ static inline int get_rlen(const emab_cand_t *a, const uint32_t *cig)
 	return l;
 }
 
+static const char *rc_table();
+static const uint8_t *nt4_table();
+
+// ---------------------------------------------------------------------------------------------
+// byte kernels of the host path: reverse(-complement) for SAM, nt4 encoding for the device.  AVX2 versions are
+// picked at run time (x86-64 only guarantees SSE2); the scalar loops are the definition.
+// ---------------------------------------------------------------------------------------------
+static void revcomp_scalar(char *dst, const char *src, size_t n)
+{
+	const char *t = rc_table();
+	for (size_t i = 0; i < n; ++i) dst[i] = t[(unsigned char)src[n - 1 - i]];
+}
+static void reverse_scalar(char *dst, const char *src, size_t n) { for (size_t i = 0; i < n; ++i) dst[i] = src[n - 1 - i]; }
+static void nt4_scalar(uint8_t *dst, const char *src, size_t n)
+{
+	const uint8_t *t = nt4_table();
+	for (size_t i = 0; i < n; ++i) dst[i] = t[(uint8_t)src[i]];
+}
+
+__attribute__((target("avx2"))) static inline __m256i rev32_avx2(__m256i v)
+{
+	const __m256i idx = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+	return _mm256_permute2x128_si256(_mm256_shuffle_epi8(v, idx), _mm256_shuffle_epi8(v, idx), 1);
+}
+// Both maps are a byte shuffle on the low nibble — A 0x41, C 0x43, G 0x47, T 0x54 have distinct low nibbles — checked
+// against the full byte, so that anything else ('N', lower case for the SAM complement, ...) takes the default.
+__attribute__((target("avx2"))) static void revcomp_avx2(char *dst, const char *src, size_t n)
+{
+	const __m256i lutc = _mm256_setr_epi8('N', 'T', 'N', 'G', 'A', 'N', 'N', 'C', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'T', 'N', 'G', 'A', 'N', 'N', 'C', 'N', 'N', 'N', 'N', 'N', 'N', 'N', 'N');
+	const __m256i lute = _mm256_setr_epi8(0, 0x41, 0, 0x43, 0x54, 0, 0, 0x47, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x41, 0, 0x43, 0x54, 0, 0, 0x47, 0, 0, 0, 0, 0, 0, 0, 0);
+	const __m256i low = _mm256_set1_epi8(0x0f), dflt = _mm256_set1_epi8('N');
+	size_t i = 0;
+	for (; i + 32 <= n; i += 32) {
+		const __m256i v = rev32_avx2(_mm256_loadu_si256((const __m256i *)(src + n - 32 - i)));
+		const __m256i nib = _mm256_and_si256(v, low);
+		const __m256i ok = _mm256_cmpeq_epi8(v, _mm256_shuffle_epi8(lute, nib));
+		_mm256_storeu_si256((__m256i *)(dst + i), _mm256_blendv_epi8(dflt, _mm256_shuffle_epi8(lutc, nib), ok));
+	}
+	if (i < n) revcomp_scalar(dst + i, src, n - i);
+}
+__attribute__((target("avx2"))) static void reverse_avx2(char *dst, const char *src, size_t n)
+{
+	size_t i = 0;
+	for (; i + 32 <= n; i += 32) _mm256_storeu_si256((__m256i *)(dst + i), rev32_avx2(_mm256_loadu_si256((const __m256i *)(src + n - 32 - i))));
+	if (i < n) reverse_scalar(dst + i, src, n - i);
+}
+__attribute__((target("avx2"))) static void nt4_avx2(uint8_t *dst, const char *src, size_t n)
+{
+	const __m256i lutc = _mm256_setr_epi8(4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4);
+	const __m256i lute = _mm256_setr_epi8(0, 0x41, 0, 0x43, 0x54, 0, 0, 0x47, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x41, 0, 0x43, 0x54, 0, 0, 0x47, 0, 0, 0, 0, 0, 0, 0, 0);
+	const __m256i low = _mm256_set1_epi8(0x0f), dflt = _mm256_set1_epi8(4), fold = _mm256_set1_epi8((char)0xdf);
+	size_t i = 0;
+	for (; i + 32 <= n; i += 32) {
+		const __m256i v = _mm256_and_si256(_mm256_loadu_si256((const __m256i *)(src + i)), fold);   // acgt -> ACGT
+		const __m256i nib = _mm256_and_si256(v, low);
+		const __m256i ok = _mm256_cmpeq_epi8(v, _mm256_shuffle_epi8(lute, nib));
+		_mm256_storeu_si256((__m256i *)(dst + i), _mm256_blendv_epi8(dflt, _mm256_shuffle_epi8(lutc, nib), ok));
+	}
+	if (i < n) nt4_scalar(dst + i, src + i, n - i);
+}
+
+static const bool g_avx2 = __builtin_cpu_supports("avx2") && !(getenv("EMAB_NO_AVX2") && atoi(getenv("EMAB_NO_AVX2")));
+static inline void revcomp_bytes(char *dst, const char *src, size_t n) { if (g_avx2) revcomp_avx2(dst, src, n); else revcomp_scalar(dst, src, n); }
+static inline void reverse_bytes(char *dst, const char *src, size_t n) { if (g_avx2) reverse_avx2(dst, src, n); else reverse_scalar(dst, src, n); }
+static inline void nt4_bytes(uint8_t *dst, const char *src, size_t n) { if (g_avx2) nt4_avx2(dst, src, n); else nt4_scalar(dst, src, n); }
+
+// test hook (tests/test_abi.py, no GPU needed): the vector kernels against their scalar definitions on every byte
+// value at every alignment and length up to 300
+int host_selftest()
+{
+	std::vector<char> src(1024), a(1024), b(1024);
+	uint32_t x = 12345;
+	for (int round = 0; round < 64; ++round) {
+		for (size_t i = 0; i < src.size(); ++i) {
+			x = x * 1664525u + 1013904223u;
+			const uint32_t r = x >> 24;
+			src[i] = round < 8 ? (char)(round * 32 + (i & 31) + (i >> 5 & 7) * 0) : (r < 200 ? "ACGTNacgtn"[r % 10] : (char)r);
+		}
+		if (round < 8) for (size_t i = 0; i < src.size(); ++i) src[i] = (char)((round * 32 + i) & 0xff);
+		for (size_t off = 0; off < 3; ++off)
+			for (size_t n = 0; n <= 300; ++n) {
+				revcomp_scalar(a.data(), src.data() + off, n); revcomp_bytes(b.data(), src.data() + off, n);
+				if (memcmp(a.data(), b.data(), n)) return 1;
+				reverse_scalar(a.data(), src.data() + off, n); reverse_bytes(b.data(), src.data() + off, n);
+				if (memcmp(a.data(), b.data(), n)) return 2;
+				nt4_scalar((uint8_t *)a.data(), src.data() + off, n); nt4_bytes((uint8_t *)b.data(), src.data() + off, n);
+				if (memcmp(a.data(), b.data(), n)) return 3;
+			}
+	}
+	return 0;
+}
+
 // SAM text goes through a raw cursor into a buffer whose room was checked once per record: the formatter is the
 // largest single consumer of host CPU on this path, and a bounds check per character was most of it.
 static inline char *put_int(char *w, long long v)
@@ -820,11 +912,10 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 	} else w = put_lit(w, "\t*\t0\t0");
 	*w++ = '\t';
 	if (rec && rec->rev) {
-		const char *rct = rc_table();
 		const size_t nr = read.size(), nq = qual.size();
-		for (size_t i = 0; i < nr; ++i) w[i] = rct[(unsigned char)read[nr - 1 - i]];
+		revcomp_bytes(w, read.data(), nr);
 		w[nr] = '\t';
-		for (size_t i = 0; i < nq; ++i) w[nr + 1 + i] = qual[nq - 1 - i];
+		reverse_bytes(w + nr + 1, qual.data(), nq);
 		w += nr + 1 + nq;
 	} else { w = put_sv(w, read); *w++ = '\t'; w = put_sv(w, qual); }
 	if (rec) {
@@ -880,7 +971,6 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	*out_buf = nullptr; *out_len = 0;
 	if (np == 0) { s->take_cloud_base(ticket, 0); *out_buf = text_alloc(1); return EMAB_OK; }
 	// ---- encode and align the whole batch on the device
-	const uint8_t *tab = nt4_table();
 	if (wk.off.ensure((2 * np + 1) * 8)) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
 	int64_t *off = (int64_t *)wk.off.p;
 	off[0] = 0;
@@ -896,9 +986,8 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	#pragma omp for schedule(static)
 	for (size_t i = 0; i < np; ++i)
 		for (int m = 0; m < 2; ++m) {
-			uint8_t *d = seq + off[2 * i + m];
 			const std::string_view r = pairs[i].read[m];
-			for (size_t k = 0; k < r.size(); ++k) d[k] = tab[(uint8_t)r[k]];
+			nt4_bytes(seq + off[2 * i + m], r.data(), r.size());
 		}
 	}
 	emab_stats_t ds;

@@ -133,6 +133,7 @@ struct GatePass {
 // Output text blocks (what emab_free releases).  Blocks of a megabyte or more are recycled through a small pool:
 // a bucket's SAM text is ~30 MB, and a fresh malloc of that size is an mmap whose 8 k first-touch page faults
 // (serialised on the process's mm lock) cost more CPU than formatting the text.
+int host_selftest();  // vector byte kernels against their scalar definitions (0 = ok)
 char *text_alloc(size_t n);
 void text_free(void *p);
 

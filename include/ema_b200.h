@@ -223,6 +223,7 @@ int emab_session_stats(const emab_session_t *s, emab_run_stats_t *out);
 int emab_session_dump_posteriors(emab_session_t *s, const char *path);
 emab_ctx_t *emab_session_ctx(emab_session_t *s);
 void emab_free(void *p);
+int emab_host_selftest(void);  /* host-side vector byte kernels checked against their scalar definitions; 0 = ok (no GPU needed) */
 
 #ifdef __cplusplus
 }
