@@ -57,6 +57,23 @@ __device__ __forceinline__ int warp_scan_max(int v, int lane)
 	return v;
 }
 
+// per-row substitution bytes of bwa_fill_scmat(1,4) (bwa/bwa.c:136-146) for a byte permute: byte q of the pair
+// (lo, hi) is the score of target base t against query code q = A,C,G,T, N (-1) and 5 = the zero-scoring
+// padding of the striped query profile (bwa/ksw.c:95-113)
+__device__ __forceinline__ uint32_t local_row_scores(int t)
+{
+	const uint32_t mis = (uint32_t)(uint8_t)(-opt::b) * 0x01010101u;
+	const uint32_t flip = (uint32_t)(uint8_t)(-opt::b) ^ (uint32_t)(uint8_t)opt::a;
+	return t < 4 ? mis ^ (flip << (t << 3)) : 0xffffffffu;
+}
+__device__ __forceinline__ int local_score(uint32_t lo, int q)
+{
+	uint32_t b, r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(b) : "r"(lo), "r"(0x000000ffu), "r"((uint32_t)q));   // byte 4 = -1 (N), byte 5 = 0 (padding)
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(0u), "r"(0x8880u));                 // sign-extend byte 0
+	return (int)r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ksw_extend2.  sm.q[0..qlen) must hold the query in extension order (and be visible: callers
 // __syncwarp() after filling it).  All arguments and the result are warp-uniform.
@@ -88,15 +105,15 @@ __device__ ExtResult warp_extend(WarpDP &sm, int qlen, const TF &tf, int tlen, i
 	int tchunk = 0;  // target bases of rows [i & ~31, +32), one per lane
 	for (int i = 0; i < tlen; ++i) {
 		if ((i & 31) == 0) tchunk = (i + lane < tlen) ? tf(i + lane) : 4;
-		const int tb = __shfl_sync(FULL_MASK, tchunk, i & 31);
+		const uint32_t rlo = local_row_scores(__shfl_sync(FULL_MASK, tchunk, i & 31));   // byte q = score(target base, q)
 		if (beg < i - w) beg = i - w;
 		if (end > i + w + 1) end = i + w + 1;
 		if (end > qlen) end = qlen;
 		int carry_h = 0;  // H(i, beg-1)
 		if (beg == 0) { carry_h = h0 - (o_del + e_del * (i + 1)); if (carry_h < 0) carry_h = 0; }
 		int carry_f = 0;  // F(i, j0)
-		int m = 0, mj = -1;           // lane-local row max / argmax (last j wins ties)
-		int nz_first = 0x7fffffff, nz_last = -1;  // first / last j in [beg,end] whose new (h,e) is non-zero
+		int key = -1;                 // lane-local row maximum and its column as (h << 12 | j): a max over keys is "last j wins ties"
+		int nz_first = 0x7fffffff, nz_last = -1;  // first / last j in [beg,end] whose new (h,e) is non-zero (warp-uniform)
 		const int h_first = carry_h;
 		if (end > beg) visited += end - beg;
 		for (int j0 = beg; j0 < end; j0 += 32) {
@@ -105,7 +122,7 @@ __device__ ExtResult warp_extend(WarpDP &sm, int qlen, const TF &tf, int tlen, i
 			int diag = 0, e = 0, M = 0;
 			if (act) {
 				diag = sm.H[j]; e = sm.E[j];
-				M = diag ? diag + sc_mat(tb, sm.q[j]) : 0;   // bwa/ksw.c:469
+				M = diag ? diag + local_score(rlo, sm.q[j]) : 0;   // bwa/ksw.c:469
 			}
 			int tI = M - oe_ins; tI = tI > 0 ? tI : 0;       // opens F(i, j+1)
 			// F(i,j) = max(carry_f - (j-j0)*e_ins, max_{j0<=k<j} (tI_k - (j-1-k)*e_ins))
@@ -117,14 +134,17 @@ __device__ ExtResult warp_extend(WarpDP &sm, int qlen, const TF &tf, int tlen, i
 			int h = max(max(M, e), f);
 			int hl = __shfl_up_sync(FULL_MASK, h, 1);        // H(i, j-1)
 			if (lane == 0) hl = carry_h;
+			int nzf = 0;
 			if (act) {
 				int t = M - oe_del; t = t > 0 ? t : 0;
 				int en = max(e - e_del, t);                   // E(i+1, j)
 				sm.H[j] = hl;
 				sm.E[j] = en;
-				if (h >= m) { m = h; mj = j; }
-				if (hl | en) { nz_first = min(nz_first, j); nz_last = j; }
+				key = max(key, (h << 12) | j);
+				nzf = hl | en;
 			}
+			const unsigned nzb = __ballot_sync(FULL_MASK, nzf != 0);
+			if (nzb) { nz_first = min(nz_first, j0 + __ffs(nzb) - 1); nz_last = j0 + 31 - __clz(nzb); }
 			const int last = min(31, end - 1 - j0);
 			carry_h = __shfl_sync(FULL_MASK, h, last);
 			carry_f = __shfl_sync(FULL_MASK, max(f - e_ins, tI), 31);
@@ -134,9 +154,8 @@ __device__ ExtResult warp_extend(WarpDP &sm, int qlen, const TF &tf, int tlen, i
 		const int h1 = (end > beg) ? carry_h : h_first;
 		if (end <= beg && lane == 0) sm.H[end] = h_first;
 		// row max with "last j wins ties"
-		const int rm = warp_max(m);
-		int cand = (m == rm) ? mj : -1;
-		const int rj = warp_max(cand);
+		const int rkey = warp_max(key);
+		const int rm = rkey < 0 ? 0 : rkey >> 12, rj = rkey < 0 ? -1 : (rkey & 4095);
 		const int jfin = end > beg ? end : beg;
 		if (jfin == qlen) {  // bwa/ksw.c:486-489: later rows win ties
 			if (!(g > h1)) g_i = i;
@@ -153,8 +172,7 @@ __device__ ExtResult warp_extend(WarpDP &sm, int qlen, const TF &tf, int tlen, i
 			else { if (best - rm - (dj - di) * e_ins > zdrop) break; }
 		}
 		// next row's [beg,end): first / last non-zero cell of eh[beg..end]  (bwa/ksw.c:502-505)
-		int nf = -warp_max(-nz_first);
-		int nl = warp_max(nz_last);
+		int nf = nz_first, nl = nz_last;
 		if (h1 != 0) { nl = max(nl, end); nf = min(nf, end); }   // eh[end].h = h1
 		int nbeg = nf < end ? nf : end;             // loop stops at j == end
 		int jl = nl >= nbeg ? nl : nbeg - 1;        // downward scan stops below beg
@@ -190,7 +208,7 @@ __device__ int warp_global(WarpDP &sm, int qlen, const TF &tf, int tlen, int w, 
 	int tchunk = 0;
 	for (int i = 0; i < tlen; ++i) {
 		if ((i & 31) == 0) tchunk = (i + lane < tlen) ? tf(i + lane) : 4;
-		const int tb = __shfl_sync(FULL_MASK, tchunk, i & 31);
+		const uint32_t rlo = local_row_scores(__shfl_sync(FULL_MASK, tchunk, i & 31));   // byte q = score(target base, q)
 		const int beg = i > w ? i - w : 0;
 		const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
 		int carry_h = beg == 0 ? -(opt::o_del + e_del * (i + 1)) : KSW_NEG_INF;
@@ -200,7 +218,7 @@ __device__ int warp_global(WarpDP &sm, int qlen, const TF &tf, int tlen, int w, 
 			const int j = j0 + lane;
 			const bool act = j < end;
 			int M = KSW_NEG_INF, e = KSW_NEG_INF;
-			if (act) { M = sm.H[j] + sc_mat(tb, sm.q[j]); e = sm.E[j]; }
+			if (act) { M = sm.H[j] + local_score(rlo, sm.q[j]); e = sm.E[j]; }
 			const int tI = M - oe_ins;
 			int v = tI + j * e_ins;
 			int p = warp_scan_max(v, lane);
@@ -276,23 +294,6 @@ __device__ inline int global_backtrack(const uint8_t *z, int qlen, int tlen, int
 // reference.  Each lane owns the columns j = lane (mod 32), so H/E need no cross-lane ordering.
 // ---------------------------------------------------------------------------------------------
 struct PassResult { int score, te, qe, score2, te2; };
-
-// per-row substitution bytes of bwa_fill_scmat(1,4) (bwa/bwa.c:136-146) for a byte permute: byte q of the pair
-// (lo, hi) is the score of target base t against query code q = A,C,G,T, N (-1) and 5 = the zero-scoring
-// padding of the striped query profile (bwa/ksw.c:95-113)
-__device__ __forceinline__ uint32_t local_row_scores(int t)
-{
-	const uint32_t mis = (uint32_t)(uint8_t)(-opt::b) * 0x01010101u;
-	const uint32_t flip = (uint32_t)(uint8_t)(-opt::b) ^ (uint32_t)(uint8_t)opt::a;
-	return t < 4 ? mis ^ (flip << (t << 3)) : 0xffffffffu;
-}
-__device__ __forceinline__ int local_score(uint32_t lo, int q)
-{
-	uint32_t b, r;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(b) : "r"(lo), "r"(0x000000ffu), "r"((uint32_t)q));   // byte 4 = -1 (N), byte 5 = 0 (padding)
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(0u), "r"(0x8880u));                 // sign-extend byte 0
-	return (int)r;
-}
 
 // One ksw_u8 / ksw_i16 pass (bwa/ksw.c:122-253,255-370) with the query laid out in STRIPS: lane l owns the S
 // consecutive columns [l*S, l*S+S) and keeps their H(i-1,.) and E(i,.) in registers.  A row is then
