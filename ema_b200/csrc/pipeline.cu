@@ -464,9 +464,9 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		int32_t *task_beg = nullptr, *task_n = nullptr;
 		if (c->rescue_plan) {
 			const int task_cap = 4 * n_pairs + 4096;
-			TRY(c->b[25].ensure((size_t)task_cap * sizeof(RescueTask)));
-			TRY(c->b[26].ensure((size_t)n_pairs * 4 * 2));
-			tasks = c->b[25].as<RescueTask>(); task_beg = c->b[26].as<int32_t>(); task_n = task_beg + n_pairs;
+			TRY(c->b[28].ensure((size_t)task_cap * sizeof(RescueTask)));   // slots 25-26 belong to launch_seed
+			TRY(c->b[29].ensure((size_t)n_pairs * 4 * 2));
+			tasks = c->b[28].as<RescueTask>(); task_beg = c->b[29].as<int32_t>(); task_n = task_beg + n_pairs;
 			k_rescue_plan<<<(n_pairs + 127) / 128, 128, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p,
 			                                                    tasks, task_cap, task_beg, task_n, c->d_counters);
 			k_rescue_sw<<<grid, PL_WARPS * 32, 0, st>>>(ix, tasks, task_cap, d_err, c->d_counters);

@@ -71,7 +71,7 @@ struct emab_ctx {
 	bool spin_wait = true;           // EMAB_SYNC=block sleeps on a blocking-sync event instead
 	double last_ms = 0;
 	int last_launches = 0;
-	DevBuf b[28];            // device scratch slots, meaning assigned by each entry point
+	DevBuf b[32];            // device scratch slots, meaning assigned by each entry point
 	HostBuf h[8];            // pinned host result buffers, owned by the ctx and valid until its next call
 	unsigned long long *d_counters = nullptr;  // 16 x u64 instrumentation / work counters
 	int n_sm = 148;
