@@ -142,7 +142,26 @@ def index_load_time(fa, threads):
     return time.time() - t0
 
 
+_RESULT_FD = None
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the process's ORIGINAL stdout (see main())."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there under
+    # torchrun) are sent to stderr for the rest of the run, the result goes to a saved copy of the original fd
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=25)
@@ -175,7 +194,7 @@ def main():
         if rank != 0:
             return
         if not os.path.exists(REF_EMA):
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ema was not built (needs /root/reference at build time)"}))
+            emit(({"impl": "reference", "unavailable": "oracle/_ref/ema was not built (needs /root/reference at build time)"}))
             return
         fa, buckets, ppbk = prepare(args.workload, args.data_dir, args.warmup + args.steps)
         for i in range(args.warmup):
@@ -186,7 +205,7 @@ def main():
         dt = time.time() - t0
         v = args.steps * ppbk / dt
         sample = f"{args.steps} steps x one bucket of {ppbk} pairs per `ema align -s -t {cores}` process (index load included, README workflow)"
-        print(json.dumps({"impl": "reference", "metric": "read pairs/sec (ema align)", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        emit(({"impl": "reference", "metric": "read pairs/sec (ema align)", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
@@ -318,7 +337,7 @@ def main():
             out["cpu_baseline"] = {"value": pairs_per_bucket / t_ref, "unit": "pairs/s", "cores": cores, "kind": "reference",
                                    "sample": f"one bucket of {pairs_per_bucket} pairs, `ema align -s -t {cores}` wall {t_ref:.2f}s incl. index load {t_idx:.2f}s",
                                    "value_excluding_index_load": pairs_per_bucket / max(t_ref - t_idx, 1e-9)}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
