@@ -626,6 +626,7 @@ EMAB_HD int append_candidates(const DevIndex &ix, DP &dp, const ScoreConsts &sc,
 		Aln &r = out[i];
 		reg2aln(ix, dp, len, seq, regs[i], &r);
 		r.keep = 0;
+		r.clip_edit_dist = 0; r.mapq = 0; r.score_mapq = 0; r.em_score = 0;  // defined bytes on the wire for dropped records too (initcheck)
 		const int clip = len - (regs[i].qe - regs[i].qb);
 		r.clip = clip;
 		if (clip >= len / 2) continue;
