@@ -792,7 +792,7 @@ static inline void nt4_bytes(uint8_t *dst, const char *src, size_t n) { if (g_av
 
 // test hook (tests/test_abi.py, no GPU needed): the vector kernels against their scalar definitions on every byte
 // value at every alignment and length up to 300
-int host_selftest()
+static int selftest_bytes()
 {
 	std::vector<char> src(1024), a(1024), b(1024);
 	uint32_t x = 12345;
@@ -1522,6 +1522,110 @@ int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2
 	s->last.parse_ms = t1 - t0;
 	s->last.total_ms += t1 - t0;
 	return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host self-test (emab_host_selftest; runs without a GPU, tests/test_abi.py): the vector byte kernels, the SSE2
+// tokenizer, the integer writer, the inline candidate lists, the output block pool and the bucket parser, each
+// against a plain restatement.  Returns 0, or a code naming the first check that failed.
+// ---------------------------------------------------------------------------------------------
+int host_selftest()
+{
+	if (int rc = selftest_bytes()) return rc;
+	uint32_t x = 2463534242u;
+	auto rnd = [&x]() { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; };
+	{  // token(): copy_until_space semantics on every kind of C-locale whitespace, at every distance from the buffer end
+		const char ws[] = {' ', '\t', '\n', '\v', '\f', '\r'};
+		for (int round = 0; round < 400; ++round) {
+			const size_t n = rnd() % 200;
+			std::string t(n, 'x');
+			for (size_t i = 0; i < n; ++i) { const uint32_t r = rnd(); t[i] = r % 9 == 0 ? ws[r % 6] : (char)(r % 7 == 0 ? (r >> 8) | 0x80 : 33 + (r >> 8) % 90); }
+			const char *p = t.data(), *end = t.data() + n;
+			size_t q = 0;
+			while (p < end) {
+				const std::string_view got = token(p, end);
+				size_t e = q;
+				while (e < n && !(t[e] == ' ' || (t[e] >= '\t' && t[e] <= '\r'))) ++e;
+				if (got.data() != t.data() + q || got.size() != e - q) return 10;
+				q = e < n ? e + 1 : e;
+				if (p != t.data() + q) return 11;
+			}
+		}
+	}
+	{  // put_int against printf
+		const long long vals[] = {0, 1, -1, 9, 10, 99, 100, 4095, -4096, 2147483647LL, -2147483648LL, 9223372036854775807LL, -9223372036854775807LL};
+		char a[32], b[32];
+		for (long long v : vals) { *put_int(a, v) = 0; snprintf(b, sizeof b, "%lld", v); if (strcmp(a, b)) return 20; }
+		for (int i = 0; i < 2000; ++i) { const long long v = (long long)(int32_t)rnd() * (long long)(rnd() % 1000); *put_int(a, v) = 0; snprintf(b, sizeof b, "%lld", v); if (strcmp(a, b)) return 21; }
+	}
+	{  // SmallVec: inline -> heap growth, moves, pops
+		SmallVec<int, 4> v;
+		for (int i = 0; i < 40; ++i) { v.push_back(i * 3); if (v.size() != (size_t)i + 1 || v[i] != i * 3) return 30; }
+		SmallVec<int, 4> w(std::move(v));
+		if (w.size() != 40 || v.size() != 0 || w[39] != 117) return 31;
+		SmallVec<int, 4> u;
+		u.push_back(7); u.push_back(8);
+		SmallVec<int, 4> z(std::move(u));
+		if (z.size() != 2 || z[0] != 7 || z[1] != 8) return 32;
+		z = std::move(w);
+		if (z.size() != 40 || z[20] != 60) return 33;
+		z.pop_back();
+		if (z.size() != 39) return 34;
+	}
+	{  // output blocks: small ones are plain, megabyte ones come back from the pool
+		char *a = text_alloc(100);
+		if (!a) return 40;
+		memset(a, 1, 100);
+		text_free(a);
+		char *b = text_alloc(3u << 20);
+		if (!b) return 41;
+		memset(b, 2, 3u << 20);
+		text_free(b);
+		char *c = text_alloc(2u << 20);   // fits the 3 MB block (cap <= 2n)
+		if (c != b) return 42;
+		text_free(c);
+		char *d = text_alloc(1u << 20);   // 3.4 MB block is more than twice 1 MB: a fresh one
+		if (!d || d == b) return 43;
+		text_free(d);
+	}
+	{  // parse_bucket: stable sort by the 16-character barcode prefix (strncmp order), fields as copy_until_space reads them
+		Session sess;
+		sess.tech = platform_by_name("10x");
+		if (!sess.tech) return 50;
+		sess.bc_len = (int)sess.tech->bc_len;
+		const int n_bc = 23, n_lines = 700;
+		std::vector<std::string> bcs(n_bc);
+		for (auto &bcode : bcs) { bcode.resize(16); for (char &ch : bcode) ch = "ACGT"[rnd() & 3]; }
+		std::string text;
+		std::vector<std::string> want_key(n_lines);
+		struct L { std::string bc, id, r1, q1, r2, q2; };
+		std::vector<L> lines(n_lines);
+		for (int i = 0; i < n_lines; ++i) {
+			L &l = lines[i];
+			l.bc = bcs[rnd() % n_bc];
+			l.id = "@r" + std::to_string(i);
+			auto seq = [&](size_t n) { std::string q(n, 'A'); for (char &ch : q) ch = "ACGTN"[rnd() % 5]; return q; };
+			l.r1 = seq(100 + rnd() % 50); l.q1 = std::string(l.r1.size(), 'I'); l.r2 = seq(120 + rnd() % 30); l.q2 = std::string(l.r2.size(), 'F');
+			text += l.bc + " " + l.id + " " + l.r1 + " " + l.q1 + " " + l.r2 + " " + l.q2 + "\n";
+		}
+		std::vector<int> order(n_lines);
+		for (int i = 0; i < n_lines; ++i) order[i] = i;
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lines[a].bc < lines[b].bc; });
+		for (int nthr : {1, 3, 7}) {
+			std::vector<Pair> pairs;
+			std::string err;
+			if (parse_bucket(&sess, nthr, text.data(), text.size(), pairs, &err) != EMAB_OK) return 51;
+			if ((int)pairs.size() != n_lines) return 52;
+			for (int i = 0; i < n_lines; ++i) {
+				const L &l = lines[order[i]];
+				const Pair &P = pairs[i];
+				uint64_t bc = 0;
+				if (!encode_bc(&sess, l.bc.data(), l.bc.size(), &bc) || P.bc != bc) return 53;
+				if (P.id1 != std::string_view(l.id).substr(1) || P.read[0] != l.r1 || P.qual[0] != l.q1 || P.read[1] != l.r2 || P.qual[1] != l.q2) return 54;
+			}
+		}
+	}
+	return 0;
 }
 
 }  // namespace emab

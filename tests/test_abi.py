@@ -54,8 +54,10 @@ def test_cli_usage_without_gpu():
     assert r.returncode != 0 and "exactly one" in r.stderr
 
 
-def test_host_vector_kernels_selftest():
-    """reverse-complement / reverse / nt4 encoding: the AVX2 paths (picked at run time) against the scalar loops that
+def test_host_selftest():
+    """host logic without a GPU (emab_host_selftest): the SSE2 tokenizer, the bucket parser (stable barcode sort, fields),
+    the integer writer, the inline candidate lists and the output block pool against plain restatements, and
+    reverse-complement / reverse / nt4 encoding: the AVX2 paths (picked at run time) against the scalar loops that
     define them, on every byte value, three alignments and every length up to 300 (emab_host_selftest)"""
     import ema_b200
     assert ema_b200.lib().emab_host_selftest() == 0
