@@ -8,7 +8,7 @@
 
 #define SEED_BLOCK 128
 
-static __global__ void __launch_bounds__(SEED_BLOCK)   // 80 registers, 6 resident blocks per SM; forcing 64 registers (8 blocks) spills and measured 3.9-4.4 ms against 3.2
+static __global__ void __launch_bounds__(SEED_BLOCK)   // 80 registers, 6 resident blocks per SM; forcing 72 or 64 registers (7 or 8 blocks) spills and measured 3.35-4.4 ms against 3.2
 k_seed(DevIndex ix, SeedBatch b)
 {
 	seed_warp(ix, b);
