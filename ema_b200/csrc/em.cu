@@ -173,37 +173,52 @@ extern "C" int emab_em_batch(emab_ctx_t *c, const emab_em_problem_t *h, double *
 	EmProblem P;
 	P.n_bc = nb; P.many_clouds = h->many_clouds; P.log_eps = log(1e-50);
 	DevBuf *b = c->b;
-	TRY(up(c, b[0], h->bc_entry_off, (size_t)(nb + 1) * 4));   P.bc_entry_off = b[0].as<int32_t>();
-	TRY(up(c, b[1], h->bc_cloud_off, (size_t)(nb + 1) * 4));   P.bc_cloud_off = b[1].as<int32_t>();
-	TRY(up(c, b[2], h->bc_group_off, (size_t)(nb + 1) * 4));   P.bc_group_off = b[2].as<int32_t>();
-	TRY(up(c, b[3], h->bc_unit_off, (size_t)(nb + 1) * 4));    P.bc_unit_off = b[3].as<int32_t>();
-	TRY(up(c, b[4], h->bc_full_em, (size_t)nb * 4));           P.bc_full_em = b[4].as<int32_t>();
-	TRY(up(c, b[5], h->entry_cand_off, (size_t)(E + 1) * 4));  P.entry_cand_off = b[5].as<int32_t>();
-	TRY(up(c, b[6], h->entry_mate, (size_t)E * 4));            P.entry_mate = b[6].as<int32_t>();
-	TRY(up(c, b[7], h->cand_score, (size_t)K * 8));            P.cand_score = b[7].as<double>();
-	TRY(up(c, b[8], h->cand_cloud, (size_t)K * 4));            P.cand_cloud = b[8].as<int32_t>();
-	TRY(up(c, b[9], h->cand_chrom, (size_t)K * 4));            P.cand_chrom = b[9].as<int32_t>();
-	TRY(up(c, b[10], h->cand_pos, (size_t)K * 4));             P.cand_pos = b[10].as<uint32_t>();
-	TRY(up(c, b[11], h->cand_flags, (size_t)K));               P.cand_flags = b[11].as<uint8_t>();
-	TRY(up(c, b[12], h->group_off, (size_t)(G + 1) * 4));      P.group_off = b[12].as<int32_t>();
-	TRY(up(c, b[13], h->group_clouds, (size_t)C * 4));         P.group_clouds = b[13].as<int32_t>();
-	TRY(up(c, b[14], h->cloud_contrib_off, (size_t)(C + 1) * 4)); P.cloud_contrib_off = b[14].as<int32_t>();
-	TRY(up(c, b[15], h->cloud_contrib, (size_t)K * 4));        P.cloud_contrib = b[15].as<int32_t>();
-	TRY(up(c, b[16], h->unit_first, (size_t)U * 4));           P.unit_first = b[16].as<int32_t>();
-	TRY(up(c, b[17], h->unit_second, (size_t)U * 4));          P.unit_second = b[17].as<int32_t>();
-	TRY(up(c, b[18], log_n, sizeof log_table.v));                    P.log_n = b[18].as<double>();
+	// The eighteen input arrays travel as ONE block: packed into a pinned staging buffer (256-byte aligned parts) and
+	// copied with one cudaMemcpyAsync — eighteen copies from pageable vectors were eighteen synchronous staging
+	// round trips inside the capped post phase of the host pipeline.
+	struct Part { const void *src; size_t bytes, off; };
+	Part parts[18] = {
+		{h->bc_entry_off, (size_t)(nb + 1) * 4, 0}, {h->bc_cloud_off, (size_t)(nb + 1) * 4, 0}, {h->bc_group_off, (size_t)(nb + 1) * 4, 0},
+		{h->bc_unit_off, (size_t)(nb + 1) * 4, 0}, {h->bc_full_em, (size_t)nb * 4, 0}, {h->entry_cand_off, (size_t)(E + 1) * 4, 0},
+		{h->entry_mate, (size_t)E * 4, 0}, {h->cand_score, (size_t)K * 8, 0}, {h->cand_cloud, (size_t)K * 4, 0}, {h->cand_chrom, (size_t)K * 4, 0},
+		{h->cand_pos, (size_t)K * 4, 0}, {h->cand_flags, (size_t)K, 0}, {h->group_off, (size_t)(G + 1) * 4, 0}, {h->group_clouds, (size_t)C * 4, 0},
+		{h->cloud_contrib_off, (size_t)(C + 1) * 4, 0}, {h->cloud_contrib, (size_t)K * 4, 0}, {h->unit_first, (size_t)U * 4, 0},
+		{h->unit_second, (size_t)U * 4, 0}};
+	size_t total = 0;
+	for (Part &q : parts) { q.off = total; total += (q.bytes + 255) & ~(size_t)255; }
+	TRY(c->h[4].ensure(total + 256));
+	TRY(b[0].ensure(total + 256));
+	for (const Part &q : parts) if (q.bytes) memcpy((char *)c->h[4].p + q.off, q.src, q.bytes);
+	CUDA_TRY(cudaMemcpyAsync(b[0].p, c->h[4].p, total, cudaMemcpyHostToDevice, c->stream));
+	char *d0 = (char *)b[0].p;
+	P.bc_entry_off = (const int32_t *)(d0 + parts[0].off); P.bc_cloud_off = (const int32_t *)(d0 + parts[1].off);
+	P.bc_group_off = (const int32_t *)(d0 + parts[2].off); P.bc_unit_off = (const int32_t *)(d0 + parts[3].off);
+	P.bc_full_em = (const int32_t *)(d0 + parts[4].off); P.entry_cand_off = (const int32_t *)(d0 + parts[5].off);
+	P.entry_mate = (const int32_t *)(d0 + parts[6].off); P.cand_score = (const double *)(d0 + parts[7].off);
+	P.cand_cloud = (const int32_t *)(d0 + parts[8].off); P.cand_chrom = (const int32_t *)(d0 + parts[9].off);
+	P.cand_pos = (const uint32_t *)(d0 + parts[10].off); P.cand_flags = (const uint8_t *)(d0 + parts[11].off);
+	P.group_off = (const int32_t *)(d0 + parts[12].off); P.group_clouds = (const int32_t *)(d0 + parts[13].off);
+	P.cloud_contrib_off = (const int32_t *)(d0 + parts[14].off); P.cloud_contrib = (const int32_t *)(d0 + parts[15].off);
+	P.unit_first = (const int32_t *)(d0 + parts[16].off); P.unit_second = (const int32_t *)(d0 + parts[17].off);
+	if (!c->em_log_ready) {  // the ln(n) table is uploaded once per ctx; slot 30 is nobody else's
+		TRY(up(c, b[30], log_n, sizeof log_table.v));
+		c->em_log_ready = true;
+	}
+	P.log_n = b[30].as<double>();
 	TRY(b[19].ensure((size_t)K * 8));                          P.gamma = b[19].as<double>();
 	TRY(b[20].ensure((size_t)K * 8));                          P.cw = b[20].as<double>();
 	TRY(b[21].ensure((size_t)C * 16 + 16));                    P.exp_cov = b[21].as<double>(); P.weight = P.exp_cov + C;
+	TRY(c->h[5].ensure((size_t)K * 8 + 8));
 	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
 	int blocks = nb;
 	if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
 	k_em<<<blocks, 128, 0, c->stream>>>(P, 5 /* EM_ITERS, include/align.h:52 */, c->d_counters);
 	CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-	CUDA_TRY(cudaMemcpyAsync(gamma_out, P.gamma, (size_t)K * 8, cudaMemcpyDeviceToHost, c->stream));
+	CUDA_TRY(cudaMemcpyAsync(c->h[5].p, P.gamma, (size_t)K * 8, cudaMemcpyDeviceToHost, c->stream));
 	CUDA_TRY(ctx_wait(c));
 	CUDA_TRY(cudaGetLastError());
+	memcpy(gamma_out, c->h[5].p, (size_t)K * 8);
 	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
 	c->last_ms = ms; c->last_launches = 1;
 	return EMAB_OK;

@@ -81,6 +81,7 @@ struct emab_ctx {
 	int sw_mode = 0;         // see emab_set_sw_mode (include/ema_b200.h)
 	bool rescue_plan = true; // mate-rescue alignments planned and run as one balanced batch (pipeline.cu, k_rescue_plan)
 	bool consts_ready = false;
+	bool em_log_ready = false; // emab_em_batch's ln(n) table is resident (slot 30)
 };
 
 // first statement of every entry point that takes a ctx: a worker thread of the host pipeline (or any caller's
