@@ -292,6 +292,10 @@ class Session:
     def set_workers(self, n: int):
         _check(lib().emab_session_workers(self._h, n))
 
+    def add_device(self, device: int):
+        """emab_session_add_device: one more index replica; align_buckets spreads over all of them (call before set_workers)"""
+        _check(lib().emab_session_add_device(self._h, device))
+
     def align_buckets(self, datas, keep_text=True):
         """emab_align_buckets (-x mode): up to `workers` buckets in flight; returns the SAM texts in input
         order (or only their lengths when keep_text is False, which skips the copy into Python objects)."""

@@ -89,6 +89,14 @@ int emab_align_buckets(emab_session_t *h, int n, const char *const *data, const 
 	return EMAB_OK;
 }
 
+int emab_session_add_device(emab_session_t *h, int device)
+{
+	if (!h) return fail(EMAB_ERR_ARG, "null session");
+	int rc = emab::session_add_device(h->s, device);
+	if (rc) return fail(rc, h->s->err);
+	return EMAB_OK;
+}
+
 int emab_session_workers(emab_session_t *h, int n_workers)
 {
 	if (!h) return fail(EMAB_ERR_ARG, "null session");

@@ -208,15 +208,31 @@ PinnedBuf::~PinnedBuf() { if (p) emab_pinned_free(p); }
 // ---------------------------------------------------------------------------------------------
 int session_set_workers(Session *s, int n_workers)
 {
+	const int n_dev = (int)s->replicas.size();
 	if (n_workers < 1) n_workers = 1;
-	if (n_workers > 8) n_workers = 8;
+	if (n_workers > 8 * n_dev) n_workers = 8 * n_dev;
 	while ((int)s->workers.size() > n_workers) { emab_ctx_free(s->workers.back().ctx); s->workers.pop_back(); }
 	while ((int)s->workers.size() < n_workers) {
+		const int slot = (int)s->workers.size() % n_dev;   // round-robin over the index replicas; workers[0] is on the first
 		s->workers.emplace_back();
-		int rc = emab_ctx_create(s->ix, &s->workers.back().ctx);
+		s->workers.back().dev_slot = slot;
+		int rc = emab_ctx_create(s->replicas[slot], &s->workers.back().ctx);
 		if (rc) { s->err = emab_last_error(); s->workers.pop_back(); return rc; }
 		emab_set_error_rate(s->workers.back().ctx, s->tech->error_rate);
 	}
+	return EMAB_OK;
+}
+
+// Replicates the index on another GPU of the box (or, for tests on a one-GPU box, a second time on the same GPU).
+int session_add_device(Session *s, int device)
+{
+	if (s->workers.size() > 1) { s->err = "add devices before setting the number of workers"; return EMAB_ERR_ARG; }
+	emab_index_t *ix = nullptr;
+	int rc = emab_index_load(s->ref_path.c_str(), device, &ix);
+	if (rc) { s->err = emab_last_error(); return rc; }
+	s->replicas.push_back(ix);
+	s->device_ids.push_back(device);
+	s->device_buckets.push_back(0);
 	return EMAB_OK;
 }
 
@@ -242,7 +258,9 @@ int session_open(const char *ref_path, const char *platform, int device, Session
 		}
 		fclose(f);
 	}
+	s->ref_path = ref_path;
 	int rc = emab_index_load(ref_path, device, &s->ix);
+	if (!rc) { s->replicas.push_back(s->ix); s->device_ids.push_back(device); s->device_buckets.push_back(0); }
 	if (rc) { *err = std::string("error: could not load reference at ") + ref_path + ": " + emab_last_error(); delete s; return rc; }
 	rc = session_set_workers(s, 1);
 	if (rc) { *err = s->err; emab_index_free(s->ix); delete s; return rc; }
@@ -269,8 +287,14 @@ void session_close(Session *s)
 {
 	if (!s) return;
 	host_profile_report();
+	if (g_hp_on && s->replicas.size() > 1) {
+		fprintf(stderr, "[emab host profile] buckets per device:");
+		for (size_t d = 0; d < s->replicas.size(); ++d) fprintf(stderr, " cuda:%d=%lld", s->device_ids[d], s->device_buckets[d]);
+		fprintf(stderr, "\n");
+	}
 	for (Worker &w : s->workers) emab_ctx_free(w.ctx);
 	s->workers.clear();
+	for (size_t d = 1; d < s->replicas.size(); ++d) emab_index_free(s->replicas[d]);
 	emab_index_free(s->ix);
 	delete s;
 }
@@ -1386,6 +1410,7 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 	int caps[PH_COUNT] = {3, 3, 3};
 	if (const char *e = getenv("EMAB_GATE_CAPS")) sscanf(e, "%d,%d,%d", &caps[0], &caps[1], &caps[2]);  // tuning knob
 	if (s->apply_opt) caps[PH_POST] = 1;  // -d consumes one rand() stream in bucket order (see process_pairs)
+	caps[PH_DEVICE] *= (int)s->replicas.size();   // the cap is per GPU
 	for (int k = 0; k < PH_COUNT; ++k) s->gate[k].cap = W > 1 ? std::max(1, std::min(caps[k], W)) : 1;
 	const int cap = W > 1 ? std::max(s->gate[PH_PARSE].cap, s->gate[PH_POST].cap) : 1;
 	const int per = std::max(1, s->n_threads / cap);
@@ -1406,6 +1431,7 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 			emab_run_stats_t st;
 			memset(&st, 0, sizeof st);
 			int rc = first_err.load() ? (GatePass(s, tickets[i]).to(PH_POST), s->take_cloud_base(tickets[i], 0), 0) : run_bucket(s, wk, tickets[i], data[i], len[i], &out[i], &out_len[i], st, &errs[w]);
+			{ std::lock_guard<std::mutex> g(s->mu); ++s->device_buckets[wk.dev_slot]; }
 			if (rc) { int z = 0; first_err.compare_exchange_strong(z, rc); if (errs[w].empty()) errs[w] = s->err; }
 			double *a = &sum[w].parse_ms; const double *b = &st.parse_ms;
 			for (int k = 0; k < 16; ++k) a[k] += b[k];

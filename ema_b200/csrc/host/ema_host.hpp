@@ -59,12 +59,20 @@ enum { PH_PARSE = 0, PH_DEVICE = 1, PH_POST = 2, PH_COUNT = 3 };
 
 struct Worker {  // one in-flight bucket: a device context (stream + scratch) and its staging buffers
 	emab_ctx_t *ctx = nullptr;
+	int dev_slot = 0;                     // which of the session's index replicas the ctx lives on
 	PinnedBuf seq, off;
 	int n_threads = 1;
 };
 
 struct Session {  // the reference's process globals (src/main.c:23-34, src/align.c:177-178) as one object
 	emab_index_t *ix = nullptr;
+	// More GPUs in ONE process: the index is replicated on every added device, workers are spread
+	// round-robin over the replicas and take buckets from one shared counter, so a bucket goes to whichever GPU has a
+	// worker free (work stealing); cloud ids and output order stay those of the input order.
+	std::vector<emab_index_t *> replicas;  // replicas[0] == ix
+	std::vector<int> device_ids;
+	std::vector<long long> device_buckets; // buckets each replica has processed (reporting)
+	std::string ref_path;
 	std::vector<Worker> workers;          // buckets in flight (-x mode / emab_align_buckets); workers[0] serves single calls
 	const Platform *tech = nullptr;
 	int bc_len = 16;
@@ -141,6 +149,7 @@ int session_open(const char *ref_path, const char *platform, int device, Session
 void session_close(Session *s);
 void sam_header(const Session *s, int argc, const char *const *argv, std::string *out);
 int session_set_workers(Session *s, int n_workers);
+int session_add_device(Session *s, int device);  // before session_set_workers
 // find_clouds_and_align (src/align.c:214) over the *contents* of the input file(s); SAM text in a malloc'ed buffer
 int align_special_fastq(Session *s, const char *data, size_t len, char **out, size_t *out_len);
 int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2, char **out, size_t *out_len);  // d2 == nullptr: interleaved

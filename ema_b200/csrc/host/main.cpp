@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include "../../../include/ema_b200.h"
 
@@ -78,6 +79,12 @@ int main(int argc, char *argv[])
 	int apply_opt = 0, multi = 0, t = 1, device = 0;
 	int c;
 	if (const char *d = getenv("EMAB_DEVICE")) device = atoi(d);
+	// EMAB_DEVICES=0,1,...: the GPUs -x mode spreads its buckets over (work stealing); the first one serves -s / -1
+	std::vector<int> devices;
+	if (const char *d = getenv("EMAB_DEVICES")) {
+		for (const char *p = d; *p;) { devices.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+		if (!devices.empty()) device = devices[0];
+	}
 	while ((c = getopt(argc - 1, &argv[1], "r:1:2:s:xo:R:dp:i:t:")) != -1) {
 		switch (c) {
 		case 'r': ref = strdup(optarg); break;
@@ -120,7 +127,9 @@ int main(int argc, char *argv[])
 		const int n_inputs = argc - optind - 1;
 		if (n_inputs == 0) { fprintf(stderr, "warning: no input files specified; nothing to do\n"); exit(EXIT_SUCCESS); }
 		// buckets are emitted in argument order; EMAB_WORKERS of them (default 3) are in flight on the GPU
-		int workers = 3;
+		for (size_t d = 1; d < devices.size(); ++d)
+			if (emab_session_add_device(s, devices[d])) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
+		int workers = 3 * (int)std::max<size_t>(1, devices.size());
 		if (const char *w = getenv("EMAB_WORKERS")) workers = atoi(w);
 		emab_session_workers(s, workers);
 		std::vector<std::string> datas(n_inputs);

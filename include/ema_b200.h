@@ -217,6 +217,11 @@ int emab_align_fastq(emab_session_t *s, const char *d1, uint64_t l1, const char 
  * CUDA stream + scratch, so one bucket's kernels overlap another's host work and copies).  sam[i] /
  * sam_len[i] are per bucket, in input order; cloud ids continue in input order. */
 int emab_session_workers(emab_session_t *s, int n_workers);
+/* More GPUs of the box in one process: replicates the index on `device` (call before emab_session_workers).
+ * emab_align_buckets then spreads its workers round-robin over the replicas and every worker takes the next
+ * bucket from one shared counter, i.e. a bucket goes to whichever GPU is free (host-side work
+ * stealing, no collective); outputs and MI cloud ids stay in input order.  Up to 8 workers per device. */
+int emab_session_add_device(emab_session_t *s, int device);
 int emab_align_buckets(emab_session_t *s, int n, const char *const *data, const uint64_t *len, char **sam, uint64_t *sam_len);
 int emab_session_stats(const emab_session_t *s, emab_run_stats_t *out);
 /* test hook: write "ident<TAB>mate<TAB>chrom<TAB>pos<TAB>gamma(%.17g)" of every chosen alignment of later calls to path (NULL = off) */

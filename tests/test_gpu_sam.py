@@ -133,3 +133,38 @@ def test_multi_bucket_pipeline_matches_serial(tmp_path):
     subprocess.run([CLI, "align", "-x", "-r", p["fasta"], "-p", "10x", "-t", "8", "-o", str(out)] + files, check=True)
     _, body = split_sam(out.read_bytes())
     assert b"\n".join(body) + b"\n" == b"".join(serial)
+
+
+def test_multi_device_session_matches_serial(tmp_path):
+    """several index replicas in one process (emab_session_add_device / EMAB_DEVICES): workers on different replicas take
+    buckets from one shared counter (host-side work stealing).  On a one-GPU box the second replica is a
+    second copy on cuda:0 — the same code path; with more GPUs visible the replicas go to different devices.  Output
+    and cloud ids must be those of the serial run."""
+    import torch
+    import ema_b200
+    from tools import synth
+    if not os.path.exists(helpers.ref_bin("bwa")):
+        pytest.skip("oracle/_ref/bwa missing")
+    p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    lines = [l for l in open(p["bucket"], "rb").read().split(b"\n") if l]
+    parts = [b"\n".join(lines[i::6]) + b"\n" for i in range(6)]
+    s1 = ema_b200.Session(p["fasta"], "10x", threads=8)
+    serial = [s1.align_bucket(d) for d in parts]
+    second = 1 if torch.cuda.device_count() > 1 else 0
+    s2 = ema_b200.Session(p["fasta"], "10x", threads=8)
+    s2.add_device(second)
+    s2.set_workers(4)
+    assert s2.align_buckets(parts) == serial
+    assert s2.align_bucket(parts[0])[:200] != b""          # single calls still work after the multi-device run
+    files = []
+    for i, d in enumerate(parts):
+        f = tmp_path / f"b{i}"
+        f.write_bytes(d)
+        files.append(str(f))
+    out = tmp_path / "x.sam"
+    env = dict(os.environ, EMAB_DEVICES=f"0,{second}", EMAB_HOST_PROFILE="1")
+    r = subprocess.run([CLI, "align", "-x", "-r", p["fasta"], "-p", "10x", "-t", "8", "-o", str(out)] + files, check=True, env=env,
+                       capture_output=True, text=True)
+    assert "buckets per device" in r.stderr, r.stderr[-500:]
+    _, body = split_sam(out.read_bytes())
+    assert b"\n".join(body) + b"\n" == b"".join(serial)
