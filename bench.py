@@ -145,6 +145,36 @@ def index_load_time(fa, threads):
 _RESULT_FD = None
 
 
+def sw_microbench(qlen=151, distinct=131072, replicate=8, reps=5, warmup=3, check=2048):
+    """The second half of BASELINE.json's metric, measured live next to the pipeline numbers: ksw_extend2 on `qlen`-bp
+    queries (BASELINE configs[4]: band 100, h0 19, 1 % subst + 0.1 % indels, tlen = qlen + 100) by the thread-per-task
+    kernel, 1 M resident tasks, device time by CUDA events; GCUPS over the DP cells the reference's loop visits
+    (counted by the kernel), 15 integer ops per cell against the integer-pipe peak measured on the spot.
+    bench_sw.py is the full version (three lengths, oracle parity of a sample, CPU baseline)."""
+    import numpy as np
+    import ema_b200
+    ctx = ema_b200.Context(None)
+    ema_b200.set_sw_mode(ctx, 0)
+    peak = max(ema_b200.int_peak(ctx, k, 4000)[0] for k in (0, 5))   # add-class lane-instructions/s (both pipes)
+    q, t = synth.extend_tasks(distinct, qlen)
+    h0 = np.full(distinct, 19, np.int32)
+    # self-consistency only (the oracle is not bench.py's to call outside the CPU baseline: parity of this kernel is
+    # tests/test_gpu_kernels.py and bench_sw.py): the host-buffer batch call and the resident run must agree
+    want, _ = ema_b200.extend_batch(ctx, list(q[:check]), list(t[:check]), h0[:check])
+    n = ema_b200.extend_resident_load(ctx, np.tile(q, (replicate, 1)), np.tile(t, (replicate, 1)), np.tile(h0, replicate))
+    ema_b200.extend_resident_run(ctx, n, reps=warmup, want_out=False)
+    out, vis, ms = ema_b200.extend_resident_run(ctx, n, reps=reps)
+    if not np.array_equal(out[:check], want):
+        raise RuntimeError("resident ksw_extend2 run differs from the batch entry point")
+    gcups = vis / (ms * 1e-3) / 1e9
+    return {"metric": "banded-SW GCUPS (ksw_extend2, thread-per-task kernel)", "qlen": qlen, "tlen": qlen + 100, "w": 100, "tasks": int(n),
+            "ms_per_launch": ms, "visited_cells_per_task": vis / n, "gcups_visited": gcups,
+            "gcups_nominal": float(n) * qlen * (qlen + 100) / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "int-alu", "achieved": gcups * 15, "peak": peak, "unit": "Gop/s", "frac": gcups * 15 / peak, "ops_per_cell": 15,
+                         "peak_source": "measured on this GPU: dependency-free add / add+mad streams on all SMs (emab_int_peak)"},
+            "parity": "bit-exact vs the oracle incl. visited cells: tests/test_gpu_kernels.py, bench_sw.py (profiles/); here batch and resident runs agree"}
+
+
 def emit(obj):
     """The one JSON line of the contract, on the process's ORIGINAL stdout (see main())."""
     line = (json.dumps(obj) + "\n").encode()
@@ -337,6 +367,11 @@ def main():
             out["cpu_baseline"] = {"value": pairs_per_bucket / t_ref, "unit": "pairs/s", "cores": cores, "kind": "reference",
                                    "sample": f"one bucket of {pairs_per_bucket} pairs, `ema align -s -t {cores}` wall {t_ref:.2f}s incl. index load {t_idx:.2f}s",
                                    "value_excluding_index_load": pairs_per_bucket / max(t_ref - t_idx, 1e-9)}
+        if not args.single_only:
+            try:
+                out["sw_microbench"] = sw_microbench()
+            except Exception as e:  # never at the expense of the pipeline line
+                out["sw_microbench"] = {"error": f"{type(e).__name__}: {e}"}
         emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -47,3 +47,6 @@ def test_our_arm_line(tmp_path):
     c = d["cpu_baseline"]
     assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    m = d["sw_microbench"]
+    assert "error" not in m, m
+    assert m["qlen"] == 151 and m["gcups_visited"] > 100 and 0.05 < m["roofline"]["frac"] < 1 and m["roofline"]["bound"] == "int-alu"
