@@ -58,6 +58,24 @@ def _pack(seqs):
     return np.ascontiguousarray(flat), off
 
 
+class IndexBuildStats(C.Structure):
+    _fields_ = [("l_pac", C.c_int64), ("primary", C.c_int64), ("n_seqs", C.c_int32), ("n_holes", C.c_int32), ("chunk_bits", C.c_int32),
+                ("n_chunks", C.c_int32), ("max_chunk", C.c_int64), ("n_tied", C.c_int64), ("max_rounds", C.c_int32), ("pad", C.c_int32),
+                ("ms_pack", C.c_double), ("ms_sort", C.c_double), ("ms_occ", C.c_double), ("ms_write", C.c_double), ("ms_total", C.c_double)]
+
+
+def index_build(fasta: str, prefix: str | None = None, device: int = 0) -> dict:
+    """emab_index_build: `bwa index` on the GPU; writes <prefix>.pac/.ann/.amb/.bwt/.sa and returns the build statistics."""
+    st = IndexBuildStats()
+    _check(lib().emab_index_build(fasta.encode(), prefix.encode() if prefix else None, device, C.byref(st)))
+    return {n: getattr(st, n) for n, _ in IndexBuildStats._fields_ if n != "pad"}
+
+
+def index_pack_fasta(fasta: str, prefix: str | None = None):
+    """emab_index_pack_fasta: the host half of the index build (.pac/.ann/.amb); runs without a GPU."""
+    _check(lib().emab_index_pack_fasta(fasta.encode(), prefix.encode() if prefix else None))
+
+
 class Index:
     """FM index + packed reference resident in one GPU's HBM (emab_index_load)."""
 

@@ -84,7 +84,9 @@ static void tune_malloc()
 {
 	static std::once_flag once;
 	std::call_once(once, [] {
-		if (const char *e = getenv("EMAB_MALLOC_TUNE")) if (atoi(e) == 0) return;
+		// process-wide settings are the application's to choose: opt-in (the CLI and bench.py set EMAB_MALLOC_TUNE=1)
+		const char *e = getenv("EMAB_MALLOC_TUNE");
+		if (!e || atoi(e) == 0) return;
 		mallopt(M_MMAP_THRESHOLD, 32 << 20);
 		mallopt(M_TRIM_THRESHOLD, 1 << 30);
 		mallopt(M_TOP_PAD, 64 << 20);
@@ -202,6 +204,15 @@ int PinnedBuf::ensure(size_t bytes)
 	return 0;
 }
 PinnedBuf::~PinnedBuf() { if (p) emab_pinned_free(p); }
+PinnedBuf &PinnedBuf::operator=(PinnedBuf &&o) noexcept
+{
+	if (this != &o) {
+		if (p) emab_pinned_free(p);
+		p = o.p; cap = o.cap;
+		o.p = nullptr; o.cap = 0;
+	}
+	return *this;
+}
 
 // ---------------------------------------------------------------------------------------------
 // session
@@ -995,14 +1006,14 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	*out_buf = nullptr; *out_len = 0;
 	if (np == 0) { s->take_cloud_base(ticket, 0); *out_buf = text_alloc(1); return EMAB_OK; }
 	// ---- encode and align the whole batch on the device
-	if (wk.off.ensure((2 * np + 1) * 8)) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
+	if (wk.off.ensure((2 * np + 1) * 8)) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
 	int64_t *off = (int64_t *)wk.off.p;
 	off[0] = 0;
 	for (size_t i = 0; i < np; ++i) {
 		off[2 * i + 1] = off[2 * i] + (int64_t)pairs[i].read[0].size();
 		off[2 * i + 2] = off[2 * i + 1] + (int64_t)pairs[i].read[1].size();
 	}
-	if (wk.seq.ensure((size_t)off[2 * np] + 1)) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
+	if (wk.seq.ensure((size_t)off[2 * np] + 1)) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
 	uint8_t *seq = (uint8_t *)wk.seq.p;
 	#pragma omp parallel num_threads(nthr)
 	{
@@ -1021,7 +1032,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	const double t1b = now_ms();
 	{
 		int rc = emab_align_pairs(wk.ctx, (int)np, seq, off, 3, 0, &res, &ds);
-		if (rc) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
+		if (rc) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
 	}
 	const int32_t *n_regs = res.n_regs;
 	const emab_cand_t *alns = res.cands;
@@ -1096,7 +1107,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	}
 	const int E = bc_entry_off[nb], C = bc_cloud_off[nb], G = bc_group_off[nb], U = bc_unit_off[nb];
 	const int64_t K = bc_cand_off[nb];
-	if (K > 0x7fffffff) { s->err = "too many candidates in one batch"; s->take_cloud_base(ticket, 0); return EMAB_ERR_OVERFLOW; }
+	if (K > 0x7fffffff) { wk.err = "too many candidates in one batch"; s->take_cloud_base(ticket, 0); return EMAB_ERR_OVERFLOW; }
 	st.n_cands = K; st.n_clouds = C;
 	std::vector<int32_t> entry_cand_off(E + 1, 0), entry_mate(E), cand_cloud(K), cand_chrom(K), group_off(G + 1, 0), group_clouds(C),
 	    contrib_off(C + 1, 0), contrib(K), unit_first(U), unit_second(U);
@@ -1166,7 +1177,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 		P.group_off = group_off.data(); P.group_clouds = group_clouds.data(); P.cloud_contrib_off = contrib_off.data(); P.cloud_contrib = contrib.data();
 		P.unit_first = unit_first.data(); P.unit_second = unit_second.data();
 		int rc = emab_em_batch(wk.ctx, &P, gamma.data());
-		if (rc) { s->err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
+		if (rc) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
 		st.em_kernel_ms = emab_last_kernel_ms(wk.ctx);
 		st.h2d_bytes += (int64_t)K * 29 + (int64_t)(E + C + G + U + 4 * nb) * 4;
 		st.d2h_bytes += (int64_t)K * 8;
@@ -1215,7 +1226,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	for (int b = 0; b < nb; ++b) soff[b + 1] = soff[b] + bcs[b].sam.size();
 	const size_t total = soff[nb];
 	char *buf = text_alloc(total + 1);
-	if (!buf) { s->err = "out of memory"; return EMAB_ERR_NOMEM; }
+	if (!buf) { wk.err = "out of memory"; return EMAB_ERR_NOMEM; }
 	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 4)
 	for (int b = 0; b < nb; ++b) { HostProf hp(HP_COPY); memcpy(buf + soff[b], bcs[b].sam.data(), bcs[b].sam.size()); }
 	buf[total] = 0;
@@ -1382,7 +1393,7 @@ static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size
 	if (rc) { s->take_cloud_base(ticket, 0); return rc; }
 	const double t1 = now_ms();
 	rc = process_pairs(s, wk, gp, pairs, out, out_len, st);
-	if (rc) *err = s->err;
+	if (rc) *err = wk.err;
 	st.parse_ms = t1 - t0;
 	st.total_ms += t1 - t0;
 	st.gate_wait_ms += t0 - tw;
@@ -1430,9 +1441,13 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 			if (i >= n) break;
 			emab_run_stats_t st;
 			memset(&st, 0, sizeof st);
-			int rc = first_err.load() ? (GatePass(s, tickets[i]).to(PH_POST), s->take_cloud_base(tickets[i], 0), 0) : run_bucket(s, wk, tickets[i], data[i], len[i], &out[i], &out_len[i], st, &errs[w]);
+			int rc = 0;
+			try {  // nothing unwinds out of a worker thread: an allocation failure fails this call, not the process
+				rc = first_err.load() ? (GatePass(s, tickets[i]).to(PH_POST), s->take_cloud_base(tickets[i], 0), 0) : run_bucket(s, wk, tickets[i], data[i], len[i], &out[i], &out_len[i], st, &errs[w]);
+			} catch (const std::bad_alloc &) { rc = EMAB_ERR_NOMEM; errs[w] = "out of host memory"; s->pass_cloud_turn(tickets[i]); }
+			catch (const std::exception &e) { rc = EMAB_ERR_ARG; errs[w] = std::string("internal error: ") + e.what(); s->pass_cloud_turn(tickets[i]); }
 			{ std::lock_guard<std::mutex> g(s->mu); ++s->device_buckets[wk.dev_slot]; }
-			if (rc) { int z = 0; first_err.compare_exchange_strong(z, rc); if (errs[w].empty()) errs[w] = s->err; }
+			if (rc) { int z = 0; first_err.compare_exchange_strong(z, rc); if (errs[w].empty()) errs[w] = "error"; }
 			double *a = &sum[w].parse_ms; const double *b = &st.parse_ms;
 			for (int k = 0; k < 16; ++k) a[k] += b[k];
 			int64_t *ai = &sum[w].h2d_bytes; const int64_t *bi = &st.h2d_bytes;
@@ -1545,6 +1560,7 @@ int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2
 	GatePass gp(s, s->new_ticket());
 	gp.to(PH_PARSE);
 	int rc = process_pairs(s, s->workers[0], gp, pairs, out, out_len, s->last);
+	if (rc) s->err = s->workers[0].err;
 	s->last.parse_ms = t1 - t0;
 	s->last.total_ms += t1 - t0;
 	return rc;

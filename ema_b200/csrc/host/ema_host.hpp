@@ -31,6 +31,12 @@ struct PinnedBuf {  // grow-only pinned host buffer (fast H2D path)
 	void *p = nullptr;
 	size_t cap = 0;
 	int ensure(size_t bytes);
+	PinnedBuf() = default;
+	// owns p: movable (the source is left empty), never copied — Worker objects live in a std::vector that reallocates
+	PinnedBuf(PinnedBuf &&o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+	PinnedBuf &operator=(PinnedBuf &&o) noexcept;
+	PinnedBuf(const PinnedBuf &) = delete;
+	PinnedBuf &operator=(const PinnedBuf &) = delete;
 	~PinnedBuf();
 };
 
@@ -62,6 +68,7 @@ struct Worker {  // one in-flight bucket: a device context (stream + scratch) an
 	int dev_slot = 0;                     // which of the session's index replicas the ctx lives on
 	PinnedBuf seq, off;
 	int n_threads = 1;
+	std::string err;                      // this worker's last error (workers run concurrently: never Session::err)
 };
 
 struct Session {  // the reference's process globals (src/main.c:23-34, src/align.c:177-178) as one object
@@ -111,6 +118,13 @@ struct Session {  // the reference's process globals (src/main.c:23-34, src/alig
 		++cloud_turn;
 		cv.notify_all();
 		return base;
+	}
+	// a ticket that failed before (or after) its turn: make sure the turn is not left waiting for it
+	void pass_cloud_turn(int ticket)
+	{
+		std::unique_lock<std::mutex> g(mu);
+		cv.wait(g, [&] { return cloud_turn >= ticket; });
+		if (cloud_turn == ticket) { ++cloud_turn; cv.notify_all(); }
 	}
 	std::string err;
 	std::string gamma_dump;               // test hook: path for full-precision posteriors of the chosen alignments

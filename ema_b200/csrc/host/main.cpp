@@ -11,20 +11,25 @@
 #include <vector>
 #include "../../../include/ema_b200.h"
 
-static char *escape(char *s)
-{  // src/util.c:22-39
-	char *p, *q;
-	for (p = q = s; *p; ++p) {
-		if (*p == '\\') {
-			++p;
-			if (*p == 't') *q++ = '\t';
-			else if (*p == 'n') *q++ = '\n';
-			else if (*p == 'r') *q++ = '\r';
-			else if (*p == '\\') *q++ = '\\';
-		} else *q++ = *p;
+// -R takes the read group with its tabs written as the two characters `\t` (src/util.c:22-39 expands \t \n \r \\ and
+// drops the backslash of any other pair).  A lone trailing backslash is dropped too.
+static std::string unescape(const char *in)
+{
+	std::string o;
+	for (const char *p = in; *p; ++p) {
+		if (*p != '\\') { o.push_back(*p); continue; }
+		const char c = p[1];
+		if (c == 0) break;
+		++p;
+		switch (c) {
+		case 't': o.push_back('\t'); break;
+		case 'n': o.push_back('\n'); break;
+		case 'r': o.push_back('\r'); break;
+		case '\\': o.push_back('\\'); break;
+		default: break;
+		}
 	}
-	*q = '\0';
-	return s;
+	return o;
 }
 
 static bool slurp(const char *path, std::string *out)
@@ -41,7 +46,7 @@ static bool slurp(const char *path, std::string *out)
 static void usage(const char *argv0, int error)
 {
 	FILE *out = error ? stderr : stdout;
-	fprintf(out, "usage: %s <align|help> [options]\n\n", argv0);
+	fprintf(out, "usage: %s <align|index|help> [options]\n\n", argv0);
 	fprintf(out, "align: choose best alignments based on barcodes\n");
 	fprintf(out, "  -1 <FASTQ1 path>: first (preprocessed and sorted) FASTQ file [none]\n");
 	fprintf(out, "  -2 <FASTQ2 path>: second (preprocessed and sorted) FASTQ file [none]\n");
@@ -55,6 +60,7 @@ static void usage(const char *argv0, int error)
 	fprintf(out, "  -i <index>: index to follow 'BX' tag in SAM output [1]\n");
 	fprintf(out, "  -t <threads>: set number of host threads [1]\n");
 	fprintf(out, "  all other arguments (only for -x): list of all preprocessed inputs\n\n");
+	fprintf(out, "index [-p <prefix>] <FASTA path>: build the BWA index `align -r` loads (= `bwa index`), on the GPU\n\n");
 	fprintf(out, "count / preproc: not part of this build (use the reference's `ema preproc` to make buckets)\n");
 	exit(error ? EXIT_FAILURE : EXIT_SUCCESS);
 }
@@ -70,6 +76,22 @@ int main(int argc, char *argv[])
 	}
 	const char *mode = argv[1];
 	if (strcmp(mode, "help") == 0) usage(argv0, 0);
+	if (strcmp(mode, "index") == 0) {
+		// `ema-b200 index [-p prefix] <ref.fa>`: what `bwa index` does for `ema align -r`, on the GPU (same five files, same bytes)
+		const char *prefix = NULL;
+		int device = 0, c;
+		if (const char *d = getenv("EMAB_DEVICE")) device = atoi(d);
+		while ((c = getopt(argc - 1, &argv[1], "p:")) != -1) {
+			if (c == 'p') prefix = optarg;
+			else usage(argv0, 1);
+		}
+		if (optind + 1 >= argc) { fprintf(stderr, "error: specify the reference FASTA\n"); exit(EXIT_FAILURE); }
+		emab_index_build_stats_t st;
+		if (emab_index_build(argv[optind + 1], prefix, device, &st)) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
+		fprintf(stderr, "[index] %lld bp in %d sequences: pack %.1f s, suffix sort %.1f s (%d chunks, %lld tied suffixes, %d rounds), occ %.1f s, write %.1f s\n",
+		        (long long)st.l_pac, st.n_seqs, st.ms_pack / 1e3, st.ms_sort / 1e3, st.n_chunks, (long long)st.n_tied, st.max_rounds, st.ms_occ / 1e3, st.ms_write / 1e3);
+		return EXIT_SUCCESS;
+	}
 	if (strcmp(mode, "align") != 0) {
 		fprintf(stderr, "error: unrecognized mode\n");
 		usage(argv0, 1);
@@ -93,7 +115,7 @@ int main(int argc, char *argv[])
 		case 's': fqx = strdup(optarg); break;
 		case 'x': multi = 1; break;
 		case 'o': out = strdup(optarg); break;
-		case 'R': rg = escape(strdup(optarg)); break;
+		case 'R': rg = strdup(unescape(optarg).c_str()); break;
 		case 'd': apply_opt = 1; break;
 		case 'p': platform = strdup(optarg); break;
 		case 'i': bx = strdup(optarg); break;
@@ -109,6 +131,7 @@ int main(int argc, char *argv[])
 	if (ref == NULL) { fprintf(stderr, "error: specify reference FASTA with -r\n"); exit(EXIT_FAILURE); }
 	FILE *out_file = out == NULL ? stdout : fopen(out, "w");
 	if (!out_file) IOERROR(out);
+	setenv("EMAB_MALLOC_TUNE", "1", 0);   // keep the per-bucket work buffers in the heap arenas (see tune_malloc in ema_host.cpp)
 	fprintf(stderr, "BWA initialization...\n");
 	emab_session_t *s = NULL;
 	if (emab_session_open(ref, platform, device, &s)) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
@@ -132,17 +155,23 @@ int main(int argc, char *argv[])
 		int workers = 3 * (int)std::max<size_t>(1, devices.size());
 		if (const char *w = getenv("EMAB_WORKERS")) workers = atoi(w);
 		emab_session_workers(s, workers);
-		std::vector<std::string> datas(n_inputs);
-		std::vector<const char *> ptrs(n_inputs);
-		std::vector<uint64_t> lens(n_inputs), olens(n_inputs);
-		std::vector<char *> outs(n_inputs);
-		for (int i = 0; i < n_inputs; ++i) {
-			if (!slurp(argv[optind + 1 + i], &datas[i])) IOERROR(argv[optind + 1 + i]);
-			ptrs[i] = datas[i].data(); lens[i] = datas[i].size();
-			fprintf(stderr, "Processing reads...\n");
+		// a window of 2 x workers buckets is resident at a time: read, align, write and release before the next
+		// window is read, so host memory is bounded by the window whatever the number of inputs
+		const int window = std::max(2, 2 * workers);
+		for (int base = 0; base < n_inputs; base += window) {
+			const int n = std::min(window, n_inputs - base);
+			std::vector<std::string> datas(n);
+			std::vector<const char *> ptrs(n);
+			std::vector<uint64_t> lens(n), olens(n);
+			std::vector<char *> outs(n);
+			for (int i = 0; i < n; ++i) {
+				if (!slurp(argv[optind + 1 + base + i], &datas[i])) IOERROR(argv[optind + 1 + base + i]);
+				ptrs[i] = datas[i].data(); lens[i] = datas[i].size();
+				fprintf(stderr, "Processing reads...\n");
+			}
+			if (emab_align_buckets(s, n, ptrs.data(), lens.data(), outs.data(), olens.data())) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
+			for (int i = 0; i < n; ++i) { fwrite(outs[i], 1, olens[i], out_file); emab_free(outs[i]); }
 		}
-		if (emab_align_buckets(s, n_inputs, ptrs.data(), lens.data(), outs.data(), olens.data())) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
-		for (int i = 0; i < n_inputs; ++i) { fwrite(outs[i], 1, olens[i], out_file); emab_free(outs[i]); }
 	} else if (fqx) {
 		std::string data;
 		if (!slurp(fqx, &data)) IOERROR(fqx);

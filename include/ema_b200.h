@@ -46,6 +46,24 @@ int emab_index_info(const emab_index_t *ix, int64_t info[12]);
 int emab_index_contig(const emab_index_t *ix, int i, int64_t *offset, int32_t *len, char *name, int name_cap);
 double emab_index_build_ms(const emab_index_t *ix); /* device time spent densifying the SA */
 
+/* ---- index construction: replaces `bwa index <fasta>` (bwa/bwtindex.c:255-323 bwa_idx_build =
+ * bns_fasta2bntseq + is_bwt/bwt_bwtgen2 + bwt_bwtupdate_core + bwt_cal_sa), the step `ema align -r` depends on.
+ * Reads the FASTA at fasta_path, sorts the suffixes of forward + reverse complement on `device` and writes
+ * <prefix>.pac/.ann/.amb/.bwt/.sa byte-identical to the reference's (prefix NULL = fasta_path, as `bwa index` does).
+ * Needs about 5 bytes of HBM per base of the reference on top of the chunk buffers (see csrc/indexbuild.cu). */
+typedef struct {
+	int64_t l_pac, primary;
+	int32_t n_seqs, n_holes;
+	int32_t chunk_bits, n_chunks;     /* the key space was cut into 2^chunk_bits chunks, n_chunks of them non-empty */
+	int64_t max_chunk;                /* suffixes in the largest chunk */
+	int64_t n_tied;                   /* suffixes that shared their first 29 bases with another one */
+	int32_t max_rounds, pad;          /* tie-refinement rounds of the slowest chunk */
+	double ms_pack, ms_sort, ms_occ, ms_write, ms_total;  /* FASTA -> pac (host) | suffix sort + BWT/SA emit | Occ | file writes */
+} emab_index_build_stats_t;
+int emab_index_build(const char *fasta_path, const char *prefix, int device, emab_index_build_stats_t *stats);
+/* the host half on its own (= `bwa fa2pac -f`): <prefix>.pac/.ann/.amb only; needs no GPU */
+int emab_index_pack_fasta(const char *fasta_path, const char *prefix);
+
 int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out);  /* ix may be NULL for the sequence-only SW calls */
 void emab_ctx_free(emab_ctx_t *ctx);
 /* Makes the ctx's device current on the calling thread.  Every entry point that takes a ctx does this itself; a

@@ -261,6 +261,10 @@ CONFIGS = {
     "c1_rep":   (5, 1_000_000, 43, 25_000, 200, 50, 0.001),
     "c2":       (10, 10_000_000, 44, 25_000, 5000, 200, 0.001),
     "c2_small": (10, 10_000_000, 44, 25_000, 500, 200, 0.001),
+    # references whose BWT does not fit the 126 MB L2: 1 Gbp, and the hg38-sized 3.1 Gbp of BASELINE configs[2]
+    # (24 contigs; 2 x l_pac > 2^32, so the u64 suffix-array paths are the ones that run)
+    "g1":       (8, 125_000_000, 46, 25_000, 5000, 200, 0.001),
+    "c3":       (24, 129_166_664, 45, 25_000, 100_000, 200, 0.001),
 }
 
 
