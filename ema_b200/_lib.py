@@ -237,7 +237,9 @@ class Stats(C.Structure):
     _fields_ = [("extend_cells", C.c_int64), ("global_cells", C.c_int64), ("local_cells", C.c_int64), ("occ_touches", C.c_int64),
                 ("n_occ", C.c_int64), ("n_regs", C.c_int64), ("kernel_ms", C.c_double), ("ms_seed", C.c_double), ("ms_chain", C.c_double),
                 ("ms_align1", C.c_double), ("ms_rescue", C.c_double), ("ms_finalize", C.c_double), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("launches", C.c_int32), ("pad", C.c_int32), ("rescue_planned_cells", C.c_int64), ("rescue_unplanned", C.c_int64)]
+                ("d2h_bytes", C.c_int64), ("launches", C.c_int32), ("pad", C.c_int32), ("rescue_planned_cells", C.c_int64), ("rescue_unplanned", C.c_int64),
+                ("ext_planned_cells", C.c_int64), ("ext_unplanned", C.c_int64), ("glob_planned_cells", C.c_int64), ("glob_unplanned", C.c_int64),
+                ("ms_ext_wave", C.c_double), ("ms_glob_wave", C.c_double)]
 
 
 class PairsResult(C.Structure):
@@ -275,7 +277,9 @@ class RunStats(C.Structure):
                                           "em_kernel_ms", "format_ms", "total_ms", "ms_seed", "ms_chain", "ms_align1", "ms_rescue",
                                           "ms_finalize", "gate_wait_ms")] + [("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)] + \
                [(n, C.c_int64) for n in ("n_pairs", "n_barcodes", "n_cands", "n_clouds", "sam_bytes", "extend_cells", "global_cells",
-                                         "local_cells", "occ_touches")] + [("launches", C.c_int32), ("pad", C.c_int32)]
+                                         "local_cells", "occ_touches")] + [("launches", C.c_int32), ("pad", C.c_int32)] + \
+               [(n, C.c_int64) for n in ("ext_planned_cells", "ext_unplanned", "glob_planned_cells", "glob_unplanned")] + \
+               [("ms_ext_wave", C.c_double), ("ms_glob_wave", C.c_double)]
 
 
 class Session:

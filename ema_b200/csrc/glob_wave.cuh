@@ -1,0 +1,200 @@
+// Inter-read wave scheduling of mem_reg2aln's ksw_global2 calls (bwa/bwamem.c:1119-1150, bwa/bwa.c:148-234,
+// bwa/ksw.c:540-642): plan, batch, replay — the same shape as ext_wave.cuh and the mate-rescue plan.
+//
+// The first bwa_gen_cigar2 call of a region is a pure function of (read, region): which bases are aligned, in which
+// orientation, with which band.  So before the per-pair kernel walks append_alignments:
+//
+//   k_glob_plan  thread / read   for every region of the read: the first call's arguments -> one GlobTask, or none when
+//                                the call takes the gap-free path (no DP)
+//   (sort, scan)                 tasks ordered by DP size; exact backtrack-matrix offsets
+//   k_glob_wave  thread / task   ksw_global2 + backtrack, 32 similar-sized tasks per warp, DP row {H, E} as two int16 in
+//                                one shared-memory word per column, one direction byte per cell (bwa/ksw.c:587-600)
+//   k_finalize   warp / pair     as before; a ksw_global2 call whose arguments match a task copies its score and CIGAR,
+//                                anything else (a band retry, bwa/bwamem.c:1136-1142) is computed inline
+//
+// int16 is exact here: a DP value is either reachable — then it lies in [-(o + e*rows) - b*cols, a*cols], a few thousand
+// at most — or it is MINUS_INF plus the same small offsets the reference accumulates on top of its -2^30; with
+// MINUS_INF16 = -16384 and offsets below 8 * (rows + cols) < 14000 the two ranges never meet and never wrap, so every
+// comparison, hence every direction byte and the score, is the reference's.
+#pragma once
+#include "align_lanes.cuh"
+
+struct GlobTask {
+	const uint8_t *query;          // the read (null: this region needs no DP or is not planned)
+	int64_t t0;
+	int32_t q0, qlen, tlen, w;
+	int8_t qstep, tstep;
+	int16_t n_cigar;               // result: CIGAR operations (may exceed EMAB_MAX_CIGAR; only the last EMAB_MAX_CIGAR are kept)
+	int32_t score;                 // result
+	uint32_t cells;
+	uint32_t pad;
+};
+#define GLOB_NEG16 (-16384)
+#define GLOB_MAX_DIM 1024          // rows + columns the int16 argument above covers; larger calls stay inline
+
+#ifdef __CUDACC__
+
+// the arguments of reg2aln's first gen_cigar call (align.cuh: reg2aln, gen_cigar); false when it does not reach the DP
+EMAB_HD bool glob_first_call(const DevIndex &ix, int l_query_read, const Reg &ar, int *q0, int *qstep, int *qlen, int64_t *t0, int *tstep, int *tlen, int *w_out)
+{
+	(void)l_query_read;
+	const int qb = ar.qb, qe = ar.qe;
+	const int64_t rb = ar.rb, re = ar.re;
+	int tmp = infer_bw(qe - qb, (int)(re - rb), ar.truesc, opt::a, opt::o_del, opt::e_del);
+	int w2 = infer_bw(qe - qb, (int)(re - rb), ar.truesc, opt::a, opt::o_ins, opt::e_ins);
+	w2 = w2 > tmp ? w2 : tmp;
+	if (w2 > opt::w) w2 = w2 < ar.w ? w2 : ar.w;
+	w2 = w2 < opt::w << 2 ? w2 : opt::w << 2;
+	const int l_query = qe - qb;
+	if (l_query <= 0 || rb >= re || (rb < ix.l_pac && re > ix.l_pac)) return false;
+	const int rlen = (int)(re - rb);
+	if (l_query == rlen && w2 == 0) return false;   // gap-free: no DP
+	const bool rev = rb >= ix.l_pac;
+	*q0 = rev ? qb + l_query - 1 : qb; *qstep = rev ? -1 : 1; *qlen = l_query;
+	*t0 = rev ? re - 1 : rb; *tstep = rev ? -1 : 1; *tlen = rlen;
+	int max_ins = (int)((double)(((l_query + 1) >> 1) * opt::a - opt::o_ins) / opt::e_ins + 1.);
+	int max_del = (int)((double)(((l_query + 1) >> 1) * opt::a - opt::o_del) / opt::e_del + 1.);
+	int max_gap = max_ins > max_del ? max_ins : max_del;
+	max_gap = max_gap > 1 ? max_gap : 1;
+	int dl = rlen - l_query; dl = dl < 0 ? -dl : dl;
+	int w = (max_gap + dl + 1) >> 1;
+	w = w < w2 ? w : w2;
+	const int min_w = dl + 3;
+	w = w > min_w ? w : min_w;
+	*w_out = w;
+	return true;
+}
+
+template <class Pools_>
+__global__ void __launch_bounds__(128)
+k_glob_plan(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools_ p, int rescue_room, const int32_t *aln_off,
+            GlobTask *tasks, uint16_t *keys, unsigned long long *zsize)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const Reg *regs = p.regs + (occ_off[r] + (size_t)rescue_room * r);
+	const int n = p.n_regs[r], l_query = (int)(off[r + 1] - off[r]);
+	for (int i = 0; i < n; ++i) {
+		const int slot = aln_off[r] + i;
+		GlobTask &t = tasks[slot];
+		int q0, qstep, qlen, tstep, tlen, w;
+		int64_t t0;
+		t.query = nullptr; t.n_cigar = 0; t.score = 0; t.cells = 0; t.pad = 0;
+		keys[slot] = 0; zsize[slot] = 0;
+		if (!glob_first_call(ix, l_query, regs[i], &q0, &qstep, &qlen, &t0, &tstep, &tlen, &w)) continue;
+		if (qlen + tlen > GLOB_MAX_DIM || qlen > EMAB_MAX_READ_LEN) continue;
+		t.query = seq + off[r]; t.t0 = t0; t.q0 = q0; t.qlen = qlen; t.tlen = tlen; t.w = w; t.qstep = (int8_t)qstep; t.tstep = (int8_t)tstep;
+		const int ncol = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+		const unsigned long long z = (unsigned long long)ncol * tlen;
+		zsize[slot] = z;
+		const unsigned long long k = (z >> 4) + 1;
+		keys[slot] = (uint16_t)(k > 65535 ? 65535 : k);
+	}
+}
+
+// ksw_global2 (bwa/ksw.c:540-622) + backtrack (:624-638) of one task per thread
+__global__ void __launch_bounds__(32)
+k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, const unsigned long long *zoff, uint8_t *zpool,
+            uint32_t *cigars, unsigned long long *planned_cells)
+{
+	extern __shared__ uint32_t glob_smem[];
+	const int lane = threadIdx.x, ti = blockIdx.x * 32 + lane;
+	const bool valid = ti < n_tasks && keys_sorted[ti] != 0;
+	if (!__any_sync(FULL_MASK, valid)) return;
+	unsigned long long cells = 0;
+	if (valid) {
+		const int slot = order[ti];
+		GlobTask &t = tasks[slot];
+		uint32_t *he = glob_smem + lane;          // column j at he[j * 32]: {H(i-1, j-1) : lo16, E(i, j) : hi16}
+		uint8_t *z = zpool + zoff[slot];
+		const uint8_t *query = t.query;
+		const int qlen = t.qlen, tlen = t.tlen, w = t.w, q0 = t.q0, qstep = t.qstep, tstep = t.tstep;
+		const int64_t t0 = t.t0;
+		constexpr int e_del = opt::e_del, e_ins = opt::e_ins, oe_del = opt::oe_del, oe_ins = opt::oe_ins;
+		const int ncol = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+		for (int j = 0; j <= qlen; ++j) {
+			const int h = j == 0 ? 0 : (j <= w ? -(opt::o_ins + e_ins * j) : GLOB_NEG16);
+			he[j * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h & 0xffffu);
+		}
+		for (int i = 0; i < tlen; ++i) {
+			const int tb = ref_base(ix, t0 + (int64_t)i * tstep);
+			const int beg = i > w ? i - w : 0;
+			const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+			int h1 = beg == 0 ? -(opt::o_del + e_del * (i + 1)) : GLOB_NEG16, f = GLOB_NEG16;
+			uint8_t *zr = z + (size_t)i * ncol - beg;
+			if (end > beg) cells += end - beg;
+			for (int j = beg; j < end; ++j) {
+				const uint32_t wv = he[j * 32];
+				const int qb = query[q0 + j * qstep];
+				const int M = (int)(short)(wv & 0xffffu) + sc_mat(tb, qb);
+				int e = (int)wv >> 16;
+				int d = M >= e ? 0 : 1;
+				int h = M >= e ? M : e;
+				d = h >= f ? d : 2;
+				h = h >= f ? h : f;
+				int tt = M - oe_del;
+				e -= e_del;
+				d |= e > tt ? 1 << 2 : 0;
+				e = e > tt ? e : tt;
+				he[j * 32] = ((uint32_t)e << 16) | ((uint32_t)h1 & 0xffffu);
+				h1 = h;
+				tt = M - oe_ins;
+				f -= e_ins;
+				d |= f > tt ? 2 << 4 : 0;
+				f = f > tt ? f : tt;
+				zr[j] = (uint8_t)d;
+			}
+			he[end * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h1 & 0xffffu);
+		}
+		t.score = (int)(short)(he[qlen * 32] & 0xffffu);
+		t.cells = (uint32_t)cells;
+		// backtrack: operations are met last to first and written back to front, so the kept ones are in forward order at
+		// the end of the task's EMAB_MAX_CIGAR slots
+		uint32_t *cg = cigars + (size_t)slot * EMAB_MAX_CIGAR;
+		int n = 0, state = 0, i = tlen - 1;
+		int k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+		uint32_t cur = 0;
+		auto push = [&](int op, int len) {
+			if (cur && (int)(cur & 0xf) == op) cur += (uint32_t)len << 4;
+			else {
+				if (cur) { if (n < EMAB_MAX_CIGAR) cg[EMAB_MAX_CIGAR - 1 - n] = cur; ++n; }
+				cur = (uint32_t)len << 4 | (uint32_t)op;
+			}
+		};
+		while (i >= 0 && k >= 0) {
+			const int lo = i > w ? i - w : 0;
+			state = z[(size_t)i * ncol + (k - lo)] >> (state << 1) & 3;
+			if (state == 0) { push(0, 1); --i; --k; }
+			else if (state == 1) { push(2, 1); --i; }
+			else { push(1, 1); --k; }
+		}
+		if (i >= 0) push(2, i + 1);
+		if (k >= 0) push(1, k + 1);
+		if (cur) { if (n < EMAB_MAX_CIGAR) cg[EMAB_MAX_CIGAR - 1 - n] = cur; ++n; }
+		t.n_cigar = (int16_t)(n > 32767 ? 32767 : n);
+	}
+	for (int d = 16; d; d >>= 1) cells += __shfl_xor_sync(FULL_MASK, cells, d);
+	if (lane == 0 && cells) atomicAdd(planned_cells, cells);
+}
+
+// a ksw_global2 call of the replay against the read's tasks; on a hit copies the CIGAR (if wanted) and returns true
+__device__ __forceinline__ bool glob_plan_lookup(const GlobTask *tasks, const uint32_t *cigars, int n_tasks, const uint8_t *query, int q0, int qstep, int qlen,
+                                                 int64_t t0, int tlen, int w, uint32_t *cigar, int *n_cigar, int *score, uint32_t *cells)
+{
+	for (int k = 0; k < n_tasks; ++k) {
+		const GlobTask &t = tasks[k];
+		if (t.query != query || t.q0 != q0 || t.qstep != qstep || t.qlen != qlen || t.t0 != t0 || t.tlen != tlen || t.w != w) continue;
+		*score = t.score; *cells = t.cells;
+		if (cigar) {
+			const int n = t.n_cigar, ns = n < EMAB_MAX_CIGAR ? n : EMAB_MAX_CIGAR;
+			const uint32_t *cg = cigars + (size_t)k * EMAB_MAX_CIGAR + (EMAB_MAX_CIGAR - ns);
+			for (int a = threadIdx.x & 31; a < ns; a += 32) cigar[a] = cg[a];
+			__syncwarp();
+			*n_cigar = n;
+		}
+		return true;
+	}
+	return false;
+}
+
+#endif

@@ -160,5 +160,10 @@ int emab_session_dump_posteriors(emab_session_t *h, const char *path)
 emab_ctx_t *emab_session_ctx(emab_session_t *h) { return h ? h->s->workers[0].ctx : nullptr; }
 void emab_free(void *p) { emab::text_free(p); }
 int emab_host_selftest(void) { return emab::host_selftest(); }
+void emab_abi_sizes(int32_t out[4])
+{
+	out[0] = (int32_t)sizeof(emab_cand_t); out[1] = (int32_t)sizeof(emab_stats_t); out[2] = (int32_t)sizeof(emab_run_stats_t);
+	out[3] = (int32_t)sizeof(emab_index_build_stats_t);
+}
 
 }  // extern "C"

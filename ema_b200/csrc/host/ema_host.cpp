@@ -1044,6 +1044,8 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	st.ms_seed = ds.ms_seed; st.ms_chain = ds.ms_chain; st.ms_align1 = ds.ms_align1; st.ms_rescue = ds.ms_rescue; st.ms_finalize = ds.ms_finalize;
 	st.h2d_bytes = ds.h2d_bytes; st.d2h_bytes = ds.d2h_bytes;
 	st.extend_cells = ds.extend_cells; st.global_cells = ds.global_cells; st.local_cells = ds.local_cells; st.occ_touches = ds.occ_touches;
+	st.ext_planned_cells = ds.ext_planned_cells; st.ext_unplanned = ds.ext_unplanned; st.glob_planned_cells = ds.glob_planned_cells;
+	st.glob_unplanned = ds.glob_unplanned; st.ms_ext_wave = ds.ms_ext_wave; st.ms_glob_wave = ds.ms_glob_wave;
 	std::vector<int64_t> aoff(2 * np + 1, 0);
 	for (size_t i = 0; i < 2 * np; ++i) aoff[i + 1] = aoff[i] + n_regs[i];
 	// ---- barcode groups (consecutive pairs with one barcode)
@@ -1453,6 +1455,9 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 			int64_t *ai = &sum[w].h2d_bytes; const int64_t *bi = &st.h2d_bytes;
 			for (int k = 0; k < 11; ++k) ai[k] += bi[k];
 			sum[w].launches += st.launches;
+			sum[w].ext_planned_cells += st.ext_planned_cells; sum[w].ext_unplanned += st.ext_unplanned;
+			sum[w].glob_planned_cells += st.glob_planned_cells; sum[w].glob_unplanned += st.glob_unplanned;
+			sum[w].ms_ext_wave += st.ms_ext_wave; sum[w].ms_glob_wave += st.ms_glob_wave;
 		}
 	};
 	std::vector<std::thread> th;
@@ -1466,6 +1471,9 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 		int64_t *ai = &s->last.h2d_bytes; const int64_t *bi = &sum[w].h2d_bytes;
 		for (int k = 0; k < 11; ++k) ai[k] += bi[k];
 		s->last.launches += sum[w].launches;
+		s->last.ext_planned_cells += sum[w].ext_planned_cells; s->last.ext_unplanned += sum[w].ext_unplanned;
+		s->last.glob_planned_cells += sum[w].glob_planned_cells; s->last.glob_unplanned += sum[w].glob_unplanned;
+		s->last.ms_ext_wave += sum[w].ms_ext_wave; s->last.ms_glob_wave += sum[w].ms_glob_wave;
 	}
 	s->last.total_ms = now_ms() - t0;
 	if (first_err.load()) {

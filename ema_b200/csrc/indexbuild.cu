@@ -253,9 +253,9 @@ __global__ void k_interleave(const uint32_t *words, uint64_t n, uint64_t n_block
 {
 	const uint64_t n_words = (n + 15) >> 4;
 	for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b <= n_blocks; b += (uint64_t)gridDim.x * blockDim.x) {
-		if (b == n_blocks) {  // "the last element"
-			unsigned long long *o = (unsigned long long *)(out + n_words + 8 * n_blocks);
-			o[0] = totals[0]; o[1] = totals[1]; o[2] = totals[2]; o[3] = totals[3];
+		if (b == n_blocks) {  // "the last element"; n_words may be odd, so the u64 totals are stored as u32 halves
+			uint32_t *o = out + n_words + 8 * n_blocks;
+			for (int k = 0; k < 4; ++k) { o[2 * k] = (uint32_t)totals[k]; o[2 * k + 1] = (uint32_t)(totals[k] >> 32); }
 			continue;
 		}
 		uint32_t *o = out + 16 * b;

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include "../../include/ema_b200.h"
 #include "runtime.cuh"
 #include "seed_launch.cuh"
@@ -21,6 +22,8 @@
 #include "ksw_warp.cuh"
 #include "align.cuh"
 #include "align_lanes.cuh"
+#include "ext_wave.cuh"
+#include "glob_wave.cuh"
 
 #define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 #define PL_WARPS 8
@@ -125,6 +128,52 @@ struct WarpPolicy {
 	__device__ __noinline__ LocResult local_unplanned(const uint8_t *ms, int l_ms, int64_t rb, int tlen) { return local(ms, l_ms, rb, tlen); }
 };
 
+// k_align1's policy when the bucket's extensions were run ahead (ext_wave.cuh): ksw_extend2 is answered from the
+// read's plans when the arguments match, computed inline otherwise
+struct PlannedExtPolicy : WarpPolicy {
+	const ExtPlan *plans = nullptr;
+	int n_plans = 0;
+	__device__ PlannedExtPolicy(const WarpPolicy &b) : WarpPolicy(b) {}
+	__device__ ExtResult extend(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, int end_bonus, int h0)
+	{
+		ExtResult r;
+		uint32_t cells;
+		if (ext_plan_lookup(plans, n_plans, q0, qstep, qlen, t0, tlen, w, h0, &r, &cells)) {
+			if ((threadIdx.x & 31) == 0 && cells) atomicAdd(&counters[0], (unsigned long long)cells);
+			return r;
+		}
+		if ((threadIdx.x & 31) == 0) atomicAdd(&counters[13], 1ull);
+		return extend_unplanned(query, q0, qstep, qlen, t0, tstep, tlen, w, end_bonus, h0);
+	}
+	__device__ __noinline__ ExtResult extend_unplanned(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, int end_bonus, int h0)
+	{
+		return WarpPolicy::extend(query, q0, qstep, qlen, t0, tstep, tlen, w, end_bonus, h0);
+	}
+};
+
+// k_finalize's policy when the bucket's first ksw_global2 calls were run ahead (glob_wave.cuh)
+struct PlannedGlobPolicy : WarpPolicy {
+	const GlobTask *gtasks = nullptr;
+	const uint32_t *gcigars = nullptr;
+	int n_gtasks = 0;
+	__device__ PlannedGlobPolicy(const WarpPolicy &b) : WarpPolicy(b) {}
+	__device__ int global(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, uint32_t *cigar, int *n_cigar)
+	{
+		int score;
+		uint32_t cells;
+		if (glob_plan_lookup(gtasks, gcigars, n_gtasks, query, q0, qstep, qlen, t0, tlen, w, cigar, n_cigar, &score, &cells)) {
+			if ((threadIdx.x & 31) == 0 && cells) atomicAdd(&counters[3], (unsigned long long)cells);
+			return score;
+		}
+		if ((threadIdx.x & 31) == 0) atomicAdd(&counters[15], 1ull);
+		return global_unplanned(query, q0, qstep, qlen, t0, tstep, tlen, w, cigar, n_cigar);
+	}
+	__device__ __noinline__ int global_unplanned(const uint8_t *query, int q0, int qstep, int qlen, int64_t t0, int tstep, int tlen, int w, uint32_t *cigar, int *n_cigar)
+	{
+		return WarpPolicy::global(query, q0, qstep, qlen, t0, tstep, tlen, w, cigar, n_cigar);
+	}
+};
+
 // the replay's policy: mem_matesw's ksw_align2 goes through the cache, everything else is WarpPolicy
 struct ReplayPolicy : WarpPolicy {
 	__device__ ReplayPolicy(const WarpPolicy &b) : WarpPolicy(b) {}
@@ -165,20 +214,27 @@ k_chain(DevIndex ix, int n_reads, const int64_t *off, const Intv *intv, const in
 
 __global__ void __launch_bounds__(PL_WARPS * 32)
 k_align1(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p,
-         uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
+         uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters, const ExtPlan *plans, const int32_t *chain_off)
 {
 	__shared__ WarpDP sm_all[PL_WARPS];
 	const int lane = threadIdx.x & 31, gw = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
-	WarpPolicy dp{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err};
+	PlannedExtPolicy dp(WarpPolicy{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err});
 	for (;;) {
 		const int r = next_item(&counters[5], lane);
 		if (r >= n_reads) break;
 		const int o = occ_off[r];
 		Reg *regs = p.regs + (o + (size_t)RESCUE_ROOM * r);
+		if (plans) { dp.plans = plans + chain_off[r]; dp.n_plans = p.n_chains[r]; }
 		const int n = align1_from_chains(ix, dp, (int)(off[r + 1] - off[r]), seq + off[r], p.chains + o, p.n_chains[r], p.seeds + o, p.srt + o, regs);
 		p.n_regs[r] = n;
 		__syncwarp();
 	}
+}
+
+__global__ void k_iota2(int n, int32_t *a, int32_t *b)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { a[i] = i; b[i] = i; }
 }
 
 // mem_align1_core with one thread per read (align_lanes.cuh): one-warp blocks, dynamic shared memory =
@@ -296,11 +352,12 @@ k_rescue(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, const
 
 __global__ void __launch_bounds__(PL_WARPS * 32)
 k_finalize(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p, const int32_t *aln_off,
-           Aln *alns, const ScoreConsts *sc, uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters)
+           Aln *alns, const ScoreConsts *sc, uint8_t *zbuf, size_t z_cap, uint32_t *tmpbuf, int *err, unsigned long long *counters,
+           const GlobTask *gtasks, const uint32_t *gcigars)
 {
 	__shared__ WarpDP sm_all[PL_WARPS];
 	const int lane = threadIdx.x & 31, gw = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
-	WarpPolicy dp{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err};
+	PlannedGlobPolicy dp(WarpPolicy{ix, sm_all[threadIdx.x >> 5], counters, zbuf + (size_t)gw * z_cap, z_cap, tmpbuf + (size_t)gw * EMAB_MAX_CIGAR, err});
 	for (;;) {
 		const int pr = next_item(&counters[7], lane);
 		if (pr >= n_pairs) break;
@@ -308,10 +365,17 @@ k_finalize(DevIndex ix, int n_pairs, const uint8_t *seq, const int64_t *off, con
 		for (int m = 0; m < 2; ++m) {
 			const int r = 2 * pr + m;
 			const Reg *regs = p.regs + (occ_off[r] + (size_t)RESCUE_ROOM * r);
+			if (gtasks) { dp.gtasks = gtasks + aln_off[r]; dp.gcigars = gcigars + (size_t)aln_off[r] * EMAB_MAX_CIGAR; dp.n_gtasks = p.n_regs[r]; }
 			append_candidates(ix, dp, *sc, (int)(off[r + 1] - off[r]), seq + off[r], regs, p.n_regs[r], alns + aln_off[r], &best_dist);
 		}
 		__syncwarp();
 	}
+}
+
+__global__ void k_iota1(int n, int32_t *a)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) a[i] = i;
 }
 
 // candidates -> compact wire records + a CIGAR pool (most CIGARs have 1-3 ops; the device-side record reserves 64)
@@ -410,7 +474,8 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 128, st));
 	CUDA_TRY(cudaMemsetAsync(d_occ_cnt, 0, (size_t)(R + 1) * 4, st));
 	int launches = 0;
-	if (!c->stage_ev[0]) for (int i = 0; i < 8; ++i) CUDA_TRY(cudaEventCreate(&c->stage_ev[i]));
+	bool ext_waves_ran = false, glob_waves_ran = false;
+	if (!c->stage_ev[0]) for (int i = 0; i < 16; ++i) CUDA_TRY(cudaEventCreate(&c->stage_ev[i]));
 	CUDA_TRY(cudaEventRecord(c->ev0, st));
 	CUDA_TRY(cudaEventRecord(c->stage_ev[0], st));
 	TRY(launch_seed(c, R, max_len, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), EMAB_MAX_INTV, c->b[3].as<int32_t>(), d_occ_cnt, d_err,
@@ -454,9 +519,48 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		int lgrid = c->n_sm * per_sm;
 		if (lgrid > (R + 31) / 32) lgrid = (R + 31) / 32;
 		k_align1_lanes<<<lgrid, 32, smem, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, d_err, c->d_counters);
-	} else
-	k_align1<<<grid, PL_WARPS * 32, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
-	                                          c->b[17].as<uint32_t>(), d_err, c->d_counters);
+	} else {
+		const ExtPlan *d_plans = nullptr;
+		const int32_t *d_chain_off = nullptr;
+		if (c->ext_plan) {
+			// every chain's top-seed extensions ahead of the per-read control flow: plan, two waves (ext_wave.cuh)
+			TRY(c->b[32].ensure((size_t)(R + 1) * 4));
+			int32_t *chain_off = c->b[32].as<int32_t>();
+			cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, p.n_chains, chain_off, R + 1, st);
+			TRY(c->b[6].ensure(tmp_bytes + 16));
+			cub::DeviceScan::ExclusiveSum(c->b[6].p, tmp_bytes, p.n_chains, chain_off, R + 1, st);
+			int32_t NCH = 0;
+			CUDA_TRY(cudaMemcpyAsync(&NCH, chain_off + R, 4, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(ctx_wait(c));
+			++launches;
+			if (NCH > 0) {
+				TRY(c->b[33].ensure((size_t)NCH * sizeof(ExtPlan)));
+				TRY(c->b[34].ensure((size_t)NCH * 4 + 64));           // lkey, rkey, and their sorted copies
+				TRY(c->b[35].ensure((size_t)NCH * 4 * 4 + 64));       // iota x2, order_l, order_r
+				ExtPlan *plans = c->b[33].as<ExtPlan>();
+				uint8_t *lkey = c->b[34].as<uint8_t>(), *rkey = lkey + NCH, *lkey_s = rkey + NCH, *rkey_s = lkey_s + NCH;
+				int32_t *iota_l = c->b[35].as<int32_t>(), *iota_r = iota_l + NCH, *order_l = iota_r + NCH, *order_r = order_l + NCH;
+				k_ext_plan<Pools><<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[1].as<int64_t>(), d_occ_off, p, chain_off, plans, lkey, rkey);
+				k_iota2<<<(NCH + 255) / 256, 256, 0, st>>>(NCH, iota_l, iota_r);
+				size_t sb = 0;
+				cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, lkey, lkey_s, iota_l, order_l, NCH, 0, 8, st);
+				TRY(c->b[6].ensure(sb + 16));
+				cub::DeviceRadixSort::SortPairsDescending(c->b[6].p, sb, lkey, lkey_s, iota_l, order_l, NCH, 0, 8, st);
+				cub::DeviceRadixSort::SortPairsDescending(c->b[6].p, sb, rkey, rkey_s, iota_r, order_r, NCH, 0, 8, st);
+				const size_t smem = lanes::smem_per_warp(max_len);
+				CUDA_TRY(cudaFuncSetAttribute(k_ext_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+				CUDA_TRY(cudaFuncSetAttribute(k_ext_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+				CUDA_TRY(cudaEventRecord(c->stage_ev[8], st));
+				k_ext_wave<false><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_l, lkey_s, NCH, &c->d_counters[12]);
+				k_ext_wave<true><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_r, rkey_s, NCH, &c->d_counters[12]);
+				CUDA_TRY(cudaEventRecord(c->stage_ev[9], st));
+				launches += 6;
+				d_plans = plans; d_chain_off = chain_off; ext_waves_ran = true;
+			}
+		}
+		k_align1<<<grid, PL_WARPS * 32, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
+		                                          c->b[17].as<uint32_t>(), d_err, c->d_counters, d_plans, d_chain_off);
+	}
 	launches += 2;
 	CUDA_TRY(cudaEventRecord(c->stage_ev[4], st));
 	if (stage >= 2) {
@@ -489,8 +593,43 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	CUDA_TRY(cudaEventRecord(c->stage_ev[6], st));
 	if (stage >= 3) {
 		TRY(c->b[18].ensure(((size_t)A + 1) * sizeof(Aln)));
+		const GlobTask *d_gtasks = nullptr;
+		const uint32_t *d_gcigars = nullptr;
+		if (c->glob_plan && A > 0) {
+			// the first ksw_global2 of every region ahead of the per-pair control flow (glob_wave.cuh)
+			TRY(c->b[36].ensure((size_t)A * sizeof(GlobTask)));
+			TRY(c->b[37].ensure((size_t)A * 2 * 2 + (size_t)A * 4 * 2 + 64));      // keys, sorted keys | iota, order
+			TRY(c->b[38].ensure(((size_t)A + 1) * 8 * 2));                           // zsize, zoff
+			TRY(c->b[39].ensure((size_t)A * EMAB_MAX_CIGAR * 4));
+			GlobTask *gt = c->b[36].as<GlobTask>();
+			int32_t *g_iota = c->b[37].as<int32_t>(), *g_order = g_iota + A;
+			uint16_t *g_keys = (uint16_t *)(g_order + A), *g_keys_s = g_keys + A;
+			unsigned long long *zsize = c->b[38].as<unsigned long long>(), *zoff = zsize + (A + 1);
+			CUDA_TRY(cudaMemsetAsync(zsize + A, 0, 8, st));
+			k_glob_plan<Pools><<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, RESCUE_ROOM, d_aln_off, gt, g_keys, zsize);
+			k_iota1<<<(A + 255) / 256, 256, 0, st>>>(A, g_iota);
+			size_t sb = 0;
+			cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, g_keys, g_keys_s, g_iota, g_order, A, 0, 16, st);
+			TRY(c->b[6].ensure(sb + 16));
+			cub::DeviceRadixSort::SortPairsDescending(c->b[6].p, sb, g_keys, g_keys_s, g_iota, g_order, A, 0, 16, st);
+			cub::DeviceScan::ExclusiveSum(nullptr, sb, zsize, zoff, A + 1, st);
+			TRY(c->b[6].ensure(sb + 16));
+			cub::DeviceScan::ExclusiveSum(c->b[6].p, sb, zsize, zoff, A + 1, st);
+			unsigned long long Z = 0;
+			CUDA_TRY(cudaMemcpyAsync(&Z, zoff + A, 8, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(ctx_wait(c));
+			TRY(c->b[40].ensure((size_t)Z + 16));
+			const size_t smem = lanes::smem_per_warp(max_len);
+			CUDA_TRY(cudaFuncSetAttribute(k_glob_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+			CUDA_TRY(cudaEventRecord(c->stage_ev[10], st));
+			k_glob_wave<<<(A + 31) / 32, 32, smem, st>>>(ix, gt, g_order, g_keys_s, A, zoff, c->b[40].as<uint8_t>(), c->b[39].as<uint32_t>(), &c->d_counters[14]);
+			CUDA_TRY(cudaEventRecord(c->stage_ev[11], st));
+			launches += 5;
+			d_gtasks = gt; d_gcigars = c->b[39].as<uint32_t>(); glob_waves_ran = true;
+		}
 		k_finalize<<<grid, PL_WARPS * 32, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, d_aln_off, c->b[18].as<Aln>(),
-		                                            c->b[23].as<ScoreConsts>(), c->b[16].as<uint8_t>(), z_cap, c->b[17].as<uint32_t>(), d_err, c->d_counters);
+		                                            c->b[23].as<ScoreConsts>(), c->b[16].as<uint8_t>(), z_cap, c->b[17].as<uint32_t>(), d_err, c->d_counters,
+		                                            d_gtasks, d_gcigars);
 		++launches;
 		// compact wire format: 56-byte records + CIGAR pool
 		TRY(c->b[20].ensure(((size_t)A + 2) * 4 * 2));
@@ -538,6 +677,10 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	if (stats) {
 		stats->extend_cells = (int64_t)cnt[0]; stats->occ_touches = (int64_t)cnt[2]; stats->global_cells = (int64_t)cnt[3];
 		stats->rescue_planned_cells = (int64_t)cnt[10]; stats->rescue_unplanned = (int64_t)cnt[11];
+		stats->ext_planned_cells = (int64_t)cnt[12]; stats->ext_unplanned = (int64_t)cnt[13];
+		stats->glob_planned_cells = (int64_t)cnt[14]; stats->glob_unplanned = (int64_t)cnt[15];
+		if (ext_waves_ran) { float tw; cudaEventElapsedTime(&tw, c->stage_ev[8], c->stage_ev[9]); stats->ms_ext_wave = tw; }
+		if (glob_waves_ran) { float tw; cudaEventElapsedTime(&tw, c->stage_ev[10], c->stage_ev[11]); stats->ms_glob_wave = tw; }
 		stats->local_cells = (int64_t)cnt[4]; stats->n_occ = T; stats->n_regs = A; stats->kernel_ms = ms; stats->launches = launches;
 		float t;
 		cudaEventElapsedTime(&t, c->stage_ev[0], c->stage_ev[1]); stats->ms_seed = t;

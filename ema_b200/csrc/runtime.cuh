@@ -66,12 +66,12 @@ struct emab_ctx {
 	int device = 0;          // every entry point makes it current first: callers may be threads that never chose a device
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	cudaEvent_t stage_ev[8] = {};
+	cudaEvent_t stage_ev[16] = {};
 	cudaEvent_t ev_wait = nullptr;   // cudaEventBlockingSync: see ctx_wait()
 	bool spin_wait = true;           // EMAB_SYNC=block sleeps on a blocking-sync event instead
 	double last_ms = 0;
 	int last_launches = 0;
-	DevBuf b[32];            // device scratch slots, meaning assigned by each entry point
+	DevBuf b[48];            // device scratch slots, meaning assigned by each entry point
 	HostBuf h[8];            // pinned host result buffers, owned by the ctx and valid until its next call
 	unsigned long long *d_counters = nullptr;  // 16 x u64 instrumentation / work counters
 	int n_sm = 148;
@@ -80,6 +80,8 @@ struct emab_ctx {
 	int res_n = 0, res_qcap = 0;
 	int sw_mode = 0;         // see emab_set_sw_mode (include/ema_b200.h)
 	bool rescue_plan = true; // mate-rescue alignments planned and run as one balanced batch (pipeline.cu, k_rescue_plan)
+	bool ext_plan = true;    // ksw_extend2 calls of every chain's top seed run ahead as two bucket-wide waves (ext_wave.cuh)
+	bool glob_plan = true;   // ksw_global2 calls of mem_reg2aln likewise (glob_wave.cuh)
 	bool consts_ready = false;
 	bool em_log_ready = false; // emab_em_batch's ln(n) table is resident (slot 30)
 };

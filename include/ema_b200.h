@@ -164,6 +164,10 @@ typedef struct {
 	int32_t pad;
 	int64_t rescue_planned_cells;                     /* local-SW cells computed ahead of the rescue replay (>= local_cells' share of them) */
 	int64_t rescue_unplanned;                         /* mem_matesw alignments the plan did not foresee (computed inline by the replay) */
+	/* the two planned waves (csrc/ext_wave.cuh, csrc/glob_wave.cuh): cells computed ahead by the thread-per-task kernels,
+	 * calls the per-read replay had to compute inline, and the waves' device time (part of ms_align1 / ms_finalize) */
+	int64_t ext_planned_cells, ext_unplanned, glob_planned_cells, glob_unplanned;
+	double ms_ext_wave, ms_glob_wave;
 } emab_stats_t;
 
 int emab_set_error_rate(emab_ctx_t *ctx, double eps);  /* platform error_rate (src/techs.c:71-127); default 0.001 */
@@ -223,6 +227,8 @@ typedef struct {
 	int64_t n_pairs, n_barcodes, n_cands, n_clouds, sam_bytes;
 	int64_t extend_cells, global_cells, local_cells, occ_touches;
 	int32_t launches, pad;
+	int64_t ext_planned_cells, ext_unplanned, glob_planned_cells, glob_unplanned;
+	double ms_ext_wave, ms_glob_wave;
 } emab_run_stats_t;
 
 int emab_session_open(const char *ref_path, const char *platform, int device, emab_session_t **out);
@@ -246,6 +252,7 @@ int emab_session_stats(const emab_session_t *s, emab_run_stats_t *out);
 int emab_session_dump_posteriors(emab_session_t *s, const char *path);
 emab_ctx_t *emab_session_ctx(emab_session_t *s);
 void emab_free(void *p);
+void emab_abi_sizes(int32_t out[4]);  /* sizeof emab_cand_t, emab_stats_t, emab_run_stats_t, emab_index_build_stats_t: lets a binding check its mirror */
 int emab_host_selftest(void);  /* host-side vector byte kernels checked against their scalar definitions; 0 = ok (no GPU needed) */
 
 #ifdef __cplusplus

@@ -28,8 +28,9 @@ def test_wire_struct_sizes():
     import ema_b200
     from ema_b200 import _lib
     assert _lib.CAND_DTYPE.itemsize == 56
-    assert C.sizeof(_lib.RunStats) == 16 * 8 + 11 * 8 + 8
-    assert C.sizeof(_lib.Stats) == 6 * 8 + 6 * 8 + 2 * 8 + 8 + 2 * 8
+    sizes = (C.c_int32 * 4)()
+    ema_b200.lib().emab_abi_sizes(sizes)   # the C side's sizeof: the ctypes mirrors must agree with the header as compiled
+    assert list(sizes) == [56, C.sizeof(_lib.Stats), C.sizeof(_lib.RunStats), C.sizeof(_lib.IndexBuildStats)]
 
 
 def test_no_cpu_fallback():

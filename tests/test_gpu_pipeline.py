@@ -181,3 +181,32 @@ def test_rescue_plan_is_transparent(emab, monkeypatch):
         n_sw = max(1, sb.local_cells // 60000)  # ~ number of ksw_align2 calls
         assert sb.rescue_unplanned * 10 <= n_sw, f"the plan should foresee nearly every alignment ({sb.rescue_unplanned} of ~{n_sw} were not)"
         print(f"rescue plan: {sb.rescue_planned_cells} cells planned, {sb.local_cells} consumed, {sb.rescue_unplanned} alignments unplanned")
+
+
+def test_wave_plans_are_transparent(emab, monkeypatch):
+    """ksw_extend2 / ksw_global2 run ahead as bucket-wide thread-per-task waves (ext_wave.cuh, glob_wave.cuh) and replayed by the
+    per-read control flow must give what the inline warp-per-task path gives: candidates, regions per read, and the
+    DP cells the reference's loops visit — on the golden bucket and on the repeat/indel variant of BASELINE configs[0]."""
+    from tools import synth
+    cases = [(os.path.join(G, "tiny_rep", "ref.fa"), helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x")))]
+    if os.path.exists(helpers.ref_bin("bwa")):
+        p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+        cases.append((p["fasta"], helpers.read_bucket(p["bucket"])))
+    for pre, lines in cases:
+        ix = emab.Index(pre)
+        monkeypatch.setenv("EMAB_EXT_PLAN", "0")
+        monkeypatch.setenv("EMAB_GLOB_PLAN", "0")
+        ctx0 = emab.Context(ix)
+        monkeypatch.delenv("EMAB_EXT_PLAN")
+        monkeypatch.delenv("EMAB_GLOB_PLAN")
+        ctx1 = emab.Context(ix)
+        a, ra = pipeline_candidates(emab, ctx0, lines)
+        b, rb = pipeline_candidates(emab, ctx1, lines)
+        assert a == b
+        assert np.array_equal(ra["n_regs"], rb["n_regs"])
+        sa, sb = ra["stats"], rb["stats"]
+        assert sa.extend_cells == sb.extend_cells and sa.extend_cells > 0
+        assert sa.global_cells == sb.global_cells
+        assert sa.ext_planned_cells == 0 and sb.ext_planned_cells > 0
+        print(f"ext plan: {sb.ext_planned_cells} cells planned, {sb.extend_cells} consumed, {sb.ext_unplanned} extensions inline; "
+              f"glob plan: {sb.glob_planned_cells} planned, {sb.global_cells} consumed, {sb.glob_unplanned} inline")

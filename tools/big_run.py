@@ -48,7 +48,7 @@ def main():
     ap.add_argument("--buckets", type=int, default=2)
     ap.add_argument("--data-dir", default=os.environ.get("EMAB_DATA", "/tmp/emab_data"))
     ap.add_argument("--density", action="store_true", help="-d (density optimisation) under the pinned clock")
-    ap.add_argument("--ref-threads", type=int, default=0, help="threads of the reference run (0 = all cores; -d runs use 1)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="threads of the reference run (0 = 1: with more, the reference's MI cloud ids depend on scheduling)")
     ap.add_argument("--no-reference", action="store_true")
     args = ap.parse_args()
     import numpy as np
@@ -97,7 +97,7 @@ def main():
              "ms_seed": st.ms_seed, "ms_chain": st.ms_chain, "ms_align1": st.ms_align1, "ms_rescue": st.ms_rescue, "ms_finalize": st.ms_finalize,
              "occ_touches": st.occ_touches, "seed_GBps": st.occ_touches * 64 / (st.ms_seed * 1e-3) / 1e9}
         if not args.no_reference and os.path.exists(REF_EMA):
-            thr = args.ref_threads or cores
+            thr = args.ref_threads or 1   # MI cloud ids are scheduling-dependent in the reference with -t > 1
             o = os.path.join(d, "ref_out.sam")
             t0 = time.time()
             subprocess.run([REF_EMA, "align", "-s", p, "-r", fa, "-p", "10x", "-t", str(thr), "-o", o],
