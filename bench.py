@@ -38,10 +38,14 @@ from tools import synth  # noqa: E402
 
 REF_EMA = os.path.join(ROOT, "oracle", "_ref", "ema")
 REF_BWA = os.path.join(ROOT, "oracle", "_ref", "bwa")
+MAX_BUCKETS = 40   # distinct synthetic buckets per run; steps beyond that cycle through them
 
 WORKLOADS = {
     # name: (synth reference config, n_buckets, barcodes per bucket, pairs per barcode, description)
-    "c2": ("c2", 25, 200, 200, "synthetic 100 Mbp reference (10x10 Mbp, planted duplications), 1M read pairs across 5k barcodes, -p 10x"),
+    "c3": ("c3", 500, 200, 200, "BASELINE configs[2] shape: synthetic 3.1 Gbp (hg38-sized, 24 contigs, planted duplications) reference, "
+                                "40 000-pair buckets of 200 barcodes out of 20M pairs / 500 buckets, -p 10x; BWT 3.1 GB + u64 dense SA 49.6 GB per GPU"),
+    "g1": ("g1", 25, 200, 200, "synthetic 1 Gbp reference (8 contigs, planted duplications), 40 000-pair buckets of 200 barcodes, -p 10x"),
+    "c2": ("c2", 25, 200, 200, "BASELINE configs[1]: synthetic 100 Mbp reference (10x10 Mbp, planted duplications), 1M read pairs across 5k barcodes, -p 10x"),
     "c1_rep": ("c1_rep", 4, 200, 50, "synthetic 5 Mbp reference with planted duplications, 10k-pair buckets of 200 barcodes, -p 10x"),
     "c1": ("c1", 4, 200, 50, "synthetic 5 Mbp iid reference, 10k-pair buckets of 200 barcodes, -p 10x"),
 }
@@ -64,10 +68,15 @@ def prepare(workload, data_root, need_buckets):
         contigs = synth.make_reference(n_contigs, clen, rseed, dup)
         synth.write_fasta(fa, contigs)
     if not os.path.exists(fa + ".sa"):
-        if not os.path.exists(REF_BWA):
-            raise SystemExit("oracle/_ref/bwa is missing: the FM index is built with the reference's own `bwa index`")
-        log(f"[bench] bwa index {fa} ...")
-        subprocess.run([REF_BWA, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        if n_contigs * clen > 200_000_000 or not os.path.exists(REF_BWA):
+            # `bwa index` is about an hour of one core at 3.1 Gbp; emab_index_build writes the same five files (byte-identical
+            # to the reference's wherever both were run: tests/test_index_build.py) in seconds.  Both arms load this index.
+            import ema_b200
+            st = ema_b200.index_build(fa)
+            log(f"[bench] emab_index_build {fa}: {st['ms_total'] / 1e3:.1f}s")
+        else:
+            log(f"[bench] bwa index {fa} ...")
+            subprocess.run([REF_BWA, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     buckets = []
     for b in range(min(need_buckets, n_buckets)):
         path = os.path.join(d, f"ema-bin-{b:03d}")
@@ -175,6 +184,23 @@ def sw_microbench(qlen=151, distinct=131072, replicate=8, reps=5, warmup=3, chec
             "parity": "bit-exact vs the oracle incl. visited cells: tests/test_gpu_kernels.py, bench_sw.py (profiles/); here batch and resident runs agree"}
 
 
+def sw_section(agg, K):
+    """In-pipeline banded SW, per kernel: DP cells the reference's loops visit / the device time of the kernels that compute them.
+    ops_per_cell as in SURVEY.md 8d (15 for ksw_extend2, 17 for ksw_global2, 14 for ksw_align2); the peak is measured by
+    sw_microbench in the same line."""
+    def gcups(cells, ms):
+        return cells / K / (max(ms / K, 1e-9) * 1e-3) / 1e9
+    return {
+        "extend_cells_per_step": agg["extend_cells"] / K, "global_cells_per_step": agg["global_cells"] / K, "local_cells_per_step": agg["local_cells"] / K,
+        "extend_planned_cells_per_step": agg["ext_planned_cells"] / K, "extend_calls_inline_per_step": agg["ext_unplanned"] / K,
+        "global_planned_cells_per_step": agg["glob_planned_cells"] / K, "global_calls_inline_per_step": agg["glob_unplanned"] / K,
+        "extend_wave_gcups": gcups(agg["ext_planned_cells"], agg["ms_ext_wave"]), "extend_stage_gcups": gcups(agg["extend_cells"], agg["ms_align1"]),
+        "global_wave_gcups": gcups(agg["glob_planned_cells"], agg["ms_glob_wave"]), "global_stage_gcups": gcups(agg["global_cells"], agg["ms_finalize"]),
+        "local_stage_gcups": gcups(agg["local_cells"], agg["ms_rescue"]),
+        "note": "wave = the thread-per-task kernels alone (CUDA events around them); stage = the whole k_align1 / k_finalize / rescue stage incl. plan, sort and replay",
+    }
+
+
 def emit(obj):
     """The one JSON line of the contract, on the process's ORIGINAL stdout (see main())."""
     line = (json.dumps(obj) + "\n").encode()
@@ -197,7 +223,7 @@ def main():
     ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("EMAB_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--data-dir", default=os.environ.get("EMAB_DATA", "/tmp/emab_data"))
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
     ap.add_argument("--workers", type=int, default=8, help="buckets in flight per GPU in the end-to-end pass")
@@ -213,9 +239,14 @@ def main():
     threads = args.threads or max(1, cores // world)
     cfg, n_buckets, nbc, ppb, desc = WORKLOADS[args.workload]
     pairs_per_bucket = nbc * ppb
-    config = {"workload": f"BASELINE configs[1]: {desc}" if args.workload == "c2" else desc,
+    n_contigs_, clen_ = synth.CONFIGS[cfg][0], synth.CONFIGS[cfg][1]
+    big = n_contigs_ * clen_ > 200_000_000
+    config = {"workload": desc, "reference_bp": n_contigs_ * clen_,
               "bucket_pairs": pairs_per_bucket, "barcodes_per_bucket": nbc, "platform": "10x",
-              "l2_policy": "inputs larger than L2: the FM index + dense SA are ~1.3 GB and every step is a different bucket",
+              "index_built_by": ("emab_index_build (GPU suffix sort; files byte-identical to `bwa index` where both ran: tests/test_index_build.py); "
+                                 "both arms load it") if big else "the reference's own `bwa index`",
+              "l2_policy": "inputs larger than L2: the BWT alone is %.1f GB, the dense SA %.1f GB; every step is a different bucket"
+                           % (n_contigs_ * clen_ * 1e-9, n_contigs_ * clen_ * 2 * (8 if n_contigs_ * clen_ * 2 >= 2 ** 32 else 4) * 1e-9),
               "host_threads_per_rank": threads,
               "timed_passes": "A: K buckets one at a time (device-time value, roofline); B: the same K buckets end to end with several in flight (e2e, ms_per_step)"}
 
@@ -226,19 +257,34 @@ def main():
         if not os.path.exists(REF_EMA):
             emit(({"impl": "reference", "unavailable": "oracle/_ref/ema was not built (needs /root/reference at build time)"}))
             return
-        fa, buckets, ppbk = prepare(args.workload, args.data_dir, args.warmup + args.steps)
-        for i in range(args.warmup):
+        fa, buckets, ppbk = prepare(args.workload, args.data_dir, min(args.warmup + args.steps, MAX_BUCKETS))
+        timed = [buckets[(args.warmup + i) % len(buckets)] for i in range(args.steps)]
+        # (a) the README workflow: one `ema align -s -t <cores>` process per bucket (each loads the index)
+        for i in range(min(args.warmup, 2)):
             time_reference(fa, buckets[i % len(buckets)], cores)
+        n_a = min(args.steps, 6)
         t0 = time.time()
-        for i in range(args.steps):
-            time_reference(fa, buckets[(args.warmup + i) % len(buckets)], cores)
-        dt = time.time() - t0
-        v = args.steps * ppbk / dt
-        sample = f"{args.steps} steps x one bucket of {ppbk} pairs per `ema align -s -t {cores}` process (index load included, README workflow)"
+        for b in timed[:n_a]:
+            time_reference(fa, b, cores)
+        per_bucket = (time.time() - t0) / n_a
+        # (b) one process for all K buckets: `ema align -x -t <cores>` (index loaded once, one thread per bucket file)
+        out = "/dev/shm/emab_ref_out.sam" if os.path.isdir("/dev/shm") else "/tmp/emab_ref_out.sam"
+        t0 = time.time()
+        subprocess.run([REF_EMA, "align", "-x", "-r", fa, "-p", "10x", "-t", str(cores), "-o", out] + timed, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        multi = time.time() - t0
+        t_idx = index_load_time(fa, cores)
+        v_a, v_b = ppbk / per_bucket, args.steps * ppbk / multi
+        v, how = (v_a, "a") if v_a >= v_b else (v_b, "b")
+        dt = args.steps * ppbk / v
+        sample = (f"the better of (a) one `ema align -s -t {cores}` process per bucket of {ppbk} pairs ({n_a} buckets timed: {v_a:.0f} pairs/s) and "
+                  f"(b) one `ema align -x -t {cores}` process over the {args.steps} buckets ({v_b:.0f} pairs/s); the line's value is ({how}); "
+                  f"index load {t_idx:.2f}s per process is inside both")
         emit(({"impl": "reference", "metric": "read pairs/sec (ema align)", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample,
+                                           "per_bucket_process_pairs_per_s": v_a, "one_process_pairs_per_s": v_b, "index_load_s": t_idx},
                           "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -259,7 +305,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    need = (args.warmup + args.steps) * world
+    need = min((args.warmup + args.steps) * world, MAX_BUCKETS)
     if rank == 0:
         fa, buckets, _ = prepare(args.workload, args.data_dir, min(need, n_buckets))
     barrier()
@@ -301,7 +347,8 @@ def main():
         st = sess.stats
         kern_ms += st.kernel_ms + st.em_kernel_ms
         launches += st.launches
-        for k in ("ms_seed", "ms_chain", "ms_align1", "ms_rescue", "ms_finalize", "em_kernel_ms", "parse_ms", "encode_ms", "align_ms",
+        for k in ("ms_seed", "ms_chain", "ms_align1", "ms_rescue", "ms_finalize", "em_kernel_ms", "ms_ext_wave", "ms_glob_wave",
+                  "ext_planned_cells", "ext_unplanned", "glob_planned_cells", "glob_unplanned", "parse_ms", "encode_ms", "align_ms",
                   "cloud_ms", "flatten_ms", "em_ms", "format_ms", "total_ms", "occ_touches", "extend_cells", "global_cells", "local_cells",
                   "h2d_bytes", "d2h_bytes", "sam_bytes"):
             agg[k] = agg.get(k, 0) + getattr(st, k)
@@ -331,10 +378,14 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None   # dram bytes per k_seed launch from the committed `ncu --set full` capture of this workload
+        # DRAM bytes per k_seed launch: not measurable inside a timed run; taken from the committed `ncu --set full` capture
+        # of this workload (profiles/ncu_traffic.json, written by tools/ncu_digest.py from the .ncu-rep of the same command)
+        traffic, traffic_src = None, None
         try:
-            if args.workload == "c2":
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_seed"]["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if args.workload in tj:
+                traffic = tj[args.workload]["k_seed"]["dram_bytes_per_launch"]
+                traffic_src = "committed ncu capture: " + tj[args.workload]["k_seed"].get("source", "profiles/")
         except Exception:
             pass
         seed_bytes = agg["occ_touches"] * 64.0 / K
@@ -351,14 +402,13 @@ def main():
             "gpu_launches": launches + launches_e2e,
             "clocks": clocks,
             "roofline": {"kernel": "k_seed (SMEM seeding, mem_collect_intv)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": seed_bytes, "ms_per_launch": seed_ms},
-            "device_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain", "ms_align1", "ms_rescue", "ms_finalize", "em_kernel_ms")},
+            "device_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain", "ms_align1", "ms_rescue", "ms_finalize", "em_kernel_ms",
+                                                              "ms_ext_wave", "ms_glob_wave")},
             "host_ms_per_step": {k: agg[k] / K for k in ("parse_ms", "encode_ms", "align_ms", "cloud_ms", "flatten_ms", "em_ms", "format_ms", "total_ms")},
-            "sw": {"extend_cells_per_step": agg["extend_cells"] / K, "global_cells_per_step": agg["global_cells"] / K,
-                   "local_cells_per_step": agg["local_cells"] / K,
-                   "gcups_in_pipeline": (agg["extend_cells"] + agg["global_cells"]) / K / (max(ext_ms, 1e-9) * 1e-3) / 1e9},
+            "sw": sw_section(agg, K),
         }
         if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_EMA):
             b = buckets[0]

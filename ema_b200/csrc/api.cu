@@ -84,6 +84,7 @@ extern "C" int emab_index_load(const char *prefix, int device, emab_index_t **ou
 	const uint64_t *sw = (const uint64_t *)sa.data();
 	if (sw[0] != ix->d.primary || sw[6] != ix->d.seq_len) { snprintf(emab_errbuf, sizeof emab_errbuf, "SA-BWT inconsistency"); delete ix; return EMAB_ERR_IO; }
 	ix->d.sa_intv = (int)sw[5];
+	{ const char *e = getenv("EMAB_SEED_LOAD_BOTH"); ix->d.seed_load_both = e ? atoi(e) != 0 : 0; }
 	ix->n_sa = (ix->d.seq_len + ix->d.sa_intv) / ix->d.sa_intv;
 	if ((ix->d.sa_intv & (ix->d.sa_intv - 1)) || sa.size() < 56 + (ix->n_sa - 1) * 8) { snprintf(emab_errbuf, sizeof emab_errbuf, "bad .sa file"); delete ix; return EMAB_ERR_IO; }
 	{  // .ann (bwa/bntseq.c:109-137)

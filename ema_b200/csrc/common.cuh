@@ -71,6 +71,7 @@ struct DevIndex {
 	int n_seqs;
 	const int64_t *ann_offset;   // n_seqs
 	const int32_t *ann_len;      // n_seqs
+	int seed_load_both;          // tuning/measurement knob (EMAB_SEED_LOAD_BOTH=1): bwt_2occ4 requests its second block even when it is the first
 };
 
 struct Intv {  // bwtintv_t (bwa/bwt.h:62-64)

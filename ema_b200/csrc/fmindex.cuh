@@ -82,10 +82,24 @@ EMAB_HD void block_occ4(const OccBlock &o, int idx, uint64_t cnt[4])
 	cnt[3] = ((uint64_t)o.c1.w << 32 | o.c1.z) + nt;
 }
 
+// 128-bit load issued only when `pred` holds; otherwise r keeps the value it came in with.  A predicated-off lane
+// issues no memory request at all: no sector, no L1 wavefront.
+EMAB_HD void ldg128_if(bool pred, const uint4 *p, uint4 &r)
+{
+#ifdef __CUDA_ARCH__
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+	             : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w) : "l"(p), "r"((unsigned)pred));
+#else
+	if (pred) r = *p;
+#endif
+}
+
 // bwt_2occ4(k, l): two positions (bwa/bwt.c:189-220).  Branch-free: with one thread per read the lanes of a
 // warp disagree on "k and l share a block", and a branch here made the warp run both arms of the ~200-instruction
-// counting code every step (ncu, profiles/r1b_ncu_summary_c2.md).  Both blocks are always loaded — the second
-// load of a shared block coalesces with the first in L1 — and both positions always counted.
+// counting code every step (ncu, profiles/r1b_ncu_summary_c2.md).  Both positions are always counted, but the
+// second block is REQUESTED only by the lanes whose l lies in another block than k (predicated loads): once an
+// interval is narrow — most steps of a read — k and l share a block, and with one read per lane every request is a
+// wavefront of its own in the L1 pipe, the unit this kernel runs out of first (profiles/r2*_ncu_seed*.md).
 // fm.touches counts 64-byte block loads as the reference would issue them (the roofline unit of
 // SURVEY.md §8d): one when k and l share a block, none for a position equal to (bwtint_t)-1.
 EMAB_HD void bwt_2occ4(Fm &fm, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t cl[4])
@@ -97,9 +111,12 @@ EMAB_HD void bwt_2occ4(Fm &fm, uint64_t k, uint64_t l, uint64_t ck[4], uint64_t 
 	const uint4 *pk = fm.ix.bwt + (bk << 2), *pl = fm.ix.bwt + (bl << 2);
 	OccBlock a, b;
 	a.c0 = ldg128(pk); a.c1 = ldg128(pk + 1); a.b0 = ldg128(pk + 2); a.b1 = ldg128(pk + 3);
-	b.c0 = ldg128(pl); b.c1 = ldg128(pl + 1); b.b0 = ldg128(pl + 2); b.b1 = ldg128(pl + 3);
+	const bool other = bk != bl || fm.ix.seed_load_both;
+	b.c0 = b.c1 = b.b0 = b.b1 = make_uint4(0, 0, 0, 0);
+	ldg128_if(other, pl, b.c0); ldg128_if(other, pl + 1, b.c1); ldg128_if(other, pl + 2, b.b0); ldg128_if(other, pl + 3, b.b1);
 	fm.touches += (unsigned)kv + (unsigned)(lv && !(kv && bk == bl));
 	block_occ4(a, (int)(_k & 127), ck);
+	if (!other) b = a;
 	block_occ4(b, (int)(_l & 127), cl);
 #pragma unroll
 	for (int i = 0; i < 4; ++i) {

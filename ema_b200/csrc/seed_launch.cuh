@@ -8,7 +8,10 @@
 
 #define SEED_BLOCK 128
 
-static __global__ void __launch_bounds__(SEED_BLOCK)   // 80 registers, 6 resident blocks per SM; forcing 72 or 64 registers (7 or 8 blocks) spills and measured 3.35-4.4 ms against 3.2
+// Two register budgets of the same kernel: 6 resident blocks per SM (80 registers, a few spilled words since the
+// predicated second Occ-block load) and 5 (no spills).  EMAB_SEED_BPS picks the grid and with it the variant.
+template <int MIN_BLOCKS>
+static __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS)
 k_seed(DevIndex ix, SeedBatch b)
 {
 	seed_warp(ix, b);
@@ -62,7 +65,8 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
 	b.n12 = (int32_t *)(b.queue + 2); b.n3 = b.n12 + R;
 	b.err = d_err; b.touches = d_touches;
 	CUDA_TRY(cudaMemsetAsync(b.queue, 0, 16, st));
-	k_seed<<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
+	if (seed_blocks_per_sm() >= 6) k_seed<6><<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
+	else k_seed<5><<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
 	k_seed_finish<<<(R + 127) / 128, 128, 0, st>>>(b, d_n_intv, d_occ_cnt);
 	*launches += 2;
 	return EMAB_OK;
