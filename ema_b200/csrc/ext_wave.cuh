@@ -69,11 +69,15 @@ k_ext_plan(DevIndex ix, int n_reads, const int64_t *off, const int32_t *occ_off,
 template <bool RIGHT>
 __global__ void __launch_bounds__(32)
 k_ext_wave(DevIndex ix, const uint8_t *seq, const int64_t *off, ExtPlan *plans, const int32_t *order, const uint8_t *keys_sorted, int n_tasks,
-           unsigned long long *planned_cells)
+           unsigned long long *planned_cells, int qlo, int qhi)
 {
+	// One launch serves the tasks whose query length lies in (qlo, qhi]: shared memory is sized for qhi, so the short
+	// extensions — most of them — run at several times the occupancy the longest read would allow.  The list is sorted
+	// by length, so all but a boundary block of a launch either take all their lanes or leave at once.
 	extern __shared__ uint32_t wave_smem[];
 	const int lane = threadIdx.x, t = blockIdx.x * 32 + lane;
-	bool valid = t < n_tasks && keys_sorted[t] != 0;
+	const int key = t < n_tasks ? keys_sorted[t] : 0;
+	bool valid = key > qlo && key <= qhi;
 	if (!__any_sync(FULL_MASK, valid)) return;
 	ExtPlan *pl = valid ? plans + order[t] : nullptr;
 	Seed s{};

@@ -6,7 +6,7 @@
 //
 //   k_glob_plan  thread / read   for every region of the read: the first call's arguments -> one GlobTask, or none when
 //                                the call takes the gap-free path (no DP)
-//   (sort, scan)                 tasks ordered by DP size; exact backtrack-matrix offsets
+//   (sort, scan)                 tasks ordered by (band width, rows); backtrack-matrix offsets per warp of 32 tasks
 //   k_glob_wave  thread / task   ksw_global2 + backtrack, 32 similar-sized tasks per warp, DP row {H, E} as two int16 in
 //                                one shared-memory word per column, one direction byte per cell (bwa/ksw.c:587-600)
 //   k_finalize   warp / pair     as before; a ksw_global2 call whose arguments match a task copies its score and CIGAR,
@@ -68,7 +68,7 @@ EMAB_HD bool glob_first_call(const DevIndex &ix, int l_query_read, const Reg &ar
 template <class Pools_>
 __global__ void __launch_bounds__(128)
 k_glob_plan(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools_ p, int rescue_room, const int32_t *aln_off,
-            GlobTask *tasks, uint16_t *keys, unsigned long long *zsize)
+            GlobTask *tasks, uint16_t *keys)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
@@ -80,52 +80,95 @@ k_glob_plan(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, co
 		int q0, qstep, qlen, tstep, tlen, w;
 		int64_t t0;
 		t.query = nullptr; t.n_cigar = 0; t.score = 0; t.cells = 0; t.pad = 0;
-		keys[slot] = 0; zsize[slot] = 0;
+		keys[slot] = 0;
 		if (!glob_first_call(ix, l_query, regs[i], &q0, &qstep, &qlen, &t0, &tstep, &tlen, &w)) continue;
 		if (qlen + tlen > GLOB_MAX_DIM || qlen > EMAB_MAX_READ_LEN) continue;
 		t.query = seq + off[r]; t.t0 = t0; t.q0 = q0; t.qlen = qlen; t.tlen = tlen; t.w = w; t.qstep = (int8_t)qstep; t.tstep = (int8_t)tstep;
+		// sort key: band width first, rows second — a warp's row costs its widest band, its length its longest task
 		const int ncol = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
-		const unsigned long long z = (unsigned long long)ncol * tlen;
-		zsize[slot] = z;
-		const unsigned long long k = (z >> 4) + 1;
-		keys[slot] = (uint16_t)(k > 65535 ? 65535 : k);
+		keys[slot] = (uint16_t)((ncol > 255 ? 255 : ncol) << 8 | (((tlen + 3) >> 2) > 255 ? 255 : ((tlen + 3) >> 2)));
 	}
 }
 
-// ksw_global2 (bwa/ksw.c:540-622) + backtrack (:624-638) of one task per thread
+// Upper bound of a warp's backtrack matrix: its 32 tasks (in sorted order) advance row by row together and a row is
+// as wide as its widest lane, so 32 * max(ncol) * max(tlen) bytes always suffice.
+__global__ void k_glob_zsize(const GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, unsigned long long *zsize_warp, int n_warps)
+{
+	const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (wi >= n_warps) return;
+	int ncol = 0, tlen = 0;
+	for (int l = 0; l < 32; ++l) {
+		const int ti = wi * 32 + l;
+		if (ti >= n_tasks || keys_sorted[ti] == 0) break;   // sorted descending: nothing valid follows
+		const GlobTask &t = tasks[order[ti]];
+		const int nc = t.qlen < 2 * t.w + 1 ? t.qlen : 2 * t.w + 1;
+		ncol = nc > ncol ? nc : ncol;
+		tlen = t.tlen > tlen ? t.tlen : tlen;
+	}
+	zsize_warp[wi] = 32ull * ncol * tlen;
+}
+
+// ksw_global2 (bwa/ksw.c:540-622) + backtrack (:624-638), one task per thread, the 32 tasks of a warp row by row
+// together.  Everything a cell touches is laid out so that a warp instruction is ONE memory transaction:
+//   * DP row and query in shared memory, lane-interleaved (word j of lane l at [j * 32 + l]): conflict-free;
+//   * direction bytes at zw[(row_base + jj) * 32 + lane], jj = column offset inside the row's band and row_base the
+//     running sum of the rows' widest bands: the 32 lanes of a store instruction write 32 consecutive bytes (one sector).
+//     With one private matrix per lane every store would be a transaction of its own — 32 L1 wavefronts and 32
+//     partial-sector writes in L2 per instruction, which is what bounded the first version of this kernel.
 __global__ void __launch_bounds__(32)
-k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, const unsigned long long *zoff, uint8_t *zpool,
-            uint32_t *cigars, unsigned long long *planned_cells)
+k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, const unsigned long long *zoff_warp, uint8_t *zpool,
+            uint32_t *cigars, unsigned long long *planned_cells, int qcap)
 {
 	extern __shared__ uint32_t glob_smem[];
 	const int lane = threadIdx.x, ti = blockIdx.x * 32 + lane;
 	const bool valid = ti < n_tasks && keys_sorted[ti] != 0;
 	if (!__any_sync(FULL_MASK, valid)) return;
+	uint32_t *he = glob_smem + lane;                          // column j at he[j * 32]: {H(i-1, j-1) : lo16, E(i, j) : hi16}
+	uint32_t *qw = glob_smem + (qcap + 1) * 32 + lane;        // query bases j..j+3 in word (j >> 2)
+	uint32_t *rowbase = glob_smem + (qcap + 1) * 32 + ((qcap + 4) >> 2) * 32;   // [GLOB_MAX_DIM] warp-uniform
+	uint8_t *zw = zpool + zoff_warp[blockIdx.x] + lane;
 	unsigned long long cells = 0;
+	int slot = 0, qlen = 0, tlen = 0, w = 0, tstep = 1;
+	int64_t t0 = 0;
+	constexpr int e_del = opt::e_del, e_ins = opt::e_ins, oe_del = opt::oe_del, oe_ins = opt::oe_ins;
 	if (valid) {
-		const int slot = order[ti];
-		GlobTask &t = tasks[slot];
-		uint32_t *he = glob_smem + lane;          // column j at he[j * 32]: {H(i-1, j-1) : lo16, E(i, j) : hi16}
-		uint8_t *z = zpool + zoff[slot];
+		slot = order[ti];
+		const GlobTask &t = tasks[slot];
+		qlen = t.qlen; tlen = t.tlen; w = t.w; tstep = t.tstep; t0 = t.t0;
 		const uint8_t *query = t.query;
-		const int qlen = t.qlen, tlen = t.tlen, w = t.w, q0 = t.q0, qstep = t.qstep, tstep = t.tstep;
-		const int64_t t0 = t.t0;
-		constexpr int e_del = opt::e_del, e_ins = opt::e_ins, oe_del = opt::oe_del, oe_ins = opt::oe_ins;
-		const int ncol = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+		const int q0 = t.q0, qstep = t.qstep;
 		for (int j = 0; j <= qlen; ++j) {
 			const int h = j == 0 ? 0 : (j <= w ? -(opt::o_ins + e_ins * j) : GLOB_NEG16);
 			he[j * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h & 0xffffu);
 		}
-		for (int i = 0; i < tlen; ++i) {
-			const int tb = ref_base(ix, t0 + (int64_t)i * tstep);
-			const int beg = i > w ? i - w : 0;
-			const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
-			int h1 = beg == 0 ? -(opt::o_del + e_del * (i + 1)) : GLOB_NEG16, f = GLOB_NEG16;
-			uint8_t *zr = z + (size_t)i * ncol - beg;
-			if (end > beg) cells += end - beg;
-			for (int j = beg; j < end; ++j) {
-				const uint32_t wv = he[j * 32];
-				const int qb = query[q0 + j * qstep];
+		for (int j = 0; j < qlen; j += 4) {
+			uint32_t v = 0;
+			for (int k = 0; k < 4 && j + k < qlen; ++k) v |= (uint32_t)query[q0 + (j + k) * qstep] << (8 * k);
+			qw[(j >> 2) * 32] = v;
+		}
+	}
+	const int tl_max = (int)__reduce_max_sync(FULL_MASK, (unsigned)tlen);
+	unsigned row_base = 0;
+	for (int i = 0; i < tl_max; ++i) {
+		const bool act = i < tlen;
+		int beg = 0, end = 0, tb = 4;
+		if (act) {
+			beg = i > w ? i - w : 0;
+			end = i + w + 1 < qlen ? i + w + 1 : qlen;
+			tb = ref_base(ix, t0 + (int64_t)i * tstep);
+		}
+		const int width = end > beg ? end - beg : 0;
+		const int mw = (int)__reduce_max_sync(FULL_MASK, (unsigned)width);
+		if (lane == 0) rowbase[i] = row_base;
+		int h1 = beg == 0 ? -(opt::o_del + e_del * (i + 1)) : GLOB_NEG16, f = GLOB_NEG16;
+		cells += width;
+		uint8_t *zr = zw + (size_t)row_base * 32;
+		uint32_t *hp = he + beg * 32;
+		for (int jj = 0; jj < mw; ++jj) {
+			if (jj < width) {
+				const int j = beg + jj;
+				const uint32_t wv = hp[jj * 32];
+				const int qb = (int)(qw[(j >> 2) * 32] >> ((j & 3) << 3)) & 0xff;
 				const int M = (int)(short)(wv & 0xffffu) + sc_mat(tb, qb);
 				int e = (int)wv >> 16;
 				int d = M >= e ? 0 : 1;
@@ -136,16 +179,21 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 				e -= e_del;
 				d |= e > tt ? 1 << 2 : 0;
 				e = e > tt ? e : tt;
-				he[j * 32] = ((uint32_t)e << 16) | ((uint32_t)h1 & 0xffffu);
+				hp[jj * 32] = ((uint32_t)e << 16) | ((uint32_t)h1 & 0xffffu);
 				h1 = h;
 				tt = M - oe_ins;
 				f -= e_ins;
 				d |= f > tt ? 2 << 4 : 0;
 				f = f > tt ? f : tt;
-				zr[j] = (uint8_t)d;
+				zr[(size_t)jj * 32] = (uint8_t)d;
 			}
-			he[end * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h1 & 0xffffu);
 		}
+		if (act) he[end * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h1 & 0xffffu);
+		row_base += (unsigned)mw;
+	}
+	__syncwarp();
+	if (valid) {
+		GlobTask &t = tasks[slot];
 		t.score = (int)(short)(he[qlen * 32] & 0xffffu);
 		t.cells = (uint32_t)cells;
 		// backtrack: operations are met last to first and written back to front, so the kept ones are in forward order at
@@ -163,7 +211,7 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 		};
 		while (i >= 0 && k >= 0) {
 			const int lo = i > w ? i - w : 0;
-			state = z[(size_t)i * ncol + (k - lo)] >> (state << 1) & 3;
+			state = zw[((size_t)rowbase[i] + (k - lo)) * 32] >> (state << 1) & 3;
 			if (state == 0) { push(0, 1); --i; --k; }
 			else if (state == 1) { push(2, 1); --i; }
 			else { push(1, 1); --k; }
@@ -176,6 +224,9 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 	for (int d = 16; d; d >>= 1) cells += __shfl_xor_sync(FULL_MASK, cells, d);
 	if (lane == 0 && cells) atomicAdd(planned_cells, cells);
 }
+
+// shared memory of one k_glob_wave warp for queries up to qcap bases
+__host__ __device__ inline size_t glob_smem_bytes(int qcap) { return ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) >> 2) * 32 + GLOB_MAX_DIM) * 4; }
 
 // a ksw_global2 call of the replay against the read's tasks; on a hit copies the CIGAR (if wanted) and returns true
 __device__ __forceinline__ bool glob_plan_lookup(const GlobTask *tasks, const uint32_t *cigars, int n_tasks, const uint8_t *query, int q0, int qstep, int qlen,

@@ -547,14 +547,22 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 				TRY(c->b[6].ensure(sb + 16));
 				cub::DeviceRadixSort::SortPairsDescending(c->b[6].p, sb, lkey, lkey_s, iota_l, order_l, NCH, 0, 8, st);
 				cub::DeviceRadixSort::SortPairsDescending(c->b[6].p, sb, rkey, rkey_s, iota_r, order_r, NCH, 0, 8, st);
-				const size_t smem = lanes::smem_per_warp(max_len);
 				CUDA_TRY(cudaFuncSetAttribute(k_ext_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 				CUDA_TRY(cudaFuncSetAttribute(k_ext_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 				CUDA_TRY(cudaEventRecord(c->stage_ev[8], st));
-				k_ext_wave<false><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_l, lkey_s, NCH, &c->d_counters[12]);
-				k_ext_wave<true><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_r, rkey_s, NCH, &c->d_counters[12]);
+				// four launches per side, by query length class (shared memory, hence occupancy, follows the class)
+				const int cls[5] = {0, 32, 64, 112, 255};
+				for (int side = 0; side < 2; ++side)
+					for (int k = 0; k < 4; ++k) {
+						if (cls[k] >= max_len) break;
+						const int qhi = cls[k + 1] < max_len ? cls[k + 1] : 255;
+						const size_t smem = lanes::smem_per_warp(qhi < max_len ? qhi : max_len);
+						if (side == 0) k_ext_wave<false><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_l, lkey_s, NCH, &c->d_counters[12], cls[k], qhi);
+						else k_ext_wave<true><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_r, rkey_s, NCH, &c->d_counters[12], cls[k], qhi);
+						++launches;
+					}
 				CUDA_TRY(cudaEventRecord(c->stage_ev[9], st));
-				launches += 6;
+				launches += 4;
 				d_plans = plans; d_chain_off = chain_off; ext_waves_ran = true;
 			}
 		}
@@ -599,32 +607,34 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 			// the first ksw_global2 of every region ahead of the per-pair control flow (glob_wave.cuh)
 			TRY(c->b[36].ensure((size_t)A * sizeof(GlobTask)));
 			TRY(c->b[37].ensure((size_t)A * 2 * 2 + (size_t)A * 4 * 2 + 64));      // keys, sorted keys | iota, order
-			TRY(c->b[38].ensure(((size_t)A + 1) * 8 * 2));                           // zsize, zoff
+			const int n_gwarps = (A + 31) / 32;
+			TRY(c->b[38].ensure(((size_t)n_gwarps + 1) * 8 * 2));                   // per-warp z size, z offset
 			TRY(c->b[39].ensure((size_t)A * EMAB_MAX_CIGAR * 4));
 			GlobTask *gt = c->b[36].as<GlobTask>();
 			int32_t *g_iota = c->b[37].as<int32_t>(), *g_order = g_iota + A;
 			uint16_t *g_keys = (uint16_t *)(g_order + A), *g_keys_s = g_keys + A;
-			unsigned long long *zsize = c->b[38].as<unsigned long long>(), *zoff = zsize + (A + 1);
-			CUDA_TRY(cudaMemsetAsync(zsize + A, 0, 8, st));
-			k_glob_plan<Pools><<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, RESCUE_ROOM, d_aln_off, gt, g_keys, zsize);
+			unsigned long long *zsize = c->b[38].as<unsigned long long>(), *zoff = zsize + (n_gwarps + 1);
+			CUDA_TRY(cudaMemsetAsync(zsize + n_gwarps, 0, 8, st));
+			k_glob_plan<Pools><<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, RESCUE_ROOM, d_aln_off, gt, g_keys);
 			k_iota1<<<(A + 255) / 256, 256, 0, st>>>(A, g_iota);
 			size_t sb = 0;
 			cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, g_keys, g_keys_s, g_iota, g_order, A, 0, 16, st);
 			TRY(c->b[6].ensure(sb + 16));
 			cub::DeviceRadixSort::SortPairsDescending(c->b[6].p, sb, g_keys, g_keys_s, g_iota, g_order, A, 0, 16, st);
-			cub::DeviceScan::ExclusiveSum(nullptr, sb, zsize, zoff, A + 1, st);
+			k_glob_zsize<<<(n_gwarps + 127) / 128, 128, 0, st>>>(gt, g_order, g_keys_s, A, zsize, n_gwarps);
+			cub::DeviceScan::ExclusiveSum(nullptr, sb, zsize, zoff, n_gwarps + 1, st);
 			TRY(c->b[6].ensure(sb + 16));
-			cub::DeviceScan::ExclusiveSum(c->b[6].p, sb, zsize, zoff, A + 1, st);
+			cub::DeviceScan::ExclusiveSum(c->b[6].p, sb, zsize, zoff, n_gwarps + 1, st);
 			unsigned long long Z = 0;
-			CUDA_TRY(cudaMemcpyAsync(&Z, zoff + A, 8, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(&Z, zoff + n_gwarps, 8, cudaMemcpyDeviceToHost, st));
 			CUDA_TRY(ctx_wait(c));
-			TRY(c->b[40].ensure((size_t)Z + 16));
-			const size_t smem = lanes::smem_per_warp(max_len);
+			TRY(c->b[40].ensure((size_t)Z + 64));
+			const size_t smem = glob_smem_bytes(max_len);
 			CUDA_TRY(cudaFuncSetAttribute(k_glob_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 			CUDA_TRY(cudaEventRecord(c->stage_ev[10], st));
-			k_glob_wave<<<(A + 31) / 32, 32, smem, st>>>(ix, gt, g_order, g_keys_s, A, zoff, c->b[40].as<uint8_t>(), c->b[39].as<uint32_t>(), &c->d_counters[14]);
+			k_glob_wave<<<n_gwarps, 32, smem, st>>>(ix, gt, g_order, g_keys_s, A, zoff, c->b[40].as<uint8_t>(), c->b[39].as<uint32_t>(), &c->d_counters[14], max_len);
 			CUDA_TRY(cudaEventRecord(c->stage_ev[11], st));
-			launches += 5;
+			launches += 6;
 			d_gtasks = gt; d_gcigars = c->b[39].as<uint32_t>(); glob_waves_ran = true;
 		}
 		k_finalize<<<grid, PL_WARPS * 32, 0, st>>>(ix, n_pairs, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, d_aln_off, c->b[18].as<Aln>(),

@@ -5,6 +5,8 @@ usage: ncu_lines.py rep kernel-regex cubin [top-n]     (cubin: cuobjdump -xelf a
 import csv, io, re, subprocess, sys
 from collections import defaultdict
 rep, kre, cubin = sys.argv[1:4]
+kre_ncu = kre   # "ncu-regex::cubin-regex" when the demangled (ncu) and mangled (nvdisasm) names need different patterns (templates)
+if "::" in kre: kre_ncu, kre = kre.split("::", 1)
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 lines = []   # (file:line) per SASS instruction of the kernel, in order
@@ -24,7 +26,7 @@ for l in dis:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", l):
         lines.append(loc)
-src = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre, "--launch-count", "1"],
+src = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre_ncu, "--launch-count", "1"],
                                                   capture_output=True, text=True).stdout)))
 h = [i for i, r in enumerate(src) if "Source" in r][0]
 sx = {n: i for i, n in enumerate(src[h])}
