@@ -550,17 +550,13 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 				CUDA_TRY(cudaFuncSetAttribute(k_ext_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 				CUDA_TRY(cudaFuncSetAttribute(k_ext_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 				CUDA_TRY(cudaEventRecord(c->stage_ev[8], st));
-				// four launches per side, by query length class (shared memory, hence occupancy, follows the class)
-				const int cls[5] = {0, 32, 64, 112, 255};
-				for (int side = 0; side < 2; ++side)
-					for (int k = 0; k < 4; ++k) {
-						if (cls[k] >= max_len) break;
-						const int qhi = cls[k + 1] < max_len ? cls[k + 1] : 255;
-						const size_t smem = lanes::smem_per_warp(qhi < max_len ? qhi : max_len);
-						if (side == 0) k_ext_wave<false><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_l, lkey_s, NCH, &c->d_counters[12], cls[k], qhi);
-						else k_ext_wave<true><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_r, rkey_s, NCH, &c->d_counters[12], cls[k], qhi);
-						++launches;
-					}
+				// One launch per side.  Launching per query-length class (less shared memory, more resident warps for the
+				// short extensions) was measured and dropped: a wave lasts as long as its longest task's single lane
+				// (~0.3 ms for a 130-column extension), and every extra launch adds such a floor (0.97 -> 2.15 ms).
+				const size_t smem = lanes::smem_per_warp(max_len);
+				k_ext_wave<false><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_l, lkey_s, NCH, &c->d_counters[12], 0, 255);
+				k_ext_wave<true><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_r, rkey_s, NCH, &c->d_counters[12], 0, 255);
+				launches += 2;
 				CUDA_TRY(cudaEventRecord(c->stage_ev[9], st));
 				launches += 4;
 				d_plans = plans; d_chain_off = chain_off; ext_waves_ran = true;

@@ -219,8 +219,55 @@ struct SeedJob {  // one read as the seeding loops see it
 // Passes 1 and 2.  feed.next(job) hands out the next read (false = queue empty); feed.done(job, n, ovf)
 // receives the number of intervals written to job.out.  buf0/buf1: this lane's prev/curr lists,
 // (longest read + 1) entries each.  ALL 32 LANES OF A WARP MUST CALL (the loop votes).
-template <class Feeder>
-EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
+// Policies of the two loops below.
+//   FmT   the FM-index step: fm.extend1(ik, c, is_back) = the interval of base c after bwt_extend (bwa/bwt.c:262-275).
+//         ThreadFm computes it in one thread (fmindex.cuh); QuadFm (device) spreads one step over four lanes.
+//   Lists bwt_smem1a's prev/curr interval lists (bwa/bwt.c:295-297): lists.put(which, idx, iv) / lists.get(which, idx),
+//         which in {0, 1}; lists.emit(out, idx, iv) stores an output interval.  PtrLists are two arrays in memory;
+//         QuadLists (device) keep them packed in shared memory.
+struct ThreadFm {
+	Fm &fm;
+	EMAB_HD Intv extend1(const Intv &ik, int c, int is_back) { return bwt_extend1(fm, ik, c, is_back); }
+	EMAB_HD const DevIndex &index() const { return fm.ix; }
+};
+struct PtrLists {
+	Intv *l[2];
+	EMAB_HD void put(int which, int idx, const Intv &v) { l[which][idx] = v; }
+	EMAB_HD Intv get(int which, int idx) const { return l[which][idx]; }
+	EMAB_HD void emit(Intv *out, int idx, const Intv &v) { out[idx] = v; }
+	EMAB_HD void sync() const {}
+};
+
+// pass 2 re-seeds inside long, rare SMEMs of pass 1 (bwa/bwamem.c:157-168).  Whether an interval qualifies is known
+// when pass 1 emits it, so the (position, min_intv) pairs are queued in a register then instead of being searched for
+// in the output list afterwards (a chain of dependent global loads run by a few lanes while the warp waits).  The
+// order of the pass-2 calls does not matter: each is independent and the final sort orders their output.
+struct Pass2Queue {
+	uint64_t bits = 0;     // up to 5 entries of 12 bits: sx (8) | min_intv (4); the count in the top 4 bits
+	int spill_from = -1;   // >= 0: the queue was full; intervals emitted from this output index on are scanned in memory
+	EMAB_HD int count() const { return (int)(bits >> 60); }
+	EMAB_HD void clear() { bits = 0; spill_from = -1; }
+	EMAB_HD void consider(const Intv &p, int start, int out_idx)
+	{
+		const int end = (int)(uint32_t)p.info;
+		if (end - start < opt::split_len || p.x2 > (uint64_t)opt::split_width) return;
+		const int n = count();
+		if (n == 5 || spill_from >= 0) { if (spill_from < 0) spill_from = out_idx; return; }
+		const uint64_t e = (uint64_t)((start + end) >> 1) | (p.x2 + 1) << 8;
+		bits = (bits & 0x0fffffffffffffffull) | e << (12 * n) | (uint64_t)(n + 1) << 60;
+	}
+	EMAB_HD bool pop(int *sx, uint64_t *min_intv)
+	{
+		const int n = count();
+		if (n == 0) return false;
+		*sx = (int)(bits & 0xff); *min_intv = (bits >> 8) & 0xf;
+		bits = ((bits & 0x0fffffffffffffffull) >> 12) | (uint64_t)(n - 1) << 60;
+		return true;
+	}
+};
+
+template <class Feeder, class FmT, class Lists>
+EMAB_HD void seed_p12(FmT &fm, Feeder &feed, Lists &lists)
 {
 	SeedJob job;
 	job.seq = nullptr; job.len = 0; job.out = nullptr; job.cap = 0; job.id = -1;
@@ -232,7 +279,8 @@ EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 	int i = 0, j = 0, n_prev = 0, n_curr = 0, sx = 0, ret = 0, last_start = 0x7fffffff;
 	uint64_t min_intv = 1, last_size = 0;
 	bool in_p2 = false, rev = false;
-	Intv *prev = buf0, *curr = buf1;
+	int cur = 1;           // which list is bwt_smem1a's `curr`; the other one is `prev`
+	Pass2Queue q2;
 	Intv ik;
 	ik.x0 = ik.x1 = ik.x2 = ik.info = 0;
 	int c = 0, back = 0;
@@ -242,7 +290,7 @@ EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 		while (!req && !drained) {
 			if (st == SD_DONE) {  // take the next read
 				if (have_job) { feed.done(job, n, ovf); have_job = false; }
-				if (feed.next(job)) { have_job = true; n = 0; ovf = 0; pass = 1; x = 0; st = SD_NEXT; }
+				if (feed.next(job)) { have_job = true; n = 0; ovf = 0; pass = 1; x = 0; st = SD_NEXT; q2.clear(); }
 				else drained = true;
 			}
 			if (st == SD_BWD && j == n_prev) {  // end of one backward round (bwa/bwt.c:346-348)
@@ -250,7 +298,7 @@ EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 					if (!in_p2) x = ret;
 					st = SD_NEXT;
 				} else {
-					{ Intv *t = curr; curr = prev; prev = t; }
+					cur ^= 1;
 					n_prev = n_curr; n_curr = 0;
 					--i; rev = false;
 					st = SD_BWD0;
@@ -263,21 +311,26 @@ EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 					if (x >= job.len) { pass = 2; old_n = n; k2 = 0; }
 					else { sx = x; min_intv = 1; in_p2 = false; start_call = true; }
 				} else {  // pass 2: bwa/bwamem.c:157-168
-					while (k2 < old_n) {
-						const Intv p = job.out[k2];
-						const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
-						if (end - start >= opt::split_len && p.x2 <= (uint64_t)opt::split_width) break;
-						++k2;
-					}
-					if (k2 >= old_n) st = SD_DONE;
-					else {
-						const Intv p = job.out[k2++];
-						sx = ((int)(p.info >> 32) + (int)(uint32_t)p.info) >> 1;
-						min_intv = p.x2 + 1; in_p2 = true; start_call = true;
-					}
+					if (q2.pop(&sx, &min_intv)) { in_p2 = true; start_call = true; }
+					else if (q2.spill_from >= 0) {  // more than five candidates: the rest are looked up in the output list
+						if (k2 < q2.spill_from) k2 = q2.spill_from;
+						lists.sync();
+						while (k2 < old_n) {
+							const Intv p = job.out[k2];
+							const int start = (int)(p.info >> 32), end = (int)(uint32_t)p.info;
+							if (end - start >= opt::split_len && p.x2 <= (uint64_t)opt::split_width) break;
+							++k2;
+						}
+						if (k2 >= old_n) st = SD_DONE;
+						else {
+							const Intv p = job.out[k2++];
+							sx = ((int)(p.info >> 32) + (int)(uint32_t)p.info) >> 1;
+							min_intv = p.x2 + 1; in_p2 = true; start_call = true;
+						}
+					} else st = SD_DONE;
 				}
 				if (start_call) {  // bwt_smem1a(sx, min_intv): bwa/bwt.c:289-302
-					bwt_set_intv(fm.ix, job.seq[sx], ik);
+					bwt_set_intv(fm.index(), job.seq[sx], ik);
 					ik.info = sx + 1;
 					i = sx + 1; n_curr = 0; last_start = 0x7fffffff;
 					st = SD_FWD;
@@ -286,8 +339,8 @@ EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 			if (st == SD_FWD) {
 				if (i < job.len && job.seq[i] < 4) { c = 3 - job.seq[i]; back = 0; req = true; }
 				else {  // ambiguous base, or i == len (bwa/bwt.c:316-321)
-					curr[n_curr++] = ik; ret = (int)ik.info;
-					{ Intv *t = curr; curr = prev; prev = t; }
+					lists.put(cur, n_curr++, ik); ret = (int)ik.info;
+					cur ^= 1;
 					n_prev = n_curr; n_curr = 0;
 					i = sx - 1; rev = true;
 					st = SD_BWD0;
@@ -298,33 +351,34 @@ EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 				if (cc < 0) {
 					// nothing can extend: only the first (longest) interval may be emitted, after which the round
 					// leaves curr empty and the call is over (bwa/bwt.c:331-338,346)
-					Intv p = prev[rev ? n_prev - 1 : 0];
+					Intv p = lists.get(cur ^ 1, rev ? n_prev - 1 : 0);
 					if (i + 1 < last_start) {
 						p.info |= (uint64_t)(i + 1) << 32;
 						if ((int)(uint32_t)p.info - (i + 1) >= opt::min_seed_len) {
-							if (n < job.cap) job.out[n++] = p; else ovf = 1;
+							if (!in_p2) q2.consider(p, i + 1, n);
+							if (n < job.cap) lists.emit(job.out, n++, p); else ovf = 1;
 						}
 					}
 					if (!in_p2) x = ret;
 					st = SD_NEXT;
 				} else { c = cc; back = 1; j = 0; last_size = 0; st = SD_BWD; }
 			}
-			if (st == SD_BWD && j < n_prev) { ik = prev[rev ? n_prev - 1 - j : j]; req = true; }
+			if (st == SD_BWD && j < n_prev) { ik = lists.get(cur ^ 1, rev ? n_prev - 1 - j : j); req = true; }
 		}
 		// ---- the one convergent step.  On the device the warp votes here every iteration: the vote is
 		// the reconvergence point that brings all lanes to the bwt_extend below together.
 		if (!EMAB_WARP_ANY(req)) break;
 		if (!req) continue;
-		Intv ok = bwt_extend1(fm, ik, c, back);
+		Intv ok = fm.extend1(ik, c, back);
 		// ---- consume
 		if (st == SD_FWD) {  // bwa/bwt.c:307-315
 			bool stop = false;
 			if (ok.x2 != ik.x2) {
-				curr[n_curr++] = ik; ret = (int)ik.info;
+				lists.put(cur, n_curr++, ik); ret = (int)ik.info;
 				stop = ok.x2 < min_intv;
 			}
 			if (stop) {
-				{ Intv *t = curr; curr = prev; prev = t; }
+				cur ^= 1;
 				n_prev = n_curr; n_curr = 0;
 				i = sx - 1; rev = true;
 				st = SD_BWD0;
@@ -339,13 +393,14 @@ EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 					Intv p = ik;
 					p.info |= (uint64_t)(i + 1) << 32;
 					if ((int)(uint32_t)p.info - (i + 1) >= opt::min_seed_len) {
-						if (n < job.cap) job.out[n++] = p; else ovf = 1;
+						if (!in_p2) q2.consider(p, i + 1, n);
+						if (n < job.cap) lists.emit(job.out, n++, p); else ovf = 1;
 					}
 					last_start = i + 1;
 				}
 			} else if (n_curr == 0 || ok.x2 != last_size) {
 				ok.info = ik.info;
-				curr[n_curr++] = ok;
+				lists.put(cur, n_curr++, ok);
 				last_size = ok.x2;
 			}
 			++j;
@@ -355,8 +410,8 @@ EMAB_HD void seed_p12(Fm &fm, Feeder &feed, Intv *buf0, Intv *buf1)
 
 // Pass 3: bwt_seed_strategy1 from every restart point (bwa/bwt.c:358-379, bwa/bwamem.c:170-185).
 // At most len / (min_seed_len + 1) + 1 intervals per read.  ALL 32 LANES OF A WARP MUST CALL.
-template <class Feeder>
-EMAB_HD void seed_p3(Fm &fm, Feeder &feed)
+template <class Feeder, class FmT, class Lists>
+EMAB_HD void seed_p3(FmT &fm, Feeder &feed, Lists &lists)
 {
 	SeedJob job;
 	job.seq = nullptr; job.len = 0; job.out = nullptr; job.cap = 0; job.id = -1;
@@ -375,7 +430,7 @@ EMAB_HD void seed_p3(Fm &fm, Feeder &feed)
 					else drained = true;
 					continue;
 				}
-				bwt_set_intv(fm.ix, job.seq[x], ik);
+				bwt_set_intv(fm.index(), job.seq[x], ik);
 				i = x + 1; active = true;
 			}
 			if (i < job.len && job.seq[i] < 4) { c = 3 - job.seq[i]; req = true; }
@@ -383,11 +438,11 @@ EMAB_HD void seed_p3(Fm &fm, Feeder &feed)
 		}
 		if (!EMAB_WARP_ANY(req)) break;
 		if (!req) continue;
-		Intv ok = bwt_extend1(fm, ik, c, 0);
+		Intv ok = fm.extend1(ik, c, 0);
 		if (ok.x2 < (uint64_t)opt::max_mem_intv && i - x >= opt::min_seed_len) {  // bwa/bwt.c:366-375
 			if (ok.x2 > 0) {
 				ok.info = (uint64_t)x << 32 | (uint64_t)(i + 1);
-				if (n < job.cap) job.out[n++] = ok; else ovf = 1;
+				if (n < job.cap) lists.emit(job.out, n++, ok); else ovf = 1;
 			}
 			x = i + 1; active = false;
 		} else { ik = ok; ++i; }
@@ -424,8 +479,10 @@ EMAB_HD int collect_intv(Fm &fm, int len, const uint8_t *seq, Intv *mem, int mem
 {
 	Intv p3[EMAB_P3_CAP];
 	OneReadFeeder f12{{seq, len, mem, mem_cap, 0}, false, 0, 0}, f3{{seq, len, p3, EMAB_P3_CAP, 0}, false, 0, 0};
-	seed_p12(fm, f12, buf0, buf1);
-	seed_p3(fm, f3);
+	ThreadFm tfm{fm};
+	PtrLists lists{{buf0, buf1}};
+	seed_p12(tfm, f12, lists);
+	seed_p3(tfm, f3, lists);
 	const int n = finish_intv(mem, f12.n, p3, f3.n, mem_cap);
 	if (f12.ovf || f3.ovf || n < 0) { *overflow = 1; return f12.n; }
 	return n;
@@ -478,8 +535,10 @@ __device__ __forceinline__ void seed_warp(const DevIndex &ix, const SeedBatch &b
 	Fm fm{ix, 0};
 	Intv *buf0 = b.scratch + (size_t)gt * 2 * b.scratch_len;
 	QueueFeeder f12{b, 0}, f3{b, 1};
-	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(fm, f3); seed_p12(fm, f12, buf0, buf0 + b.scratch_len); }
-	else { seed_p12(fm, f12, buf0, buf0 + b.scratch_len); seed_p3(fm, f3); }
+	ThreadFm tfm{fm};
+	PtrLists lists{{buf0, buf0 + b.scratch_len}};
+	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(tfm, f3, lists); seed_p12(tfm, f12, lists); }
+	else { seed_p12(tfm, f12, lists); seed_p3(tfm, f3, lists); }
 	unsigned touches = fm.touches;
 	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
 	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(b.touches, (unsigned long long)touches);

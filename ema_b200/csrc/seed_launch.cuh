@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include "runtime.cuh"
 #include "seed.cuh"
+#include "seed_quad.cuh"
 
 #define SEED_BLOCK 128
 
@@ -15,6 +16,15 @@ static __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS)
 k_seed(DevIndex ix, SeedBatch b)
 {
 	seed_warp(ix, b);
+}
+
+// four lanes per read (seed_quad.cuh): 32 reads per 128-thread block, interval lists in shared memory
+template <int MIN_BLOCKS>
+static __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS)
+k_seed_quad(DevIndex ix, SeedBatch b)
+{
+	extern __shared__ uint4 seedq_smem[];
+	seed_quads(ix, b, seedq_smem);
 }
 
 static __global__ void __launch_bounds__(128)
@@ -34,11 +44,18 @@ k_seed_finish(SeedBatch b, int32_t *n_intv, int32_t *occ_cnt)
 	}
 }
 
+// EMAB_SEED_MODE: 4 (default) = four lanes per read (seed_quad.cuh), 1 = one lane per read (seed.cuh)
+static inline int seed_mode()
+{
+	static int v = 0;
+	if (!v) { const char *e = getenv("EMAB_SEED_MODE"); v = e ? atoi(e) : 4; if (v != 1) v = 4; }
+	return v;
+}
 // EMAB_SEED_BPS: resident 128-thread blocks per SM of the persistent seeding grid (tuning knob)
 static inline int seed_blocks_per_sm()
 {
 	static int v = 0;
-	if (!v) { const char *e = getenv("EMAB_SEED_BPS"); v = e ? atoi(e) : 0; if (v < 1 || v > 16) v = 6; }
+	if (!v) { const char *e = getenv("EMAB_SEED_BPS"); v = e ? atoi(e) : 0; if (v < 1 || v > 16) v = seed_mode() == 4 ? 8 : 6; }
 	return v;
 }
 
@@ -48,11 +65,13 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
                        int32_t *d_n_intv, int32_t *d_occ_cnt, int *d_err, unsigned long long *d_touches, int *launches)
 {
 	cudaStream_t st = c->stream;
+	const bool quad = seed_mode() == 4;
 	int grid = c->n_sm * seed_blocks_per_sm();
-	const int want = (2 * R + SEED_BLOCK - 1) / SEED_BLOCK;  // never more lanes than (read, role) items
+	const int per_block = quad ? SEED_BLOCK / 4 : SEED_BLOCK;                // reads in flight per block
+	const int want = (2 * R + per_block - 1) / per_block;  // never more lanes than (read, role) items
 	if (grid > want) grid = want;
 	if (grid < 1) grid = 1;
-	const size_t lanes = (size_t)grid * SEED_BLOCK;
+	const size_t lanes = (size_t)grid * per_block;                            // interval-list owners: lanes or quads
 	SeedBatch b;
 	b.n_reads = R; b.seq = d_seq; b.off = d_off; b.intv = d_intv; b.max_intv = max_intv;
 	b.scratch_len = max_len + 1;
@@ -65,7 +84,12 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
 	b.n12 = (int32_t *)(b.queue + 2); b.n3 = b.n12 + R;
 	b.err = d_err; b.touches = d_touches;
 	CUDA_TRY(cudaMemsetAsync(b.queue, 0, 16, st));
-	if (seed_blocks_per_sm() >= 6) k_seed<6><<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
+	if (quad) {
+		if (c->ix->d.seq_len >> 39) { snprintf(emab_errbuf, sizeof emab_errbuf, "reference too long for the packed interval lists (2^39)"); return EMAB_ERR_ARG; }
+		if (seed_blocks_per_sm() >= 10) k_seed_quad<10><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
+		else if (seed_blocks_per_sm() >= 8) k_seed_quad<8><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
+		else k_seed_quad<6><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
+	} else if (seed_blocks_per_sm() >= 6) k_seed<6><<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
 	else k_seed<5><<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
 	k_seed_finish<<<(R + 127) / 128, 128, 0, st>>>(b, d_n_intv, d_occ_cnt);
 	*launches += 2;
