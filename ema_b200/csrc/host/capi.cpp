@@ -143,6 +143,16 @@ int emab_align_fastq(emab_session_t *h, const char *d1, uint64_t l1, const char 
 	});
 }
 
+int emab_align_fastq_stream(emab_session_t *h, emab_read_cb r1, void *u1, emab_read_cb r2, void *u2, emab_write_cb w, void *uw, int batch_pairs)
+{
+	return guarded([&]() -> int {
+		if (!h || !r1 || !w) return fail(EMAB_ERR_ARG, "null argument");
+		int rc = emab::align_fastq_stream(h->s, r1, u1, r2, u2, w, uw, batch_pairs);
+		if (rc) return fail(rc, h->s->err);
+		return EMAB_OK;
+	});
+}
+
 int emab_session_stats(const emab_session_t *h, emab_run_stats_t *out)
 {
 	if (!h || !out) return EMAB_ERR_ARG;

@@ -63,6 +63,28 @@ struct PhaseGate {
 };
 enum { PH_PARSE = 0, PH_DEVICE = 1, PH_POST = 2, PH_COUNT = 3 };
 
+// Turns served one at a time in the order they were taken (the -d density pass: one random stream, bucket order).
+struct OrderedTurn {
+	std::mutex mu;
+	std::condition_variable cv;
+	int next = 0, serving = 0;
+	int take() { std::lock_guard<std::mutex> g(mu); return next++; }
+	void wait(int t) { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return serving == t; }); }
+	void done() { std::lock_guard<std::mutex> g(mu); ++serving; cv.notify_all(); }
+};
+// One turn: taken at construction, begun explicitly, always finished (an error path that never begins it still waits
+// for its place and gives it up, so later turns are not left waiting).
+struct TurnPass {
+	OrderedTurn &o;
+	int t;
+	bool begun = false;
+	explicit TurnPass(OrderedTurn &o_) : o(o_), t(o_.take()) {}
+	void begin() { o.wait(t); begun = true; }
+	~TurnPass() { if (!begun) o.wait(t); o.done(); }
+	TurnPass(const TurnPass &) = delete;
+	TurnPass &operator=(const TurnPass &) = delete;
+};
+
 struct Worker {  // one in-flight bucket: a device context (stream + scratch) and its staging buffers
 	emab_ctx_t *ctx = nullptr;
 	int dev_slot = 0;                     // which of the session's index replicas the ctx lives on
@@ -108,6 +130,7 @@ struct Session {  // the reference's process globals (src/main.c:23-34, src/alig
 	std::condition_variable cv;
 	int next_ticket = 0, cloud_turn = 0;
 	PhaseGate gate[PH_COUNT];             // parse+encode | device pipeline | clouds, EM, SAM text
+	OrderedTurn density;                  // -d: bad clouds are optimised bucket by bucket in input order
 	int new_ticket() { std::lock_guard<std::mutex> g(mu); return next_ticket++; }
 	int take_cloud_base(int ticket, int n_clouds)
 	{
@@ -167,6 +190,8 @@ int session_add_device(Session *s, int device);  // before session_set_workers
 // find_clouds_and_align (src/align.c:214) over the *contents* of the input file(s); SAM text in a malloc'ed buffer
 int align_special_fastq(Session *s, const char *data, size_t len, char **out, size_t *out_len);
 int align_fastq(Session *s, const char *d1, size_t l1, const char *d2, size_t l2, char **out, size_t *out_len);  // d2 == nullptr: interleaved
+// the same over streams: barcode groups cut into batches of ~batch_pairs pairs (0 = 40 000), SAM text delivered in order
+int align_fastq_stream(Session *s, emab_read_cb r1, void *u1, emab_read_cb r2, void *u2, emab_write_cb w, void *uw, int batch_pairs);
 // -x mode: n buckets, up to workers.size() in flight, outputs in input order
 int align_special_fastq_multi(Session *s, int n, const char *const *data, const size_t *len, char **out, size_t *out_len);
 

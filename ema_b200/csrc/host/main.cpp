@@ -178,11 +178,22 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "Processing reads...\n");
 		emit(emab_align_bucket(s, data.data(), data.size(), &text, &len));
 	} else {
-		std::string d1, d2;
-		if (!slurp(fq1, &d1)) IOERROR(fq1);
-		if (fq2 && !slurp(fq2, &d2)) IOERROR(fq2);
+		// -1 / -2: streamed — barcode groups are cut into device batches, memory stays bounded by the batches in flight
+		FILE *f1 = fopen(fq1, "r");
+		if (!f1) IOERROR(fq1);
+		FILE *f2 = fq2 ? fopen(fq2, "r") : NULL;
+		if (fq2 && !f2) IOERROR(fq2);
 		fprintf(stderr, "Processing reads...\n");
-		emit(emab_align_fastq(s, d1.data(), d1.size(), fq2 ? d2.data() : NULL, d2.size(), &text, &len));
+		int workers = 3;
+		if (const char *w = getenv("EMAB_WORKERS")) workers = atoi(w);
+		emab_session_workers(s, workers);
+		int batch = 0;
+		if (const char *b = getenv("EMAB_FASTQ_BATCH")) batch = atoi(b);
+		auto rd = [](void *u, char *buf, int64_t cap) -> int64_t { FILE *f = (FILE *)u; size_t n = fread(buf, 1, (size_t)cap, f); return ferror(f) ? -1 : (int64_t)n; };
+		auto wr = [](void *u, const char *t, uint64_t n) -> int { return fwrite(t, 1, (size_t)n, (FILE *)u) == n ? 0 : -1; };
+		if (emab_align_fastq_stream(s, rd, f1, f2 ? (emab_read_cb)rd : NULL, f2, wr, out_file, batch)) { fprintf(stderr, "%s\n", emab_last_error()); exit(EXIT_FAILURE); }
+		fclose(f1);
+		if (f2) fclose(f2);
 	}
 	if (out_file != stdout) fclose(out_file);
 	emab_session_close(s);

@@ -199,7 +199,7 @@ struct Pools {  // device pools sized by the total number of SA occurrences T an
 };
 
 __global__ void __launch_bounds__(128)
-k_chain(DevIndex ix, int n_reads, const int64_t *off, const Intv *intv, const int32_t *n_intv, const int32_t *occ_off, Pools p)
+k_chain(DevIndex ix, int n_reads, const int64_t *off, const Intv *intv, int max_intv, const int32_t *n_intv, const int32_t *occ_off, Pools p)
 {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
@@ -209,7 +209,7 @@ k_chain(DevIndex ix, int n_reads, const int64_t *off, const Intv *intv, const in
 	wk.chains = p.w_chains + o;
 	wk.nodes = p.w_nodes + (o / 3 + 2 * (size_t)r);
 	wk.ord = p.w_ord + 3 * (size_t)o;
-	p.n_chains[r] = chain_read(ix, (int)(off[r + 1] - off[r]), intv + (size_t)r * EMAB_MAX_INTV, n_intv[r], wk, cap, p.chains + o, p.seeds + o);
+	p.n_chains[r] = chain_read(ix, (int)(off[r + 1] - off[r]), intv + (size_t)r * max_intv, n_intv[r], wk, cap, p.chains + o, p.seeds + o);
 }
 
 __global__ void __launch_bounds__(PL_WARPS * 32)
@@ -229,6 +229,15 @@ k_align1(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const
 		p.n_regs[r] = n;
 		__syncwarp();
 	}
+}
+
+// 64-bit total of the per-read occurrence counts: the int32 prefix sums are only valid if it fits
+__global__ void k_sum64(int n, const int32_t *v, unsigned long long *out)
+{
+	unsigned long long s = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (unsigned long long)(uint32_t)v[i];
+	for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(FULL_MASK, s, d);
+	if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
 __global__ void k_iota2(int n, int32_t *a, int32_t *b)
@@ -464,32 +473,46 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	// slots: 0 seq, 1 off, 2 intv, 3 n_intv, 4 smem scratch, 5 occ_cnt/off, 6 cub temp, 7.. pools
 	TRY(upload(c, c->b[0], seq, (size_t)off[R]));
 	TRY(upload(c, c->b[1], off, (size_t)(R + 1) * 8));
-	TRY(c->b[2].ensure((size_t)R * EMAB_MAX_INTV * sizeof(Intv)));
 	TRY(c->b[3].ensure((size_t)R * 4));
 	TRY(c->b[5].ensure((size_t)(R + 1) * 4 * 2));
 	int32_t *d_occ_cnt = c->b[5].as<int32_t>(), *d_occ_off = d_occ_cnt + (R + 1);
 	TRY(c->b[22].ensure(16));
 	int *d_err = c->b[22].as<int>();
-	CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
-	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 128, st));
-	CUDA_TRY(cudaMemsetAsync(d_occ_cnt, 0, (size_t)(R + 1) * 4, st));
 	int launches = 0;
 	bool ext_waves_ran = false, glob_waves_ran = false;
 	if (!c->stage_ev[0]) for (int i = 0; i < 16; ++i) CUDA_TRY(cudaEventCreate(&c->stage_ev[i]));
 	CUDA_TRY(cudaEventRecord(c->ev0, st));
 	CUDA_TRY(cudaEventRecord(c->stage_ev[0], st));
-	TRY(launch_seed(c, R, max_len, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), EMAB_MAX_INTV, c->b[3].as<int32_t>(), d_occ_cnt, d_err,
-	                &c->d_counters[2], &launches));
-	CUDA_TRY(cudaEventRecord(c->stage_ev[1], st));
-	size_t tmp_bytes = 0;
-	cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_occ_cnt, d_occ_off, R + 1, st);
-	TRY(c->b[6].ensure(tmp_bytes + 16));
-	cub::DeviceScan::ExclusiveSum(c->b[6].p, tmp_bytes, d_occ_cnt, d_occ_off, R + 1, st);
-	++launches;
+	// Seeding keeps max_intv SA intervals per read.  The reference's list grows without bound (bwtintv_v, bwa/bwamem.c:140-188);
+	// here a bucket in which some read needs more is seeded again with four times the room (128 covers every read of the
+	// synthetic workloads; low-complexity reads are what needs more), so the result never depends on the capacity.
+	int max_intv = EMAB_MAX_INTV;
 	int32_t T = 0;
-	CUDA_TRY(cudaMemcpyAsync(&T, d_occ_off + R, 4, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(ctx_wait(c));
-	if (T < 0) { snprintf(emab_errbuf, sizeof emab_errbuf, "seed occurrence count overflow"); return EMAB_ERR_OVERFLOW; }
+	size_t tmp_bytes = 0;
+	for (;;) {
+		TRY(c->b[2].ensure((size_t)R * max_intv * sizeof(Intv)));
+		CUDA_TRY(cudaMemsetAsync(d_err, 0, 16, st));
+		CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 128, st));
+		CUDA_TRY(cudaMemsetAsync(d_occ_cnt, 0, (size_t)(R + 1) * 4, st));
+		TRY(launch_seed(c, R, max_len, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), c->b[2].as<Intv>(), max_intv, c->b[3].as<int32_t>(), d_occ_cnt, d_err,
+		                &c->d_counters[2], &launches));
+		CUDA_TRY(cudaEventRecord(c->stage_ev[1], st));
+		cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_occ_cnt, d_occ_off, R + 1, st);
+		TRY(c->b[6].ensure(tmp_bytes + 16));
+		cub::DeviceScan::ExclusiveSum(c->b[6].p, tmp_bytes, d_occ_cnt, d_occ_off, R + 1, st);
+		k_sum64<<<64, 256, 0, st>>>(R, d_occ_cnt, &c->d_counters[1]);
+		launches += 2;
+		int seed_err = 0;
+		unsigned long long T64 = 0;
+		CUDA_TRY(cudaMemcpyAsync(&T, d_occ_off + R, 4, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaMemcpyAsync(&T64, &c->d_counters[1], 8, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaMemcpyAsync(&seed_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(ctx_wait(c));
+		if (T64 > 0x7fffff00ull) { snprintf(emab_errbuf, sizeof emab_errbuf, "%llu seed occurrences in one batch: split the batch (the per-batch pools are indexed with 32 bits)", T64); return EMAB_ERR_OVERFLOW; }
+		if (seed_err != 3) break;
+		if (max_intv >= 8192) { snprintf(emab_errbuf, sizeof emab_errbuf, "a read has more than %d SA intervals", max_intv); return EMAB_ERR_OVERFLOW; }
+		max_intv *= 4;
+	}
 	const size_t Tn = (size_t)T + 1, NR = (size_t)T + (size_t)RESCUE_ROOM * R + 1;
 	Pools p;
 	TRY(c->b[7].ensure(Tn * sizeof(Seed)));   p.w_seeds = c->b[7].as<Seed>();
@@ -509,7 +532,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	TRY(c->b[16].ensure((size_t)n_warps * z_cap));
 	TRY(c->b[17].ensure((size_t)n_warps * EMAB_MAX_CIGAR * 4));
 	CUDA_TRY(cudaEventRecord(c->stage_ev[2], st));
-	k_chain<<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[1].as<int64_t>(), c->b[2].as<Intv>(), c->b[3].as<int32_t>(), d_occ_off, p);
+	k_chain<<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[1].as<int64_t>(), c->b[2].as<Intv>(), max_intv, c->b[3].as<int32_t>(), d_occ_off, p);
 	CUDA_TRY(cudaEventRecord(c->stage_ev[3], st));
 	if (c->sw_mode == 2) {  // thread-per-read mem_align1_core: wins only when a batch holds many more reads than the GPU has lanes
 		const size_t smem = lanes::smem_per_warp(max_len);

@@ -27,6 +27,15 @@ k_seed_quad(DevIndex ix, SeedBatch b)
 	seed_quads(ix, b, seedq_smem);
 }
 
+// one lane per read, Occ blocks staged through shared memory by cp.async (seed_quad.cuh: StagedFm)
+template <int MIN_BLOCKS>
+static __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS)
+k_seed_staged(DevIndex ix, SeedBatch b)
+{
+	extern __shared__ uint4 seedq_smem[];
+	seed_staged(ix, b, seedq_smem);
+}
+
 static __global__ void __launch_bounds__(128)
 k_seed_finish(SeedBatch b, int32_t *n_intv, int32_t *occ_cnt)
 {
@@ -44,11 +53,15 @@ k_seed_finish(SeedBatch b, int32_t *n_intv, int32_t *occ_cnt)
 	}
 }
 
-// EMAB_SEED_MODE: 4 (default) = four lanes per read (seed_quad.cuh), 1 = one lane per read (seed.cuh)
+// EMAB_SEED_MODE: 1 (default) = one lane per read, Occ blocks in registers (seed.cuh); 2 = one lane per read, Occ blocks
+// staged in shared memory by cp.async; 4 = four lanes per read (seed_quad.cuh).  Measured on the 3.1 Gbp index, one
+// 40 000-pair bucket (profiles/r2e_*): mode 1 5.1 ms, mode 4 6.0-6.5 ms — the quad form moves 16 % less DRAM traffic and
+// keeps its lists in shared memory, but runs the loops' bookkeeping on four lanes per read: 2.5 x the warp instructions,
+// 70 % ALU-pipe utilisation; the kernel's length is set by its longest reads' dependent chains, not by bandwidth.
 static inline int seed_mode()
 {
 	static int v = 0;
-	if (!v) { const char *e = getenv("EMAB_SEED_MODE"); v = e ? atoi(e) : 4; if (v != 1) v = 4; }
+	if (!v) { const char *e = getenv("EMAB_SEED_MODE"); v = e ? atoi(e) : 1; if (v != 2 && v != 4) v = 1; }
 	return v;
 }
 // EMAB_SEED_BPS: resident 128-thread blocks per SM of the persistent seeding grid (tuning knob)
@@ -89,6 +102,9 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
 		if (seed_blocks_per_sm() >= 10) k_seed_quad<10><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
 		else if (seed_blocks_per_sm() >= 8) k_seed_quad<8><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
 		else k_seed_quad<6><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
+	} else if (seed_mode() == 2) {
+		if (seed_blocks_per_sm() >= 8) k_seed_staged<8><<<grid, SEED_BLOCK, SEEDS_SMEM(SEED_BLOCK), st>>>(c->ix->d, b);
+		else k_seed_staged<6><<<grid, SEED_BLOCK, SEEDS_SMEM(SEED_BLOCK), st>>>(c->ix->d, b);
 	} else if (seed_blocks_per_sm() >= 6) k_seed<6><<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
 	else k_seed<5><<<grid, SEED_BLOCK, 0, st>>>(c->ix->d, b);
 	k_seed_finish<<<(R + 127) / 128, 128, 0, st>>>(b, d_n_intv, d_occ_cnt);

@@ -161,6 +161,105 @@ struct QuadFeeder {
 	}
 };
 
+// ---------------------------------------------------------------------------------------------
+// One lane per read, Occ blocks STAGED IN SHARED MEMORY by cp.async: the eight 16-byte pieces of a step's two blocks
+// travel global -> shared without occupying destination registers while they are in flight (the register form holds
+// 32 registers for them, which is what pins the kernel at 80 registers / 24 warps per SM), and are then consumed
+// piece by piece.  Slot layout: piece p of thread t at [(p * blockDim + t)] as uint4 — every warp access is 512
+// consecutive bytes.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint4 *dst_smem, const uint4 *src, bool pred)
+{
+	const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.ca.shared.global [%0], [%1], 16;\n\t}" ::"r"(d), "l"(src), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+struct StagedFm {
+	Fm &fm;
+	uint4 *slot;         // this thread's piece 0; piece p at slot[p * stride]
+	int stride;          // blockDim.x
+	__device__ const DevIndex &index() const { return fm.ix; }
+
+	__device__ __forceinline__ void occ4(int base_piece, int idx, bool valid, uint64_t cnt[4]) const
+	{
+		uint32_t nhi = 0, nlo = 0, nt = 0;
+		const int n = idx + 1, n2 = n << 1;
+		{
+			const uint4 w = slot[(base_piece + 2) * stride];
+			pair_counts(w.x, w.y, n2, 0, nhi, nlo, nt);
+			pair_counts(w.z, w.w, n2, 64, nhi, nlo, nt);
+		}
+		{
+			const uint4 w = slot[(base_piece + 3) * stride];
+			pair_counts(w.x, w.y, n2, 128, nhi, nlo, nt);
+			pair_counts(w.z, w.w, n2, 192, nhi, nlo, nt);
+		}
+		const uint32_t ng = nhi - nt, nc = nlo - nt, na = (uint32_t)n - nc - ng - nt;
+		const uint4 c0 = slot[base_piece * stride], c1 = slot[(base_piece + 1) * stride];
+		cnt[0] = valid ? ((uint64_t)c0.y << 32 | c0.x) + na : 0;
+		cnt[1] = valid ? ((uint64_t)c0.w << 32 | c0.z) + nc : 0;
+		cnt[2] = valid ? ((uint64_t)c1.y << 32 | c1.x) + ng : 0;
+		cnt[3] = valid ? ((uint64_t)c1.w << 32 | c1.z) + nt : 0;
+	}
+
+	__device__ Intv extend1(const Intv &ik, int c, int is_back)
+	{
+		const DevIndex &ix = fm.ix;
+		const uint64_t NEG1 = ~0ull;
+		const uint64_t xa = is_back ? ik.x0 : ik.x1, xb = is_back ? ik.x1 : ik.x0;
+		const uint64_t k = xa - 1, l = xa - 1 + ik.x2;
+		const bool kv = k != NEG1, lv = l != NEG1;
+		const uint64_t _k = kv ? k - (k >= ix.primary) : 0, _l = lv ? l - (l >= ix.primary) : 0;
+		const uint64_t bk = _k >> 7, bl = _l >> 7;
+		const uint4 *pk = ix.bwt + (bk << 2), *pl = ix.bwt + (bl << 2);
+		const bool other = bk != bl || ix.seed_load_both;
+#pragma unroll
+		for (int p = 0; p < 4; ++p) cp_async16(slot + p * stride, pk + p, true);
+#pragma unroll
+		for (int p = 0; p < 4; ++p) cp_async16(slot + (4 + p) * stride, pl + p, other);
+		fm.touches += (unsigned)kv + (unsigned)(lv && !(kv && bk == bl));
+		cp_async_wait_all();
+		uint64_t tk[4], tl[4];
+		occ4(0, (int)(_k & 127), kv, tk);
+		occ4(other ? 4 : 0, (int)(_l & 127), lv, tl);
+		uint64_t na = tk[0], ns = tl[0] - tk[0], above = 0;
+#pragma unroll
+		for (int i = 1; i < 4; ++i) {
+			const uint64_t d = tl[i] - tk[i];
+			if (c == i) { na = tk[i]; ns = d; }
+			if (c < i) above += d;
+		}
+		na += ix.L2[c] + 1;
+		const uint64_t nb = xb + (xa <= ix.primary && xa + ik.x2 - 1 >= ix.primary) + above;
+		Intv ok;
+		ok.x0 = is_back ? na : nb;
+		ok.x1 = is_back ? nb : na;
+		ok.x2 = ns;
+		ok.info = 0;
+		return ok;
+	}
+};
+#define SEEDS_SMEM(threads) ((threads) * 8 * 16)
+
+__device__ __forceinline__ void seed_staged(const DevIndex &ix, const SeedBatch &b, uint4 *smem)
+{
+	const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+	Fm fm{ix, 0};
+	StagedFm sfm{fm, smem + threadIdx.x, (int)blockDim.x};
+	Intv *buf0 = b.scratch + (size_t)gt * 2 * b.scratch_len;
+	PtrLists lists{{buf0, buf0 + b.scratch_len}};
+	QueueFeeder f12{b, 0}, f3{b, 1};
+	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(sfm, f3, lists); seed_p12(sfm, f12, lists); }
+	else { seed_p12(sfm, f12, lists); seed_p3(sfm, f3, lists); }
+	unsigned touches = fm.touches;
+	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
+	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(b.touches, (unsigned long long)touches);
+}
+
 // shared memory of one 128-thread block of k_seed_quad
 #define SEEDQ_SMEM (32 * SEEDQ_STRIDE * 16)
 

@@ -237,6 +237,13 @@ int emab_session_config(emab_session_t *s, const char *rg, const char *bx_index,
 int emab_sam_header(emab_session_t *s, int argc, const char *const *argv, char **text, uint64_t *len);
 int emab_align_bucket(emab_session_t *s, const char *data, uint64_t len, char **sam, uint64_t *sam_len);
 int emab_align_fastq(emab_session_t *s, const char *d1, uint64_t l1, const char *d2, uint64_t l2, char **sam, uint64_t *sam_len);
+/* -1/-2 as a stream (the reference reads barcode groups one at a time under a lock, src/align.c:296-341,653-744): the
+ * callbacks supply barcode-sorted FASTQ text (read: up to cap bytes into buf, 0 at the end, < 0 on error; r2 == NULL means
+ * one interleaved input) and receive the SAM body in input order.  Groups are cut into device batches of about batch_pairs
+ * pairs (0 = 40 000) at barcode boundaries, up to `workers` batches in flight; memory is bounded by the batches in flight. */
+typedef int64_t (*emab_read_cb)(void *user, char *buf, int64_t cap);
+typedef int (*emab_write_cb)(void *user, const char *text, uint64_t len);
+int emab_align_fastq_stream(emab_session_t *s, emab_read_cb r1, void *u1, emab_read_cb r2, void *u2, emab_write_cb w, void *uw, int batch_pairs);
 /* -x (multi-input) mode: n buckets with up to `workers` of them in flight on this GPU (each worker is a
  * CUDA stream + scratch, so one bucket's kernels overlap another's host work and copies).  sam[i] /
  * sam_len[i] are per bucket, in input order; cloud ids continue in input order. */

@@ -33,12 +33,26 @@ def _run_both(p, platform, in_flag, tmp_path, extra=(), env=None, threads="6"):
     return b1
 
 
-@pytest.mark.parametrize("platform,in_flag", [("haplotag", "-s"), ("dbs", "-s"), ("tru", "-1"), ("tellseq", "-1")])
+@pytest.mark.parametrize("platform,in_flag", [("haplotag", "-s"), ("dbs", "-s"), ("tru", "-1"), ("tellseq", "-1"), ("cpt", "-1")])
 def test_platform_sweep(platform, in_flag, tmp_path):
     cfg = "c1_rep"
     p = _data(cfg, platform)
     body = _run_both(p, platform, in_flag, tmp_path)
     assert any(b"\tBX:Z:" in l for l in body[:50])
+
+
+@pytest.mark.parametrize("platform,in_flag", [("tru", "-1"), ("haplotag", "-s"), ("tellseq", "-1"), ("cpt", "-1")])
+def test_platform_sweep_100mbp(platform, in_flag, tmp_path):
+    """BASELINE configs[3] on the reference it names: the 100 Mbp reference of configs[1] (10 x 10 Mbp, planted
+    duplications), one bucket of 20 barcodes x 200 pairs per platform.  The index is built once by emab_index_build
+    (tests/test_index_build.py pins its files to `bwa index`'s); both programs load it."""
+    from tools import synth
+    import ema_b200
+    if not os.path.exists(helpers.ref_bin("ema")):
+        pytest.skip("oracle/_ref/ema missing")
+    p = synth.build_config("c2", helpers.DATA_ROOT, None, platform=platform, indexer=ema_b200.index_build, n_barcodes=20, tag="_sweep")
+    body = _run_both(p, platform, in_flag, tmp_path)
+    assert len(body) == 2 * 20 * 200
 
 
 def test_10x_interleaved_fastq(tmp_path):

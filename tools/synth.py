@@ -227,11 +227,12 @@ def write_bucket(path: str, sim, *, platform="10x", shuffle=True):
 def write_interleaved_fastq(path: str, sim, *, platform="tru"):
     """Barcode-sorted interleaved FASTQ for `-1` mode.
     tru:     id ``@<int>_<name>`` (barcode = atoi, src/techs.c:57-61)
+    cpt:     id ``@name:bc<int>`` (barcode = atoi after the last ':' + 2 characters, src/techs.c:63-69)
     tellseq: id ``@name:<18-mer>`` (src/techs.c:33-55)
     10x:     id ``@name:<16-mer>`` (src/techs.c:19-30)"""
     rng = np.random.default_rng(sim["seed"] + 104729)
     nb = sim["n_barcodes"]
-    if platform == "tru":
+    if platform in ("tru", "cpt"):
         bcs = [str(i + 1).encode() for i in range(nb)]
     else:
         bcs = random_barcodes(nb, 18 if platform == "tellseq" else 16, rng)
@@ -243,6 +244,8 @@ def write_interleaved_fastq(path: str, sim, *, platform="tru"):
             b = bcs[bc_idx[i]]
             if platform == "tru":
                 rid = b"@" + b + b"_r" + str(i).encode()
+            elif platform == "cpt":   # extract_bc_cptseq (src/techs.c:63-69): atoi of what follows ":xx" at the end of the id
+                rid = b"@r" + str(i).encode() + b":bc" + b
             else:
                 rid = b"@r" + str(i).encode() + b":" + b
             out.append(rid + b"\n" + s1[i] + b"\n+\n" + q1 + b"\n" + rid + b"\n" + s2[i] + b"\n+\n" + q2 + b"\n")
@@ -268,13 +271,17 @@ CONFIGS = {
 }
 
 
-def build_config(name: str, root: str, bwa_bin: str | None = None, platform: str = "10x"):
+def build_config(name: str, root: str, bwa_bin: str | None = None, platform: str = "10x", indexer=None, n_barcodes: int | None = None,
+                 tag: str = ""):
     """Materialise a named config under ``root/name``; returns dict of paths.
-    The FM index is built with the reference's own ``bwa index`` (index construction is out of
-    scope for this repo) when ``bwa_bin`` is given and the index is absent."""
+    The FM index is built with the reference's own ``bwa index`` when ``bwa_bin`` is given and the index is absent, or by
+    ``indexer(fasta_path)`` (ema_b200.index_build: the same files, on the GPU) when that is given instead.
+    ``n_barcodes`` overrides the config's bucket size (the platform sweep uses small buckets on a large reference)."""
     import subprocess
     n_contigs, clen, rseed, dup, nbc, ppb, indel = CONFIGS[name]
-    d = os.path.join(root, name)
+    if n_barcodes:
+        nbc = n_barcodes
+    d = os.path.join(root, name + tag)
     os.makedirs(d, exist_ok=True)
     fa = os.path.join(d, "ref.fa")
     bucket = os.path.join(d, f"ema-bin-000.{platform}")
@@ -290,8 +297,11 @@ def build_config(name: str, root: str, bwa_bin: str | None = None, platform: str
             write_bucket(bucket, sim, platform=platform)
         else:
             write_interleaved_fastq(bucket, sim, platform=platform)
-    if bwa_bin and not os.path.exists(fa + ".sa"):
-        subprocess.run([bwa_bin, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if not os.path.exists(fa + ".sa"):
+        if indexer is not None:
+            indexer(fa)
+        elif bwa_bin:
+            subprocess.run([bwa_bin, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return dict(dir=d, fasta=fa, bucket=bucket, n_pairs=nbc * ppb)
 
 
