@@ -227,7 +227,13 @@ struct SeedJob {  // one read as the seeding loops see it
 //         QuadLists (device) keep them packed in shared memory.
 struct ThreadFm {
 	Fm &fm;
-	EMAB_HD Intv extend1(const Intv &ik, int c, int is_back) { return bwt_extend1(fm, ik, c, is_back); }
+	EMAB_HD Intv extend1(const Intv &ik, int c, int is_back, bool counted = true)
+	{
+		const unsigned before = fm.touches;
+		const Intv r = bwt_extend1(fm, ik, c, is_back);
+		if (!counted) fm.touches = before;
+		return r;
+	}
 	EMAB_HD const DevIndex &index() const { return fm.ix; }
 };
 struct PtrLists {
@@ -235,7 +241,18 @@ struct PtrLists {
 	EMAB_HD void put(int which, int idx, const Intv &v) { l[which][idx] = v; }
 	EMAB_HD Intv get(int which, int idx) const { return l[which][idx]; }
 	EMAB_HD void emit(Intv *out, int idx, const Intv &v) { out[idx] = v; }
+	EMAB_HD void put_by(int, int which, int idx, const Intv &v) { l[which][idx] = v; }
+	EMAB_HD void emit_by(int, Intv *out, int idx, const Intv &v) { out[idx] = v; }
 	EMAB_HD void sync() const {}
+};
+//   Coop  how many lanes work on one read.  The entries of one backward round of bwt_smem1a are extended independently of
+//         each other (bwa/bwt.c:328-345: only the bookkeeping after each bwt_extend is sequential), so a group of WIDTH
+//         lanes takes WIDTH entries per step, one per lane, and shares the few values the bookkeeping needs.  SoloCoop is
+//         one lane per read (WIDTH 1); QuadCoop (device) four.
+struct SoloCoop {
+	static constexpr int WIDTH = 1;
+	EMAB_HD int lane() const { return 0; }
+	EMAB_HD uint64_t bcast(uint64_t v, int) const { return v; }
 };
 
 // pass 2 re-seeds inside long, rare SMEMs of pass 1 (bwa/bwamem.c:157-168).  Whether an interval qualifies is known
@@ -266,9 +283,10 @@ struct Pass2Queue {
 	}
 };
 
-template <class Feeder, class FmT, class Lists>
-EMAB_HD void seed_p12(FmT &fm, Feeder &feed, Lists &lists)
+template <class Feeder, class FmT, class Lists, class Coop>
+EMAB_HD void seed_p12(FmT &fm, Feeder &feed, Lists &lists, const Coop &coop)
 {
+	constexpr int WIDTH = Coop::WIDTH;
 	SeedJob job;
 	job.seq = nullptr; job.len = 0; job.out = nullptr; job.cap = 0; job.id = -1;
 	int n = 0, ovf = 0;   // intervals kept so far for this read
@@ -284,6 +302,7 @@ EMAB_HD void seed_p12(FmT &fm, Feeder &feed, Lists &lists)
 	Intv ik;
 	ik.x0 = ik.x1 = ik.x2 = ik.info = 0;
 	int c = 0, back = 0;
+	bool counted = true;   // does this lane's next bwt_extend count as an Occ-block load of the reference's
 	for (;;) {
 		// ---- bookkeeping until the next bwt_extend is known (or the queue is empty)
 		bool req = false;
@@ -293,11 +312,12 @@ EMAB_HD void seed_p12(FmT &fm, Feeder &feed, Lists &lists)
 				if (feed.next(job)) { have_job = true; n = 0; ovf = 0; pass = 1; x = 0; st = SD_NEXT; q2.clear(); }
 				else drained = true;
 			}
-			if (st == SD_BWD && j == n_prev) {  // end of one backward round (bwa/bwt.c:346-348)
+			if (st == SD_BWD && j >= n_prev) {  // end of one backward round (bwa/bwt.c:346-348)
 				if (n_curr == 0) {  // the call is over
 					if (!in_p2) x = ret;
 					st = SD_NEXT;
 				} else {
+					lists.sync();   // entries of the next round were stored by their owner lanes
 					cur ^= 1;
 					n_prev = n_curr; n_curr = 0;
 					--i; rev = false;
@@ -363,13 +383,20 @@ EMAB_HD void seed_p12(FmT &fm, Feeder &feed, Lists &lists)
 					st = SD_NEXT;
 				} else { c = cc; back = 1; j = 0; last_size = 0; st = SD_BWD; }
 			}
-			if (st == SD_BWD && j < n_prev) { ik = lists.get(cur ^ 1, rev ? n_prev - 1 - j : j); req = true; }
+			if (st == SD_BWD && j < n_prev) {  // this lane's entry of the round: j + lane (the last one again past the end)
+				int jj = j + coop.lane();
+				counted = jj < n_prev;
+				jj = counted ? jj : n_prev - 1;
+				ik = lists.get(cur ^ 1, rev ? n_prev - 1 - jj : jj);
+				req = true;
+			}
 		}
 		// ---- the one convergent step.  On the device the warp votes here every iteration: the vote is
 		// the reconvergence point that brings all lanes to the bwt_extend below together.
 		if (!EMAB_WARP_ANY(req)) break;
 		if (!req) continue;
-		Intv ok = fm.extend1(ik, c, back);
+		if (st == SD_FWD) counted = coop.lane() == 0;   // the lanes of a group walk forward together: one block load to count
+		Intv ok = fm.extend1(ik, c, back, counted);
 		// ---- consume
 		if (st == SD_FWD) {  // bwa/bwt.c:307-315
 			bool stop = false;
@@ -387,23 +414,30 @@ EMAB_HD void seed_p12(FmT &fm, Feeder &feed, Lists &lists)
 				ik = ok;
 				++i;
 			}
-		} else {  // SD_BWD: bwa/bwt.c:328-345
-			if (ok.x2 < min_intv) {
-				if (n_curr == 0 && i + 1 < last_start) {
-					Intv p = ik;
-					p.info |= (uint64_t)(i + 1) << 32;
-					if ((int)(uint32_t)p.info - (i + 1) >= opt::min_seed_len) {
-						if (!in_p2) q2.consider(p, i + 1, n);
-						if (n < job.cap) lists.emit(job.out, n++, p); else ovf = 1;
+		} else {  // SD_BWD: bwa/bwt.c:328-345 for up to WIDTH entries of the round, in list order
+#pragma unroll
+			for (int t = 0; t < WIDTH; ++t) {
+				if (j + t >= n_prev) break;
+				const uint64_t ok_x2 = coop.bcast(ok.x2, t);
+				if (ok_x2 < min_intv) {
+					if (n_curr == 0 && i + 1 < last_start) {
+						const uint64_t p_info = coop.bcast(ik.info, t) | (uint64_t)(i + 1) << 32;
+						if ((int)(uint32_t)p_info - (i + 1) >= opt::min_seed_len) {
+							Intv p = ik;
+							p.info = p_info;
+							if (!in_p2) { Intv pq; pq.x2 = coop.bcast(ik.x2, t); pq.info = p_info; q2.consider(pq, i + 1, n); }
+							if (n < job.cap) lists.emit_by(t, job.out, n++, p); else ovf = 1;
+						}
+						last_start = i + 1;
 					}
-					last_start = i + 1;
+				} else if (n_curr == 0 || ok_x2 != last_size) {
+					Intv v = ok;
+					v.info = ik.info;
+					lists.put_by(t, cur, n_curr++, v);
+					last_size = ok_x2;
 				}
-			} else if (n_curr == 0 || ok.x2 != last_size) {
-				ok.info = ik.info;
-				lists.put(cur, n_curr++, ok);
-				last_size = ok.x2;
 			}
-			++j;
+			j += WIDTH;
 		}
 	}
 }
@@ -481,7 +515,7 @@ EMAB_HD int collect_intv(Fm &fm, int len, const uint8_t *seq, Intv *mem, int mem
 	OneReadFeeder f12{{seq, len, mem, mem_cap, 0}, false, 0, 0}, f3{{seq, len, p3, EMAB_P3_CAP, 0}, false, 0, 0};
 	ThreadFm tfm{fm};
 	PtrLists lists{{buf0, buf1}};
-	seed_p12(tfm, f12, lists);
+	seed_p12(tfm, f12, lists, SoloCoop());
 	seed_p3(tfm, f3, lists);
 	const int n = finish_intv(mem, f12.n, p3, f3.n, mem_cap);
 	if (f12.ovf || f3.ovf || n < 0) { *overflow = 1; return f12.n; }
@@ -537,8 +571,8 @@ __device__ __forceinline__ void seed_warp(const DevIndex &ix, const SeedBatch &b
 	QueueFeeder f12{b, 0}, f3{b, 1};
 	ThreadFm tfm{fm};
 	PtrLists lists{{buf0, buf0 + b.scratch_len}};
-	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(tfm, f3, lists); seed_p12(tfm, f12, lists); }
-	else { seed_p12(tfm, f12, lists); seed_p3(tfm, f3, lists); }
+	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(tfm, f3, lists); seed_p12(tfm, f12, lists, SoloCoop()); }
+	else { seed_p12(tfm, f12, lists, SoloCoop()); seed_p3(tfm, f3, lists); }
 	unsigned touches = fm.touches;
 	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
 	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(b.touches, (unsigned long long)touches);

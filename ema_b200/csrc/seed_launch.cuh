@@ -27,6 +27,15 @@ k_seed_quad(DevIndex ix, SeedBatch b)
 	seed_quads(ix, b, seedq_smem);
 }
 
+// four lanes per read, one backward-round entry per lane (seed_quad.cuh: seed_quads_wide)
+template <int MIN_BLOCKS>
+static __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS)
+k_seed_wide(DevIndex ix, SeedBatch b)
+{
+	extern __shared__ uint4 seedq_smem[];
+	seed_quads_wide(ix, b, seedq_smem);
+}
+
 // one lane per read, Occ blocks staged through shared memory by cp.async (seed_quad.cuh: StagedFm)
 template <int MIN_BLOCKS>
 static __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS)
@@ -61,14 +70,14 @@ k_seed_finish(SeedBatch b, int32_t *n_intv, int32_t *occ_cnt)
 static inline int seed_mode()
 {
 	static int v = 0;
-	if (!v) { const char *e = getenv("EMAB_SEED_MODE"); v = e ? atoi(e) : 1; if (v != 2 && v != 4) v = 1; }
+	if (!v) { const char *e = getenv("EMAB_SEED_MODE"); v = e ? atoi(e) : 3; if (v < 1 || v > 4) v = 3; }
 	return v;
 }
 // EMAB_SEED_BPS: resident 128-thread blocks per SM of the persistent seeding grid (tuning knob)
 static inline int seed_blocks_per_sm()
 {
 	static int v = 0;
-	if (!v) { const char *e = getenv("EMAB_SEED_BPS"); v = e ? atoi(e) : 0; if (v < 1 || v > 16) v = seed_mode() == 4 ? 8 : 6; }
+	if (!v) { const char *e = getenv("EMAB_SEED_BPS"); v = e ? atoi(e) : 0; if (v < 1 || v > 16) v = seed_mode() == 4 ? 8 : (seed_mode() == 3 ? 5 : 6); }
 	return v;
 }
 
@@ -78,7 +87,7 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
                        int32_t *d_n_intv, int32_t *d_occ_cnt, int *d_err, unsigned long long *d_touches, int *launches)
 {
 	cudaStream_t st = c->stream;
-	const bool quad = seed_mode() == 4;
+	const bool quad = seed_mode() == 4 || seed_mode() == 3;
 	int grid = c->n_sm * seed_blocks_per_sm();
 	const int per_block = quad ? SEED_BLOCK / 4 : SEED_BLOCK;                // reads in flight per block
 	const int want = (2 * R + per_block - 1) / per_block;  // never more lanes than (read, role) items
@@ -97,7 +106,11 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
 	b.n12 = (int32_t *)(b.queue + 2); b.n3 = b.n12 + R;
 	b.err = d_err; b.touches = d_touches;
 	CUDA_TRY(cudaMemsetAsync(b.queue, 0, 16, st));
-	if (quad) {
+	if (seed_mode() == 3) {
+		if (c->ix->d.seq_len >> 39) { snprintf(emab_errbuf, sizeof emab_errbuf, "reference too long for the packed interval lists (2^39)"); return EMAB_ERR_ARG; }
+		if (seed_blocks_per_sm() >= 6) k_seed_wide<6><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
+		else k_seed_wide<5><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
+	} else if (quad) {
 		if (c->ix->d.seq_len >> 39) { snprintf(emab_errbuf, sizeof emab_errbuf, "reference too long for the packed interval lists (2^39)"); return EMAB_ERR_ARG; }
 		if (seed_blocks_per_sm() >= 10) k_seed_quad<10><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
 		else if (seed_blocks_per_sm() >= 8) k_seed_quad<8><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);

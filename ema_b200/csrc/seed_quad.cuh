@@ -53,7 +53,7 @@ struct QuadFm {
 	}
 
 	// the interval of base c after bwt_extend(ik) (bwa/bwt.c:262-275 + bwt_2occ4 :189-220); info is left 0
-	__device__ Intv extend1(const Intv &ik, int c, int is_back)
+	__device__ Intv extend1(const Intv &ik, int c, int is_back, bool = true)
 	{
 		const uint64_t NEG1 = ~0ull;
 		const uint64_t xa = is_back ? ik.x0 : ik.x1, xb = is_back ? ik.x1 : ik.x0;
@@ -131,7 +131,18 @@ struct QuadLists {
 		const uint64_t comp = q == 0 ? v.x0 : (q == 1 ? v.x1 : (q == 2 ? v.x2 : v.info));
 		((uint64_t *)(out + idx))[q] = comp;
 	}
-	__device__ __forceinline__ void sync() const { __syncwarp(qmask); }   // before reading back what emit() stored
+	// one lane of the quad stores its own value (the others hold different ones); readers sync() first
+	__device__ __forceinline__ void put_by(int owner, int which, int idx, const Intv &v) { if (q == owner) put(which, idx, v); }
+	__device__ __forceinline__ void emit_by(int owner, Intv *out, int idx, const Intv &v) { if (q == owner) out[idx] = v; }
+	__device__ __forceinline__ void sync() const { __syncwarp(qmask); }   // before reading what another lane stored
+};
+
+struct QuadCoop {
+	static constexpr int WIDTH = 4;
+	int q;
+	unsigned qmask;
+	__device__ __forceinline__ int lane() const { return q; }
+	__device__ __forceinline__ uint64_t bcast(uint64_t v, int t) const { return __shfl_sync(qmask, v, ((threadIdx.x & 31) & ~3) + t); }
 };
 
 struct QuadFeeder {
@@ -160,6 +171,36 @@ struct QuadFeeder {
 		}
 	}
 };
+
+// ---------------------------------------------------------------------------------------------
+// FOUR LANES PER READ, ONE LIST ENTRY PER LANE (the form the pipeline runs).  What bounds seeding is not bandwidth but
+// the longest reads' chains of dependent bwt_extend calls (a kernel of 3 blocks per SM is as fast as one of 6,
+// profiles/r2f_*), and most links of those chains are backward rounds of bwt_smem1a over a dozen intervals whose
+// extensions do not depend on each other.  A quad takes four entries of a round per step — each lane a whole
+// bwt_extend of its own entry, registers and loads as in the one-lane form — and exchanges only the interval sizes
+// the bookkeeping needs (QuadCoop::bcast).  On BASELINE configs[1] reads that shortens the passes-1/2 chain from 457
+// to 257 steps on average and from 1369 to 570 at the maximum (tests/hostsim hs_seed_profile).  Forward sweeps have one
+// extension per step: the four lanes compute it together (same addresses, one request).  Pass 3 has no such
+// parallelism and keeps one lane per read on its own warps.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void seed_quads_wide(const DevIndex &ix, const SeedBatch &b, uint4 *smem)
+{
+	const int quad = threadIdx.x >> 2, q = threadIdx.x & 3;
+	const unsigned qmask = 0xfu << ((threadIdx.x & 31) & ~3);
+	const size_t gquad = (size_t)blockIdx.x * (blockDim.x >> 2) + quad;
+	Fm fm{ix, 0};
+	ThreadFm tfm{fm};
+	QuadLists lists{smem + quad * SEEDQ_STRIDE, b.scratch + gquad * 2 * b.scratch_len, b.scratch_len, q, qmask};
+	QuadCoop coop{q, qmask};
+	QuadFeeder f12{b, 0, q, qmask};
+	QueueFeeder f3{b, 1};
+	PtrLists none{{nullptr, nullptr}};
+	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(tfm, f3, none); seed_p12(tfm, f12, lists, coop); }
+	else { seed_p12(tfm, f12, lists, coop); seed_p3(tfm, f3, none); }
+	unsigned touches = fm.touches;
+	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
+	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(b.touches, (unsigned long long)touches);
+}
 
 // ---------------------------------------------------------------------------------------------
 // One lane per read, Occ blocks STAGED IN SHARED MEMORY by cp.async: the eight 16-byte pieces of a step's two blocks
@@ -206,7 +247,7 @@ struct StagedFm {
 		cnt[3] = valid ? ((uint64_t)c1.w << 32 | c1.z) + nt : 0;
 	}
 
-	__device__ Intv extend1(const Intv &ik, int c, int is_back)
+	__device__ Intv extend1(const Intv &ik, int c, int is_back, bool counted = true)
 	{
 		const DevIndex &ix = fm.ix;
 		const uint64_t NEG1 = ~0ull;
@@ -221,7 +262,7 @@ struct StagedFm {
 		for (int p = 0; p < 4; ++p) cp_async16(slot + p * stride, pk + p, true);
 #pragma unroll
 		for (int p = 0; p < 4; ++p) cp_async16(slot + (4 + p) * stride, pl + p, other);
-		fm.touches += (unsigned)kv + (unsigned)(lv && !(kv && bk == bl));
+		if (counted) fm.touches += (unsigned)kv + (unsigned)(lv && !(kv && bk == bl));
 		cp_async_wait_all();
 		uint64_t tk[4], tl[4];
 		occ4(0, (int)(_k & 127), kv, tk);
@@ -253,8 +294,8 @@ __device__ __forceinline__ void seed_staged(const DevIndex &ix, const SeedBatch 
 	Intv *buf0 = b.scratch + (size_t)gt * 2 * b.scratch_len;
 	PtrLists lists{{buf0, buf0 + b.scratch_len}};
 	QueueFeeder f12{b, 0}, f3{b, 1};
-	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(sfm, f3, lists); seed_p12(sfm, f12, lists); }
-	else { seed_p12(sfm, f12, lists); seed_p3(sfm, f3, lists); }
+	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(sfm, f3, lists); seed_p12(sfm, f12, lists, SoloCoop()); }
+	else { seed_p12(sfm, f12, lists, SoloCoop()); seed_p3(sfm, f3, lists); }
 	unsigned touches = fm.touches;
 	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
 	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(b.touches, (unsigned long long)touches);
@@ -271,8 +312,8 @@ __device__ __forceinline__ void seed_quads(const DevIndex &ix, const SeedBatch &
 	QuadFm fm{ix, q, qmask, 0};
 	QuadLists lists{smem + quad * SEEDQ_STRIDE, b.scratch + gquad * 2 * b.scratch_len, b.scratch_len, q, qmask};
 	QuadFeeder f12{b, 0, q, qmask}, f3{b, 1, q, qmask};
-	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(fm, f3, lists); seed_p12(fm, f12, lists); }
-	else { seed_p12(fm, f12, lists); seed_p3(fm, f3, lists); }
+	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(fm, f3, lists); seed_p12(fm, f12, lists, SoloCoop()); }
+	else { seed_p12(fm, f12, lists, SoloCoop()); seed_p3(fm, f3, lists); }
 	unsigned touches = fm.touches;
 	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
 	if ((threadIdx.x & 31) == 0 && touches) atomicAdd(b.touches, (unsigned long long)touches);

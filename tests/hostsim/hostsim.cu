@@ -149,6 +149,50 @@ int64_t hs_collect_intv_touches(void *h_, int len, const uint8_t *seq)
 	return fm.touches;
 }
 
+// Seeding work profile of one read (measurement aid for DESIGN.md: what bounds k_seed).  out[0] = bwt_extend calls of
+// passes 1+2, out[1] = of pass 3, out[2] = backward rounds, out[3] = dependent steps of passes 1+2 if the (independent)
+// extensions of one backward round ran four at a time, out[4] = largest prev list.
+struct CountingFm {
+	Fm &fm;
+	int64_t calls = 0;
+	Intv extend1(const Intv &ik, int c, int is_back, bool = true) { ++calls; return bwt_extend1(fm, ik, c, is_back); }
+	const DevIndex &index() const { return fm.ix; }
+};
+struct ProfilingLists {
+	PtrLists base;
+	int last_which = -1, last_idx = -100, run = 0;
+	int64_t rounds = 0, par4 = 0, serial = 0, longest = 0;
+	void close_run() { if (run) { ++rounds; par4 += (run + 3) / 4; serial += run; if (run > longest) longest = run; } run = 0; }
+	void put(int which, int idx, const Intv &v) { base.put(which, idx, v); }
+	Intv get(int which, int idx)
+	{
+		const int d = idx - last_idx;
+		if (which != last_which || (d != 1 && d != -1)) close_run();
+		++run; last_which = which; last_idx = idx;
+		return base.get(which, idx);
+	}
+	void emit(Intv *out, int idx, const Intv &v) { out[idx] = v; }
+	void put_by(int, int which, int idx, const Intv &v) { base.put(which, idx, v); }
+	void emit_by(int, Intv *out, int idx, const Intv &v) { out[idx] = v; }
+	void sync() const {}
+};
+int hs_seed_profile(void *h_, int len, const uint8_t *seq, int64_t *out)
+{
+	HostIndex *h = (HostIndex *)h_;
+	std::vector<Intv> mem(4096), p3(EMAB_P3_CAP), b0(EMAB_MAX_READ_LEN + 1), b1(EMAB_MAX_READ_LEN + 1);
+	Fm fm{h->d, 0};
+	CountingFm c12{fm}, c3{fm};
+	ProfilingLists lists{PtrLists{{b0.data(), b1.data()}}};
+	OneReadFeeder f12{{seq, len, mem.data(), 4096, 0}, false, 0, 0}, f3{{seq, len, p3.data(), EMAB_P3_CAP, 0}, false, 0, 0};
+	seed_p12(c12, f12, lists, SoloCoop());
+	lists.close_run();
+	seed_p3(c3, f3, lists);
+	out[0] = c12.calls; out[1] = c3.calls; out[2] = lists.rounds;
+	out[3] = c12.calls - lists.serial + lists.par4;
+	out[4] = lists.longest;
+	return f12.n;
+}
+
 struct ReadWork {
 	std::vector<Intv> intv, b0, b1;
 	std::vector<Seed> w_seeds, seeds;

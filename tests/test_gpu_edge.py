@@ -72,7 +72,7 @@ def test_read_with_many_sa_intervals(tmp_path):
     lines.append(bc + b" @engineered " + synth.ACGT[read].tobytes() + b" " + b"I" * L + b" " + mate + b" " + b"I" * 150)
     open(bucket, "wb").write(b"\n".join(lines) + b"\n")
     ctx = ema_b200.Context(ema_b200.Index(fa))
-    ivs, _ = ema_b200.smem_batch(ctx, [helpers.nt4(synth.ACGT[read].tobytes())], max_intv=1024)
+    ivs, _ = ema_b200.smem_batch(ctx, [helpers.nt4(synth.ACGT[read].tobytes())], max_intv=8192)
     assert len(ivs[0]) > 128, "the construction should exceed the default capacity (got %d intervals)" % len(ivs[0])
     body = _compare(["-s", bucket, "-r", fa, "-p", "10x"], tmp_path, min_records=2 * 241)
     assert any(l.startswith(b"engineered\t") for l in body)
