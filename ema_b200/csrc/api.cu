@@ -197,7 +197,8 @@ extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
 	CUDA_TRY(cudaEventCreate(&c->ev0));
 	CUDA_TRY(cudaEventCreate(&c->ev1));
 	CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
-	if (const char *e = getenv("EMAB_SYNC")) c->spin_wait = strcmp(e, "block") != 0;
+	if (const char *e = getenv("EMAB_SYNC")) c->wait_mode = strcmp(e, "block") == 0 ? 2 : (strcmp(e, "spin") == 0 ? 1 : 0);
+	if (const char *e = getenv("EMAB_SPIN_US")) c->spin_us = atoi(e);
 	CUDA_TRY(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));

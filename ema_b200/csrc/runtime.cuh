@@ -68,7 +68,8 @@ struct emab_ctx {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaEvent_t stage_ev[16] = {};
 	cudaEvent_t ev_wait = nullptr;   // cudaEventBlockingSync: see ctx_wait()
-	bool spin_wait = true;           // EMAB_SYNC=block sleeps on a blocking-sync event instead
+	int wait_mode = 0;               // 0: poll briefly, then sleep between polls; 1: spin (cudaStreamSynchronize); 2: blocking-sync event
+	int spin_us = 150;               // how long mode 0 polls before it starts sleeping (EMAB_SPIN_US)
 	double last_ms = 0;
 	int last_launches = 0;
 	DevBuf b[48];            // device scratch slots, meaning assigned by each entry point
@@ -90,15 +91,33 @@ struct emab_ctx {
 // thread) starts on device 0, and a stream or buffer of another device is an invalid argument there
 #define CTX_ENTER(c) do { if (c) CUDA_TRY(cudaSetDevice((c)->device)); } while (0)
 
-// Wait for the ctx's stream.  cudaStreamSynchronize spins on a host core while the kernels run; EMAB_SYNC=block
-// sleeps on a blocking-sync event instead.  Measured on the 16-core box with 8 buckets in flight the spin is the
-// faster one end to end (10.2 vs 11.1 ms per bucket: the wake-up latency of four waits per bucket costs more than
-// the cores the spin takes from parsing and SAM formatting), so it is the default; boxes with fewer cores per GPU
-// may prefer `block`.
+// Wait for the ctx's stream.  cudaStreamSynchronize spins on a host core for as long as the kernels run — with several
+// buckets in flight that is several cores taken from parsing and SAM formatting (on the 16-core box a fifth of the CPU
+// time of an end-to-end run, and with 4 cores per GPU on an 8-GPU node most of it).  A blocking-sync event frees the core
+// but wakes up late (a wait per ~2 ms stage: 11.1 vs 10.2 ms per bucket, round 1).  So: poll the stream for a short
+// while — most waits inside a bucket are for kernels of a few hundred microseconds — then sleep between polls.
+// EMAB_SYNC=spin / block select the pure forms.
+#include <time.h>
 static inline cudaError_t ctx_wait(emab_ctx *c)
 {
-	if (c->spin_wait || !c->ev_wait) return cudaStreamSynchronize(c->stream);
-	cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
-	if (e != cudaSuccess) return e;
-	return cudaEventSynchronize(c->ev_wait);
+	if (c->wait_mode == 1) return cudaStreamSynchronize(c->stream);
+	if (c->wait_mode == 2 && c->ev_wait) {
+		cudaError_t e = cudaEventRecord(c->ev_wait, c->stream);
+		if (e != cudaSuccess) return e;
+		return cudaEventSynchronize(c->ev_wait);
+	}
+	struct timespec t0, t;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int polls = 0;; ++polls) {
+		const cudaError_t e = cudaStreamQuery(c->stream);
+		if (e != cudaErrorNotReady) return e;
+		if ((polls & 15) == 15) {
+			clock_gettime(CLOCK_MONOTONIC, &t);
+			const long long us = (t.tv_sec - t0.tv_sec) * 1000000LL + (t.tv_nsec - t0.tv_nsec) / 1000;
+			if (us > c->spin_us) {   // the short spin is over: give the core away between polls
+				const struct timespec nap = {0, 30000};
+				nanosleep(&nap, nullptr);
+			}
+		}
+	}
 }
