@@ -1303,10 +1303,90 @@ static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size
 	return rc;
 }
 
+// One bucket over several GPUs (fewer buckets than GPUs).  The bucket's pairs — already sorted by barcode —
+// are cut at barcode boundaries into one part per worker; the parts run concurrently on the session's index replicas
+// and their SAM texts are joined in order.  Cloud ids stay those of the serial run: the parts take their tickets in
+// order and every part draws its ids after the parts before it (init_cloud's counter, src/align.c:19-23), which is the
+// exclusive prefix sum of clouds per part.
+static int align_pairs_split(Session *s, const std::vector<Pair> &pairs, char **out, size_t *out_len)
+{
+	const size_t n = pairs.size();
+	const int W = (int)s->workers.size();
+	std::vector<size_t> cut{0};
+	for (int k = 1; k < W; ++k) {
+		size_t at = n * (size_t)k / (size_t)W;
+		while (at < n && at > 0 && pairs[at].bc == pairs[at - 1].bc) ++at;   // never inside a barcode
+		if (at > cut.back() && at < n) cut.push_back(at);
+	}
+	cut.push_back(n);
+	const int P = (int)cut.size() - 1;
+	std::vector<int> tickets(P);
+	for (int k = 0; k < P; ++k) tickets[k] = s->new_ticket();
+	for (int k = 0; k < PH_COUNT; ++k) s->gate[k].cap = P;
+	std::vector<char *> texts(P, nullptr);
+	std::vector<size_t> lens(P, 0);
+	std::vector<int> rcs(P, 0);
+	std::vector<std::string> errs(P);
+	std::vector<emab_run_stats_t> sts(P);
+	auto body = [&](int k) {
+		Worker &wk = s->workers[k];
+		emab_ctx_make_current(wk.ctx);
+		wk.n_threads = std::max(1, s->n_threads / P);
+		memset(&sts[k], 0, sizeof sts[k]);
+		try {
+			GatePass gp(s, tickets[k]);
+			gp.to(PH_PARSE);
+			std::vector<Pair> part(pairs.begin() + (ptrdiff_t)cut[k], pairs.begin() + (ptrdiff_t)cut[k + 1]);
+			rcs[k] = process_pairs(s, wk, gp, part, &texts[k], &lens[k], sts[k]);
+			if (rcs[k]) errs[k] = wk.err;
+		} catch (const std::bad_alloc &) { rcs[k] = EMAB_ERR_NOMEM; errs[k] = "out of host memory"; s->pass_cloud_turn(tickets[k]); }
+		std::lock_guard<std::mutex> g(s->mu);
+		++s->device_buckets[wk.dev_slot];
+	};
+	std::vector<std::thread> th;
+	for (int k = 1; k < P; ++k) th.emplace_back(body, k);
+	body(0);
+	for (auto &t : th) t.join();
+	memset(&s->last, 0, sizeof s->last);
+	size_t total = 0;
+	int rc = 0;
+	for (int k = 0; k < P; ++k) {
+		if (rcs[k] && !rc) { rc = rcs[k]; s->err = errs[k]; }
+		total += lens[k];
+		double *a = &s->last.parse_ms; const double *b = &sts[k].parse_ms;
+		for (int i = 0; i < 16; ++i) a[i] += b[i];
+		int64_t *ai = &s->last.h2d_bytes; const int64_t *bi = &sts[k].h2d_bytes;
+		for (int i = 0; i < 11; ++i) ai[i] += bi[i];
+		s->last.launches += sts[k].launches;
+	}
+	char *buf = rc ? nullptr : text_alloc(total + 1);
+	if (!rc && !buf) { rc = EMAB_ERR_NOMEM; s->err = "out of memory"; }
+	size_t at = 0;
+	for (int k = 0; k < P; ++k) {
+		if (buf && lens[k]) { memcpy(buf + at, texts[k], lens[k]); at += lens[k]; }
+		text_free(texts[k]);
+	}
+	if (rc) return rc;
+	buf[total] = 0;
+	*out = buf; *out_len = total;
+	return EMAB_OK;
+}
+
 int align_special_fastq(Session *s, const char *data, size_t len, char **out, size_t *out_len)
 {
 	s->workers[0].n_threads = s->n_threads;
 	std::string err;
+	if (s->replicas.size() > 1 && s->workers.size() > 1) {  // several GPUs, one bucket: split it
+		std::vector<Pair> pairs;
+		int rc = parse_bucket(s, s->n_threads, data, len, pairs, &err);
+		if (rc) { s->err = err; return rc; }
+		if (pairs.size() >= 2000) return align_pairs_split(s, pairs, out, out_len);
+		GatePass gp(s, s->new_ticket());
+		gp.to(PH_PARSE);
+		rc = process_pairs(s, s->workers[0], gp, pairs, out, out_len, s->last);
+		if (rc) s->err = s->workers[0].err;
+		return rc;
+	}
 	int rc = run_bucket(s, s->workers[0], s->new_ticket(), data, len, out, out_len, s->last, &err);
 	if (rc) s->err = err;
 	return rc;

@@ -168,3 +168,22 @@ def test_multi_device_session_matches_serial(tmp_path):
     assert "buckets per device" in r.stderr, r.stderr[-500:]
     _, body = split_sam(out.read_bytes())
     assert b"\n".join(body) + b"\n" == b"".join(serial)
+
+
+def test_single_bucket_split_over_replicas():
+    """fewer buckets than GPUs: one bucket is cut at barcode boundaries into one part per worker, the parts
+    run on the session's index replicas concurrently, and the joined SAM — cloud ids included — is the serial run's."""
+    import torch
+    import ema_b200
+    from tools import synth
+    if not os.path.exists(helpers.ref_bin("bwa")):
+        pytest.skip("oracle/_ref/bwa missing")
+    p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    data = open(p["bucket"], "rb").read()
+    serial = ema_b200.Session(p["fasta"], "10x", threads=8).align_bucket(data)
+    s2 = ema_b200.Session(p["fasta"], "10x", threads=8)
+    s2.add_device(1 if torch.cuda.device_count() > 1 else 0)
+    s2.set_workers(4)
+    split = s2.align_bucket(data)
+    assert split == serial
+    assert s2.align_bucket(data).count(b"\n") == serial.count(b"\n")
