@@ -279,7 +279,7 @@ class RunStats(C.Structure):
                [(n, C.c_int64) for n in ("n_pairs", "n_barcodes", "n_cands", "n_clouds", "sam_bytes", "extend_cells", "global_cells",
                                          "local_cells", "occ_touches")] + [("launches", C.c_int32), ("pad", C.c_int32)] + \
                [(n, C.c_int64) for n in ("ext_planned_cells", "ext_unplanned", "glob_planned_cells", "glob_unplanned")] + \
-               [("ms_ext_wave", C.c_double), ("ms_glob_wave", C.c_double)]
+               [("ms_ext_wave", C.c_double), ("ms_glob_wave", C.c_double), ("format_kernel_ms", C.c_double)]
 
 
 class Session:

@@ -187,10 +187,10 @@ extern "C" int emab_em_batch(emab_ctx_t *c, const emab_em_problem_t *h, double *
 	size_t total = 0;
 	for (Part &q : parts) { q.off = total; total += (q.bytes + 255) & ~(size_t)255; }
 	TRY(c->h[4].ensure(total + 256));
-	TRY(b[0].ensure(total + 256));
+	TRY(b[41].ensure(total + 256));   // slots 41-44: the pipeline's slots (reads, candidates, CIGARs) stay valid for emab_sam_format
 	for (const Part &q : parts) if (q.bytes) memcpy((char *)c->h[4].p + q.off, q.src, q.bytes);
-	CUDA_TRY(cudaMemcpyAsync(b[0].p, c->h[4].p, total, cudaMemcpyHostToDevice, c->stream));
-	char *d0 = (char *)b[0].p;
+	CUDA_TRY(cudaMemcpyAsync(b[41].p, c->h[4].p, total, cudaMemcpyHostToDevice, c->stream));
+	char *d0 = (char *)b[41].p;
 	P.bc_entry_off = (const int32_t *)(d0 + parts[0].off); P.bc_cloud_off = (const int32_t *)(d0 + parts[1].off);
 	P.bc_group_off = (const int32_t *)(d0 + parts[2].off); P.bc_unit_off = (const int32_t *)(d0 + parts[3].off);
 	P.bc_full_em = (const int32_t *)(d0 + parts[4].off); P.entry_cand_off = (const int32_t *)(d0 + parts[5].off);
@@ -205,9 +205,9 @@ extern "C" int emab_em_batch(emab_ctx_t *c, const emab_em_problem_t *h, double *
 		c->em_log_ready = true;
 	}
 	P.log_n = b[30].as<double>();
-	TRY(b[19].ensure((size_t)K * 8));                          P.gamma = b[19].as<double>();
-	TRY(b[20].ensure((size_t)K * 8));                          P.cw = b[20].as<double>();
-	TRY(b[21].ensure((size_t)C * 16 + 16));                    P.exp_cov = b[21].as<double>(); P.weight = P.exp_cov + C;
+	TRY(b[42].ensure((size_t)K * 8));                          P.gamma = b[42].as<double>();
+	TRY(b[43].ensure((size_t)K * 8));                          P.cw = b[43].as<double>();
+	TRY(b[44].ensure((size_t)C * 16 + 16));                    P.exp_cov = b[44].as<double>(); P.weight = P.exp_cov + C;
 	TRY(c->h[5].ensure((size_t)K * 8 + 8));
 	CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
 	CUDA_TRY(cudaEventRecord(c->ev0, c->stream));

@@ -41,41 +41,47 @@ namespace emab {
 namespace {
 struct BlockHdr { size_t cap; uint64_t magic; };
 constexpr uint64_t BLOCK_MAGIC = 0x656d6162424c4b31ull;
+constexpr uint64_t BLOCK_MAGIC_PINNED = 0x656d6162424c4b50ull;   // page-locked: the device writes SAM text straight into it
 constexpr size_t POOL_MIN = 1u << 20;
 std::mutex g_pool_mu;
 std::vector<BlockHdr *> g_pool;
 }
 
-char *text_alloc(size_t n)
+static char *block_alloc(size_t n, bool pinned)
 {
 	BlockHdr *h = nullptr;
+	const uint64_t magic = pinned ? BLOCK_MAGIC_PINNED : BLOCK_MAGIC;
 	if (n >= POOL_MIN) {
 		std::lock_guard<std::mutex> lk(g_pool_mu);
 		size_t best = g_pool.size();
 		for (size_t i = 0; i < g_pool.size(); ++i)
-			if (g_pool[i]->cap >= n && g_pool[i]->cap <= 2 * n && (best == g_pool.size() || g_pool[i]->cap < g_pool[best]->cap)) best = i;
+			if (g_pool[i]->magic == magic && g_pool[i]->cap >= n && g_pool[i]->cap <= 2 * n && (best == g_pool.size() || g_pool[i]->cap < g_pool[best]->cap)) best = i;
 		if (best < g_pool.size()) { h = g_pool[best]; g_pool[best] = g_pool.back(); g_pool.pop_back(); }
 	}
 	if (!h) {
 		const size_t cap = n >= POOL_MIN ? n + n / 8 : n;
-		h = (BlockHdr *)malloc(sizeof(BlockHdr) + cap + 1);
+		h = (BlockHdr *)(pinned ? emab_pinned_alloc(sizeof(BlockHdr) + cap + 1) : malloc(sizeof(BlockHdr) + cap + 1));
 		if (!h) return nullptr;
-		h->cap = cap; h->magic = BLOCK_MAGIC;
+		h->cap = cap; h->magic = magic;
 	}
 	return (char *)(h + 1);
 }
+char *text_alloc(size_t n) { return block_alloc(n, false); }
+// page-locked blocks (recycled like the others: pinning 30 MB costs milliseconds) for text the device delivers
+char *text_alloc_pinned(size_t n) { return block_alloc(n < POOL_MIN ? POOL_MIN : n, true); }
 
 void text_free(void *p)
 {
 	if (!p) return;
 	BlockHdr *h = (BlockHdr *)p - 1;
-	if (h->magic != BLOCK_MAGIC) { fprintf(stderr, "emab_free: not a block returned by this library\n"); return; }
+	if (h->magic != BLOCK_MAGIC && h->magic != BLOCK_MAGIC_PINNED) { fprintf(stderr, "emab_free: not a block returned by this library\n"); return; }
 	if (h->cap >= POOL_MIN) {
 		std::lock_guard<std::mutex> lk(g_pool_mu);
-		if (g_pool.size() < 32) { g_pool.push_back(h); return; }
+		if (g_pool.size() < 48) { g_pool.push_back(h); return; }
 	}
+	const bool pinned = h->magic == BLOCK_MAGIC_PINNED;
 	h->magic = 0;
-	free(h);
+	if (pinned) emab_pinned_free(h); else free(h);
 }
 
 // glibc serves blocks above its mmap threshold (128 KB, growing to at most 32 MB) straight from mmap and gives them
@@ -231,6 +237,12 @@ int session_set_workers(Session *s, int n_workers)
 		int rc = emab_ctx_create(s->replicas[slot], &s->workers.back().ctx);
 		if (rc) { s->err = emab_last_error(); s->workers.pop_back(); return rc; }
 		emab_set_error_rate(s->workers.back().ctx, s->tech->error_rate);
+		{   // what the device formatter needs of the session: contig names as the .fai has them, index contig -> name
+			std::vector<const char *> names;
+			for (const std::string &nm : s->fai_names) names.push_back(nm.c_str());
+			rc = emab_sam_tables(s->workers.back().ctx, (int)names.size(), names.data(), (int)s->rid2chrom.size(), s->rid2chrom.data());
+			if (rc) { s->err = emab_last_error(); emab_ctx_free(s->workers.back().ctx); s->workers.pop_back(); return rc; }
+		}
 	}
 	return EMAB_OK;
 }
@@ -274,8 +286,6 @@ int session_open(const char *ref_path, const char *platform, int device, Session
 	int rc = emab_index_load(ref_path, device, &s->ix);
 	if (!rc) { s->replicas.push_back(s->ix); s->device_ids.push_back(device); s->device_buckets.push_back(0); }
 	if (rc) { *err = std::string("error: could not load reference at ") + ref_path + ": " + emab_last_error(); delete s; return rc; }
-	rc = session_set_workers(s, 1);
-	if (rc) { *err = s->err; emab_index_free(s->ix); delete s; return rc; }
 	int64_t info[12];
 	emab_index_info(s->ix, info);
 	for (int i = 0; i < (int)info[1]; ++i) {
@@ -291,6 +301,8 @@ int session_open(const char *ref_path, const char *platform, int device, Session
 		if (found < 0) { *err = std::string("error: contig ") + name + " is not in the .fai"; session_close(s); return EMAB_ERR_ARG; }
 		s->rid2chrom.push_back(found);
 	}
+	rc = session_set_workers(s, 1);   // after the contig tables: every worker's ctx gets a copy for the device formatter
+	if (rc) { *err = s->err; session_close(s); return rc; }
 	*out = s;
 	return EMAB_OK;
 }
@@ -342,7 +354,7 @@ struct Rec {  // SAMRecord (include/samrecord.h:22-58), fields on the path only
 	uint8_t mate, rev, duplicate, unique, active, visited;
 	int pair;                 // index of the pair inside its barcode
 	const emab_cand_t *aln;
-	const uint32_t *cig;      // aln's CIGAR ops
+	int cand;                 // aln's index among the batch's candidates (what the device formatter is told)
 	double gamma;
 	int cloud;                // index into Barcode::clouds
 	int selected_mate;        // record index or -1
@@ -436,7 +448,7 @@ struct Barcode {
 	uint32_t slot_mask = 0;
 	std::vector<int> final_;               // records_final
 	std::vector<std::vector<int>> opt_jobs; // -d: name-sorted records of each bad cloud, in cloud order (see process_pairs)
-	TextBuf sam;
+	int n_out = 0;                         // pairs this barcode prints (two SAM records each)
 	std::string bc_str;                    // decode_bc(bc), printed in every BX tag of this barcode
 
 	void dict_init(size_t n_keys)
@@ -776,20 +788,18 @@ static const char *rc_table()
 	return tab.t;
 }
 
-static void print_sam_record(const Session *s, const Barcode &b, const std::vector<Pair> &pairs, int ri, int mi, int cloud_base, TextBuf *o)
+// What print_sam_record (src/samrecord.c:104-284) decides for one record — flag, MAPQ, which candidate, mate, XA
+// alternative, cloud id, the %.5g text of the posterior — as the descriptor the device formatter (csrc/sam_format.cu) turns
+// into text.  ri: the record printed (-1: this read is unmapped, its mate is mi), mi: its mate's record (-1: none).
+static void fill_sam_rec(const Barcode &b, int bc_index, int ri, int mi, int cloud_base, emab_sam_rec_t *d)
 {
 	const Rec *rec = ri >= 0 ? &b.recs[ri] : nullptr, *mate = mi >= 0 ? &b.recs[mi] : nullptr;
-	int flag = 1;
-	std::string_view ident, read, qual;
-	std::string_view chrom("*");
-	uint32_t pos = 0;
-	int mapq = 0;
+	int flag = 1, mapq = 0;
+	memset(d, 0, sizeof *d);
+	d->bc = (uint32_t)bc_index;
 	if (rec) {
-		const Pair &p = pairs[b.first_pair + rec->pair];
-		ident = rec->ident;
-		chrom = s->fai_names[rec->chrom];
-		pos = rec->pos;
-		read = p.read[rec->mate]; qual = p.qual[rec->mate];
+		d->pair = (uint32_t)(b.first_pair + rec->pair);
+		d->which = rec->mate;
 		const double gamma = rec->gamma;
 		const int gamma_mapq = (gamma <= 0.999999) ? (int)(-10 * log10(1 - gamma)) : 60;
 		mapq = std::min(gamma_mapq, rec->score_mapq);
@@ -799,10 +809,18 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 		if (rec->rev) flag |= 16;
 		if (rec->duplicate) flag |= 1024;
 		flag |= rec->mate == 0 ? 64 : 128;
+		if (gamma == 1.0) { d->gamma[0] = '1'; d->gamma_len = 1; }   // what %.5g prints for 1.0: the common case skips snprintf
+		else {
+			char buf[32];
+			const int n = snprintf(buf, sizeof buf, "%.5g", gamma);
+			d->gamma_len = (uint8_t)std::min(n, (int)sizeof d->gamma);
+			memcpy(d->gamma, buf, d->gamma_len);
+		}
+		d->mi = cloud_base + rec->cloud;
+		d->xf = b.clouds[rec->cloud].bad ? 1 : 0;
 	} else {
-		const Pair &p = pairs[b.first_pair + mate->pair];
-		ident = mate->ident;
-		read = p.read[1 - mate->mate]; qual = p.qual[1 - mate->mate];
+		d->pair = (uint32_t)(b.first_pair + mate->pair);
+		d->which = (uint8_t)(1 - mate->mate);
 		flag |= 4;
 		flag |= mate->mate == 0 ? 128 : 64;
 	}
@@ -810,59 +828,11 @@ static void print_sam_record(const Session *s, const Barcode &b, const std::vect
 		if (rec && is_pair(*rec, *mate)) flag |= 2;
 		if (mate->rev) flag |= 32;
 	} else flag |= 8;
-	const Rec *alt = rec && rec->alt >= 0 ? &b.recs[rec->alt] : nullptr;
-	const std::string &bc_str = b.bc_str;
-	// everything of variable length, plus room for the fixed tags, every integer and two full CIGARs
-	const size_t bound = ident.size() + read.size() + qual.size() + chrom.size() + bc_str.size() + s->bx_index.size() + s->rg_id.size() +
-	                     (mate ? s->fai_names[mate->chrom].size() : 0) + (alt ? s->fai_names[alt->chrom].size() : 0) + 2 * 64 * 12 + 512;  // 64 = the most CIGAR ops a candidate carries (include/align.h:41)
-	char *w = o->room(bound);
-	w = put_sv(w, ident); *w++ = '\t'; w = put_int(w, flag); *w++ = '\t'; w = put_sv(w, chrom); *w++ = '\t';
-	w = put_int(w, pos); *w++ = '\t'; w = put_int(w, mapq); *w++ = '\t';
-	if (rec) w = put_cigar(w, rec->aln, rec->cig); else *w++ = '*';
-	if (mate) {
-		const bool same = rec && mate->chrom == rec->chrom;
-		*w++ = '\t';
-		if (same) *w++ = '='; else w = put_sv(w, s->fai_names[mate->chrom]);
-		*w++ = '\t'; w = put_int(w, (int)mate->pos);
-		if (same) {
-			const emab_cand_t *r = rec->aln, *m = mate->aln;
-			const int64_t p0 = r->pos + (r->is_rev ? get_rlen(r, rec->cig) - 1 : 0), p1 = m->pos + (m->is_rev ? get_rlen(m, mate->cig) - 1 : 0);
-			*w++ = '\t';
-			if (m->n_cigar == 0 || r->n_cigar == 0) *w++ = '0';
-			else w = put_int(w, -(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
-		} else w = put_lit(w, "\t0");
-	} else w = put_lit(w, "\t*\t0\t0");
-	*w++ = '\t';
-	if (rec && rec->rev) {
-		const size_t nr = read.size(), nq = qual.size();
-		revcomp_bytes(w, read.data(), nr);
-		w[nr] = '\t';
-		reverse_bytes(w + nr + 1, qual.data(), nq);
-		w += nr + 1 + nq;
-	} else { w = put_sv(w, read); *w++ = '\t'; w = put_sv(w, qual); }
-	if (rec) {
-		w = put_lit(w, "\tNM:i:"); w = put_int(w, rec->aln->NM);
-		w = put_lit(w, "\tBX:Z:"); w = put_sv(w, bc_str);
-		if (!s->is_haplotag) { *w++ = '-'; w = put_sv(w, s->bx_index); }
-		if (rec->gamma == 1.0) w = put_lit(w, "\tXG:f:1");  // what %.5g prints for 1.0: the common case skips snprintf
-		else w += snprintf(w, 64, "\tXG:f:%.5g", rec->gamma);
-		w = put_lit(w, "\tMI:i:"); w = put_int(w, cloud_base + rec->cloud);
-		w = put_lit(w, "\tXF:i:"); *w++ = b.clouds[rec->cloud].bad ? '1' : '0';
-	} else {
-		w = put_lit(w, "\tBX:Z:"); w = put_sv(w, bc_str);
-		if (!s->is_haplotag) w = put_lit(w, "-1");
-	}
-	if (s->has_rg) {
-		w = put_lit(w, "\tRG:Z:");
-		w = put_sv(w, s->rg_id);
-	}
-	if (alt) {
-		w = put_lit(w, "\tXA:Z:"); w = put_sv(w, s->fai_names[alt->chrom]); *w++ = ','; *w++ = alt->rev ? '-' : '+'; w = put_int(w, (int)alt->pos); *w++ = ',';
-		w = put_cigar(w, alt->aln, alt->cig);
-		*w++ = ','; w = put_int(w, alt->aln->NM); *w++ = ';';
-	}
-	*w++ = '\n';
-	o->n = (size_t)(w - o->p);
+	d->flag = (uint16_t)flag;
+	d->mapq = (uint8_t)mapq;
+	d->rec_cand = rec ? rec->cand : -1;
+	d->mate_cand = mate ? mate->cand : -1;
+	d->alt_cand = rec && rec->alt >= 0 ? b.recs[rec->alt].cand : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -882,7 +852,10 @@ static const uint8_t *nt4_table()
 	return tab.t;
 }
 
-static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector<Pair> &pairs, char **out_buf, size_t *out_len, emab_run_stats_t &st)
+// The text a batch's pairs point into: one block (a bucket's contents) or two (-1 and -2 files).
+struct TextSrc { const char *base[2] = {nullptr, nullptr}; size_t len[2] = {0, 0}; };
+
+static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector<Pair> &pairs, const TextSrc &src, char **out_buf, size_t *out_len, emab_run_stats_t &st)
 {
 	const int ticket = gp.ticket;
 	const double t0 = now_ms();
@@ -900,25 +873,48 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 		off[2 * i + 1] = off[2 * i] + (int64_t)pairs[i].read[0].size();
 		off[2 * i + 2] = off[2 * i + 1] + (int64_t)pairs[i].read[1].size();
 	}
-	if (wk.seq.ensure((size_t)off[2 * np] + 1)) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
-	uint8_t *seq = (uint8_t *)wk.seq.p;
+	// the batch's text goes to the device as it is (page-locked copy first: the caller's buffer is pageable), with one
+	// record per pair saying where names, bases and qualities are; the device derives the nt4 reads from it
+	const size_t text_len = src.len[0] + src.len[1];
+	if (text_len >= 0xffffffffull) { wk.err = "batch text larger than 4 GB"; s->take_cloud_base(ticket, 0); return EMAB_ERR_ARG; }
+	if (wk.seq.ensure(text_len + 16) || wk.ptab.ensure(np * sizeof(emab_pair_text_t) + 16)) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
+	char *text = (char *)wk.seq.p;
+	emab_pair_text_t *ptab = (emab_pair_text_t *)wk.ptab.p;
+	int bad_view = 0;
 	#pragma omp parallel num_threads(nthr)
 	{
 	HostProf hp(HP_ENCODE);
-	#pragma omp for schedule(static)
-	for (size_t i = 0; i < np; ++i)
-		for (int m = 0; m < 2; ++m) {
-			const std::string_view r = pairs[i].read[m];
-			nt4_bytes(seq + off[2 * i + m], r.data(), r.size());
+	#pragma omp for schedule(static) nowait
+	for (long long blk = 0; blk < (long long)((text_len + (1u << 20) - 1) >> 20); ++blk) {   // the copy, a megabyte at a time
+		const size_t a0 = (size_t)blk << 20, a1 = std::min(text_len, a0 + (1u << 20));
+		for (int k = 0; k < 2; ++k) {
+			const size_t lo = k ? src.len[0] : 0, hi = lo + src.len[k];
+			const size_t x0 = std::max(a0, lo), x1 = std::min(a1, hi);
+			if (x0 < x1) memcpy(text + x0, src.base[k] + (x0 - lo), x1 - x0);
 		}
 	}
+	#pragma omp for schedule(static)
+	for (size_t i = 0; i < np; ++i) {
+		auto where = [&](std::string_view v, uint32_t *o, uint32_t *l) {
+			const char *p = v.data();
+			*l = (uint32_t)v.size();
+			if (p >= src.base[0] && p + v.size() <= src.base[0] + src.len[0]) *o = (uint32_t)(p - src.base[0]);
+			else if (src.base[1] && p >= src.base[1] && p + v.size() <= src.base[1] + src.len[1]) *o = (uint32_t)(src.len[0] + (size_t)(p - src.base[1]));
+			else { *o = 0; *l = 0; if (v.size()) bad_view = 1; }
+		};
+		emab_pair_text_t &t = ptab[i];
+		where(pairs[i].id1, &t.id_off[0], &t.id_len[0]); where(pairs[i].id2, &t.id_off[1], &t.id_len[1]);
+		for (int m = 0; m < 2; ++m) { where(pairs[i].read[m], &t.read_off[m], &t.read_len[m]); where(pairs[i].qual[m], &t.qual_off[m], &t.qual_len[m]); }
+	}
+	}
+	if (bad_view) { wk.err = "internal error: a pair's text lies outside the batch text"; s->take_cloud_base(ticket, 0); return EMAB_ERR_ARG; }
 	emab_stats_t ds;
 	emab_pairs_result_t res;
 	const double t1 = now_ms();
 	gp.to(PH_DEVICE);
 	const double t1b = now_ms();
 	{
-		int rc = emab_align_pairs(wk.ctx, (int)np, seq, off, 3, 0, &res, &ds);
+		int rc = emab_align_pairs_text(wk.ctx, (int)np, text, text_len, ptab, off, &res, &ds);
 		if (rc) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
 	}
 	const int32_t *n_regs = res.n_regs;
@@ -966,7 +962,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 					r.ident = m == 0 ? pairs[gp].id1 : pairs[gp].id2;
 					r.score = a.em_score; r.mapq = a.mapq; r.score_mapq = a.score_mapq; r.clip = a.clip; r.clip_edit_dist = a.clip_edit_dist;
 					r.mate = (uint8_t)m; r.rev = (uint8_t)a.is_rev; r.duplicate = 0; r.unique = 0; r.active = 1; r.visited = 0;
-					r.pair = pi; r.aln = &a; r.cig = res.cigars + a.cigar_off; r.gamma = 0; r.cloud = -1; r.selected_mate = -1; r.alt = -1;
+					r.pair = pi; r.aln = &a; r.cand = (int)k; r.gamma = 0; r.cloud = -1; r.selected_mate = -1; r.alt = -1;
 					B.recs.push_back(r);
 					++added;
 				}
@@ -1103,16 +1099,15 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 		B.choose(s);
 		B.bc_str.clear();
 		decode_bc(s, B.bc, &B.bc_str);
-		hp.next(HP_PRINT);
-		B.sam.reserve(B.final_.size() * 1100 + 4096);
+		// the pairs this barcode prints, in records_final order (src/align.c:585-611): two records each
+		B.n_out = 0;
 		for (int ri : B.final_) {
 			Rec &best = B.recs[ri];
 			if (best.visited) continue;
-			const int mi = best.selected_mate;
-			if (mi >= 0) B.recs[mi].visited = 1;
-			print_sam_record(s, B, pairs, ri, mi, cloud_base[b], &B.sam);
-			print_sam_record(s, B, pairs, mi, ri, cloud_base[b], &B.sam);
+			if (best.selected_mate >= 0) B.recs[best.selected_mate].visited = 1;
+			++B.n_out;
 		}
+		for (int ri : B.final_) if (B.recs[ri].selected_mate >= 0) B.recs[B.recs[ri].selected_mate].visited = 0;
 	}
 	if (!s->gamma_dump.empty()) {  // test hook: chosen alignments with full-precision posteriors
 		FILE *f = fopen(s->gamma_dump.c_str(), "w");
@@ -1125,15 +1120,56 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 			fclose(f);
 		}
 	}
-	std::vector<size_t> soff(nb + 1, 0);
-	for (int b = 0; b < nb; ++b) soff[b + 1] = soff[b] + bcs[b].sam.size();
-	const size_t total = soff[nb];
-	char *buf = text_alloc(total + 1);
-	if (!buf) { wk.err = "out of memory"; return EMAB_ERR_NOMEM; }
+	// ---- one descriptor per SAM record; the text is assembled on the device and lands in the (page-locked) output block
+	std::vector<int64_t> rec_off(nb + 1, 0);
+	std::vector<int32_t> bc_off(nb + 1, 0);
+	for (int b = 0; b < nb; ++b) { rec_off[b + 1] = rec_off[b] + 2 * (int64_t)bcs[b].n_out; bc_off[b + 1] = bc_off[b] + (int32_t)bcs[b].bc_str.size(); }
+	const int64_t n_out = rec_off[nb];
+	if (n_out > 0x7fffffff) { wk.err = "too many records in one batch"; return EMAB_ERR_OVERFLOW; }
+	std::vector<emab_sam_rec_t> descs((size_t)n_out);
+	std::string bc_text((size_t)bc_off[nb], 0);
+	std::vector<size_t> bound_part((size_t)nb, 0);
 	#pragma omp parallel for num_threads(nthr) schedule(dynamic, 4)
-	for (int b = 0; b < nb; ++b) { HostProf hp(HP_COPY); memcpy(buf + soff[b], bcs[b].sam.data(), bcs[b].sam.size()); }
+	for (int b = 0; b < nb; ++b) {
+		HostProf hp(HP_PRINT);
+		Barcode &B = bcs[b];
+		memcpy(&bc_text[(size_t)bc_off[b]], B.bc_str.data(), B.bc_str.size());
+		emab_sam_rec_t *d = descs.data() + rec_off[b];
+		size_t bound = 0;
+		for (int ri : B.final_) {
+			Rec &best = B.recs[ri];
+			if (best.visited) continue;
+			const int mi = best.selected_mate;
+			if (mi >= 0) B.recs[mi].visited = 1;
+			fill_sam_rec(B, b, ri, mi, cloud_base[b], d++);
+			fill_sam_rec(B, b, mi, ri, cloud_base[b], d++);
+			const emab_pair_text_t &t = ptab[d[-1].pair];
+			bound += (size_t)t.id_len[0] + t.id_len[1] + t.read_len[0] + t.read_len[1] + t.qual_len[0] + t.qual_len[1] + 2 * B.bc_str.size();
+		}
+		bound_part[(size_t)b] = bound;
+	}
+	// capacity: the variable-length text plus, per record, contig names, two CIGARs of up to 64 operations, tags and integers
+	size_t max_name = 1;
+	for (const std::string &nm : s->fai_names) max_name = std::max(max_name, nm.size());
+	size_t cap = (size_t)n_out * (3 * max_name + s->bx_index.size() + s->rg_id.size() + 2 * 64 * 5 + 256) + 64;
+	for (size_t v : bound_part) cap += v;
+	char *buf = text_alloc_pinned(cap + 1);
+	if (!buf) { wk.err = "out of memory"; return EMAB_ERR_NOMEM; }
+	uint64_t total = 0;
+	if (n_out > 0) {
+		emab_sam_job_t job;
+		memset(&job, 0, sizeof job);
+		job.n_recs = (int32_t)n_out; job.n_bc = nb; job.recs = descs.data(); job.bc_off = bc_off.data(); job.bc_text = bc_text.data();
+		job.bx_index = s->bx_index.c_str(); job.rg_id = s->has_rg ? s->rg_id.c_str() : nullptr; job.is_haplotag = s->is_haplotag ? 1 : 0;
+		int rc = emab_sam_format(wk.ctx, &job, buf, (uint64_t)cap, &total);
+		if (rc) { wk.err = emab_last_error(); text_free(buf); return rc; }
+		st.launches += 4;
+		st.d2h_bytes += (int64_t)total;
+		st.h2d_bytes += (int64_t)n_out * (int64_t)sizeof(emab_sam_rec_t) + (int64_t)bc_text.size();
+		st.format_kernel_ms = emab_last_kernel_ms(wk.ctx);
+	}
 	buf[total] = 0;
-	*out_buf = buf; *out_len = total;
+	*out_buf = buf; *out_len = (size_t)total;
 	const double t6 = now_ms();
 	st.encode_ms = t1 - t0; st.cloud_ms = t3 - t2; st.flatten_ms = t4 - t3; st.em_ms = t5 - t4; st.format_ms = t6 - t5; st.total_ms = t6 - t0;
 	st.sam_bytes = (int64_t)total;
@@ -1295,7 +1331,9 @@ static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size
 	int rc = parse_bucket(s, wk.n_threads, data, len, pairs, err);
 	if (rc) { s->take_cloud_base(ticket, 0); return rc; }
 	const double t1 = now_ms();
-	rc = process_pairs(s, wk, gp, pairs, out, out_len, st);
+	TextSrc src;
+	src.base[0] = data; src.len[0] = len;
+	rc = process_pairs(s, wk, gp, pairs, src, out, out_len, st);
 	if (rc) *err = wk.err;
 	st.parse_ms = t1 - t0;
 	st.total_ms += t1 - t0;
@@ -1308,7 +1346,7 @@ static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size
 // and their SAM texts are joined in order.  Cloud ids stay those of the serial run: the parts take their tickets in
 // order and every part draws its ids after the parts before it (init_cloud's counter, src/align.c:19-23), which is the
 // exclusive prefix sum of clouds per part.
-static int align_pairs_split(Session *s, const std::vector<Pair> &pairs, char **out, size_t *out_len)
+static int align_pairs_split(Session *s, const std::vector<Pair> &pairs, const TextSrc &src, char **out, size_t *out_len)
 {
 	const size_t n = pairs.size();
 	const int W = (int)s->workers.size();
@@ -1337,7 +1375,7 @@ static int align_pairs_split(Session *s, const std::vector<Pair> &pairs, char **
 			GatePass gp(s, tickets[k]);
 			gp.to(PH_PARSE);
 			std::vector<Pair> part(pairs.begin() + (ptrdiff_t)cut[k], pairs.begin() + (ptrdiff_t)cut[k + 1]);
-			rcs[k] = process_pairs(s, wk, gp, part, &texts[k], &lens[k], sts[k]);
+			rcs[k] = process_pairs(s, wk, gp, part, src, &texts[k], &lens[k], sts[k]);
 			if (rcs[k]) errs[k] = wk.err;
 		} catch (const std::bad_alloc &) { rcs[k] = EMAB_ERR_NOMEM; errs[k] = "out of host memory"; s->pass_cloud_turn(tickets[k]); }
 		std::lock_guard<std::mutex> g(s->mu);
@@ -1380,10 +1418,12 @@ int align_special_fastq(Session *s, const char *data, size_t len, char **out, si
 		std::vector<Pair> pairs;
 		int rc = parse_bucket(s, s->n_threads, data, len, pairs, &err);
 		if (rc) { s->err = err; return rc; }
-		if (pairs.size() >= 2000) return align_pairs_split(s, pairs, out, out_len);
+		TextSrc src;
+		src.base[0] = data; src.len[0] = len;
+		if (pairs.size() >= 2000) return align_pairs_split(s, pairs, src, out, out_len);
 		GatePass gp(s, s->new_ticket());
 		gp.to(PH_PARSE);
-		rc = process_pairs(s, s->workers[0], gp, pairs, out, out_len, s->last);
+		rc = process_pairs(s, s->workers[0], gp, pairs, src, out, out_len, s->last);
 		if (rc) s->err = s->workers[0].err;
 		return rc;
 	}
@@ -1698,7 +1738,10 @@ int align_fastq_stream(Session *s, emab_read_cb r1, void *u1, emab_read_cb r2, v
 				const double tq = now_ms();
 				if (rc) s->pass_cloud_turn(ticket);
 				else {
-					rc = process_pairs(s, wk, gp, pairs, &text, &text_len, st);
+					TextSrc src;
+					src.base[0] = t1.data(); src.len[0] = t1.size();
+					if (cut.paired_files) { src.base[1] = t2.data(); src.len[1] = t2.size(); }
+					rc = process_pairs(s, wk, gp, pairs, src, &text, &text_len, st);
 					if (rc) msg = wk.err;
 					st.parse_ms = tq - tp;
 					st.total_ms += tq - tp;

@@ -88,7 +88,7 @@ struct TurnPass {
 struct Worker {  // one in-flight bucket: a device context (stream + scratch) and its staging buffers
 	emab_ctx_t *ctx = nullptr;
 	int dev_slot = 0;                     // which of the session's index replicas the ctx lives on
-	PinnedBuf seq, off;
+	PinnedBuf seq, off, ptab;             // the batch's text, read offsets, per-pair text table (page-locked staging)
 	int n_threads = 1;
 	std::string err;                      // this worker's last error (workers run concurrently: never Session::err)
 };
@@ -180,6 +180,7 @@ struct GatePass {
 // (serialised on the process's mm lock) cost more CPU than formatting the text.
 int host_selftest();  // vector byte kernels against their scalar definitions (0 = ok)
 char *text_alloc(size_t n);
+char *text_alloc_pinned(size_t n);
 void text_free(void *p);
 
 int session_open(const char *ref_path, const char *platform, int device, Session **out, std::string *err);

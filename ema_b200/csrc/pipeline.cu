@@ -452,6 +452,25 @@ extern "C" int emab_set_error_rate(emab_ctx_t *c, double eps)
 	return EMAB_OK;
 }
 
+// nt4 codes of the reads straight from the batch's text on the device (what the host did with nt4_bytes per read)
+__global__ void __launch_bounds__(256)
+k_encode_reads(const char *text, const emab_pair_text_t *pairs, int n_reads, const int64_t *off, uint8_t *seq)
+{
+	const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (r >= n_reads) return;
+	const emab_pair_text_t &pt = pairs[r >> 1];
+	const char *src = text + pt.read_off[r & 1];
+	const int len = (int)pt.read_len[r & 1];
+	uint8_t *dst = seq + off[r];
+	for (int i = lane; i < len; i += 32) {
+		const char ch = src[i];
+		dst[i] = ch == 'A' || ch == 'a' ? 0 : ch == 'C' || ch == 'c' ? 1 : ch == 'G' || ch == 'g' ? 2 : ch == 'T' || ch == 't' ? 3 : 4;
+	}
+}
+
+static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t total_len, int64_t h2d_bytes, int stage, int want_regs,
+                            emab_pairs_result_t *res, emab_stats_t *stats, bool want_cigars);
+
 extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, const int64_t *off, int stage, int want_regs,
                                 emab_pairs_result_t *res, emab_stats_t *stats)
 {
@@ -467,12 +486,52 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		if (l > max_len && l <= EMAB_MAX_READ_LEN) max_len = (int)l;
 		if (l < 0 || l > EMAB_MAX_READ_LEN) { snprintf(emab_errbuf, sizeof emab_errbuf, "read %d: length %lld out of range (max %d)", i, (long long)l, EMAB_MAX_READ_LEN); return EMAB_ERR_ARG; }
 	}
-	if (!c->consts_ready) TRY(emab_set_error_rate(c, 0.001));
-	const DevIndex &ix = c->ix->d;
-	cudaStream_t st = c->stream;
 	// slots: 0 seq, 1 off, 2 intv, 3 n_intv, 4 smem scratch, 5 occ_cnt/off, 6 cub temp, 7.. pools
 	TRY(upload(c, c->b[0], seq, (size_t)off[R]));
 	TRY(upload(c, c->b[1], off, (size_t)(R + 1) * 8));
+	c->text_ready = false;
+	return align_pairs_core(c, n_pairs, max_len, off[R], (int64_t)off[R] + (int64_t)(R + 1) * 8, stage, want_regs, res, stats, true);
+}
+
+// The batch as TEXT: the bytes the reads, names and qualities are taken from (a pinned host buffer, e.g. the bucket file's
+// contents) and one emab_pair_text_t per pair saying where they are.  The text stays on the device for emab_sam_format;
+// the nt4 read array the pipeline works on is derived from it there.  `off` = 2*n_pairs+1 prefix sums of the read lengths.
+extern "C" int emab_align_pairs_text(emab_ctx_t *c, int n_pairs, const char *text, uint64_t text_len, const emab_pair_text_t *pairs,
+                                     const int64_t *off, emab_pairs_result_t *res, emab_stats_t *stats)
+{
+	CTX_ENTER(c);
+	if (!c || !c->ix || !res || n_pairs < 0 || !text || !pairs || !off) return EMAB_ERR_ARG;
+	const int R = 2 * n_pairs;
+	memset(res, 0, sizeof *res);
+	if (stats) memset(stats, 0, sizeof *stats);
+	c->text_ready = false;
+	if (R == 0) return EMAB_OK;
+	int max_len = 1;
+	for (int i = 0; i < R; ++i) {
+		const int64_t l = off[i + 1] - off[i];
+		if (l < 0 || l > EMAB_MAX_READ_LEN || l != (int64_t)pairs[i >> 1].read_len[i & 1]) { snprintf(emab_errbuf, sizeof emab_errbuf, "read %d: bad length %lld", i, (long long)l); return EMAB_ERR_ARG; }
+		if (l > max_len) max_len = (int)l;
+		if ((uint64_t)pairs[i >> 1].read_off[i & 1] + (uint64_t)l > text_len) { snprintf(emab_errbuf, sizeof emab_errbuf, "read %d lies outside the text", i); return EMAB_ERR_ARG; }
+	}
+	cudaStream_t st = c->stream;
+	TRY(upload(c, c->b[31], text, (size_t)text_len));
+	TRY(upload(c, c->b[27], pairs, (size_t)n_pairs * sizeof(emab_pair_text_t)));
+	TRY(upload(c, c->b[1], off, (size_t)(R + 1) * 8));
+	TRY(c->b[0].ensure((size_t)off[R] + 16));
+	k_encode_reads<<<(R * 32 + 255) / 256, 256, 0, st>>>(c->b[31].as<char>(), c->b[27].as<emab_pair_text_t>(), R, c->b[1].as<int64_t>(), c->b[0].as<uint8_t>());
+	c->text_ready = true;
+	return align_pairs_core(c, n_pairs, max_len, off[R], (int64_t)text_len + (int64_t)n_pairs * (int64_t)sizeof(emab_pair_text_t) + (int64_t)(R + 1) * 8,
+	                        3, 0, res, stats, false);
+}
+
+static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t total_len, int64_t h2d_bytes, int stage, int want_regs,
+                            emab_pairs_result_t *res, emab_stats_t *stats, bool want_cigars)
+{
+	const int R = 2 * n_pairs;
+	(void)total_len;
+	if (!c->consts_ready) TRY(emab_set_error_rate(c, 0.001));
+	const DevIndex &ix = c->ix->d;
+	cudaStream_t st = c->stream;
 	TRY(c->b[3].ensure((size_t)R * 4));
 	TRY(c->b[5].ensure((size_t)(R + 1) * 4 * 2));
 	int32_t *d_occ_cnt = c->b[5].as<int32_t>(), *d_occ_off = d_occ_cnt + (R + 1);
@@ -678,7 +737,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		TRY(c->h[1].ensure(((size_t)A + 1) * sizeof(emab_cand_t)));
 		TRY(c->h[2].ensure(((size_t)NC + 1) * 4));
 		if (A) CUDA_TRY(cudaMemcpyAsync(c->h[1].p, c->b[21].p, (size_t)A * sizeof(emab_cand_t), cudaMemcpyDeviceToHost, st));
-		if (NC) CUDA_TRY(cudaMemcpyAsync(c->h[2].p, c->b[19].p, (size_t)NC * 4, cudaMemcpyDeviceToHost, st));
+		if (NC && want_cigars) CUDA_TRY(cudaMemcpyAsync(c->h[2].p, c->b[19].p, (size_t)NC * 4, cudaMemcpyDeviceToHost, st));
 	} else {
 		CUDA_TRY(cudaEventRecord(c->ev1, st));
 		CUDA_TRY(cudaEventRecord(c->stage_ev[7], st));
@@ -699,7 +758,7 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 	CUDA_TRY(cudaGetLastError());
 	res->n_cands = A; res->n_cigar_ops = NC; res->n_regs = (const int32_t *)c->h[0].p;
 	res->cands = stage >= 3 ? (const emab_cand_t *)c->h[1].p : nullptr;
-	res->cigars = stage >= 3 ? (const uint32_t *)c->h[2].p : nullptr;
+	res->cigars = stage >= 3 && want_cigars ? (const uint32_t *)c->h[2].p : nullptr;
 	res->regs_dbg = want_regs ? (const int64_t *)c->h[3].p : nullptr;
 	float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
 	c->last_ms = ms; c->last_launches = launches;
@@ -717,8 +776,8 @@ extern "C" int emab_align_pairs(emab_ctx_t *c, int n_pairs, const uint8_t *seq, 
 		cudaEventElapsedTime(&t, c->stage_ev[3], c->stage_ev[4]); stats->ms_align1 = t;
 		cudaEventElapsedTime(&t, c->stage_ev[4], c->stage_ev[5]); stats->ms_rescue = t;
 		cudaEventElapsedTime(&t, c->stage_ev[6], c->stage_ev[7]); stats->ms_finalize = t;
-		stats->h2d_bytes = (int64_t)off[R] + (int64_t)(R + 1) * 8;
-		stats->d2h_bytes = (int64_t)R * 4 + (int64_t)A * (int64_t)sizeof(emab_cand_t) + (int64_t)NC * 4 + 96;
+		stats->h2d_bytes = h2d_bytes;
+		stats->d2h_bytes = (int64_t)R * 4 + (int64_t)A * (int64_t)sizeof(emab_cand_t) + (want_cigars ? (int64_t)NC * 4 : 0) + 96;
 	}
 	if (h_err[0]) {
 		snprintf(emab_errbuf, sizeof emab_errbuf, "device pipeline error %d (1: backtrack scratch too small, 2: rescue window too long, 3: too many SA intervals, 4: internal DP dispatch)", h_err[0]);

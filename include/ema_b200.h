@@ -173,6 +173,48 @@ typedef struct {
 int emab_set_error_rate(emab_ctx_t *ctx, double eps);  /* platform error_rate (src/techs.c:71-127); default 0.001 */
 int emab_align_pairs(emab_ctx_t *ctx, int n_pairs, const uint8_t *seq, const int64_t *off, int stage, int want_regs,
                      emab_pairs_result_t *result, emab_stats_t *stats);
+/* ---- the batch as text, and SAM text from the device ------------------------------------------------
+ * emab_align_pairs_text = emab_align_pairs where the reads are not handed over as nt4 arrays but as positions inside the
+ * batch's TEXT (the bucket file's contents, or FASTQ text): the text and one emab_pair_text_t per pair are uploaded, the
+ * nt4 reads are derived on the device, and text + candidates stay resident for emab_sam_format.  res->cigars is NULL
+ * (CIGARs are only needed for printing, which then happens on the device).
+ * emab_sam_tables  = once per ctx: the .fai contig names (src/main.c:57-71) and the index-contig -> name map
+ * emab_sam_format  = print_sam_record (src/samrecord.c:104-284) for n_recs records described by emab_sam_rec_t, into
+ *                    `out` (host memory; pinned for speed), in the order given.  Everything the record copies — name,
+ *                    bases (reverse-complemented for reverse-strand hits), qualities, CIGAR, contig names — comes from the
+ *                    device-resident batch; the host supplies decisions only. */
+typedef struct {
+	uint32_t id_off[2], id_len[2];      /* read names without the leading '@' */
+	uint32_t read_off[2], read_len[2];
+	uint32_t qual_off[2], qual_len[2];
+} emab_pair_text_t;
+typedef struct {            /* one SAM record: 48 bytes */
+	uint32_t pair;          /* pair index in the batch */
+	int32_t rec_cand;       /* index of the candidate printed (into the call's candidates), -1: the read is unmapped */
+	int32_t mate_cand;      /* its mate's chosen candidate, -1: none */
+	int32_t alt_cand;       /* the XA:Z candidate, -1: none */
+	int32_t mi;             /* MI:i */
+	uint32_t bc;            /* index of the barcode's BX string */
+	uint16_t flag;
+	uint8_t which;          /* which read of the pair: 0 / 1 */
+	uint8_t mapq;
+	uint8_t xf;             /* XF:i */
+	uint8_t gamma_len;
+	char gamma[14];         /* the XG:f value as printed by %.5g */
+} emab_sam_rec_t;
+typedef struct {
+	int32_t n_recs, n_bc;
+	const emab_sam_rec_t *recs;
+	const int32_t *bc_off;      /* [n_bc + 1] into bc_text */
+	const char *bc_text;
+	const char *bx_index;       /* -i suffix */
+	const char *rg_id;          /* RG:Z value, NULL: no read group */
+	int32_t is_haplotag, pad;
+} emab_sam_job_t;
+int emab_align_pairs_text(emab_ctx_t *ctx, int n_pairs, const char *text, uint64_t text_len, const emab_pair_text_t *pairs,
+                          const int64_t *off, emab_pairs_result_t *result, emab_stats_t *stats);
+int emab_sam_tables(emab_ctx_t *ctx, int n_chrom, const char *const *names, int n_rid, const int32_t *rid2chrom);
+int emab_sam_format(emab_ctx_t *ctx, const emab_sam_job_t *job, char *out, uint64_t out_cap, uint64_t *out_len);
 /* pinned host memory for callers that want their input buffers to take the fast H2D path */
 void *emab_pinned_alloc(uint64_t bytes);
 void emab_pinned_free(void *p);
@@ -229,6 +271,7 @@ typedef struct {
 	int32_t launches, pad;
 	int64_t ext_planned_cells, ext_unplanned, glob_planned_cells, glob_unplanned;
 	double ms_ext_wave, ms_glob_wave;
+	double format_kernel_ms;                          /* device time of the SAM text kernels */
 } emab_run_stats_t;
 
 int emab_session_open(const char *ref_path, const char *platform, int device, emab_session_t **out);
