@@ -197,7 +197,8 @@ extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
 	CUDA_TRY(cudaEventCreate(&c->ev0));
 	CUDA_TRY(cudaEventCreate(&c->ev1));
 	CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
-	if (const char *e = getenv("EMAB_SYNC")) c->wait_mode = strcmp(e, "block") == 0 ? 2 : (strcmp(e, "spin") == 0 ? 1 : 0);
+	c->wait_mode = 1;   // a bare ctx spins; a session switches its workers to poll-then-sleep when host threads are scarce (emab_ctx_set_wait)
+	if (const char *e = getenv("EMAB_SYNC")) { c->wait_mode = strcmp(e, "block") == 0 ? 2 : (strcmp(e, "spin") == 0 ? 1 : 0); c->wait_fixed = true; }
 	if (const char *e = getenv("EMAB_SPIN_US")) c->spin_us = atoi(e);
 	CUDA_TRY(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
 	cudaDeviceProp prop;
@@ -238,6 +239,14 @@ extern "C" void *emab_pinned_alloc(uint64_t bytes)
 	return p;
 }
 extern "C" void emab_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+
+// mode 0: poll ~150 us then sleep between polls, 1: spin, 2: blocking-sync event.  EMAB_SYNC overrides.
+extern "C" int emab_ctx_set_wait(emab_ctx_t *c, int mode)
+{
+	if (!c || mode < 0 || mode > 2) return EMAB_ERR_ARG;
+	if (!c->wait_fixed) c->wait_mode = mode;
+	return EMAB_OK;
+}
 
 extern "C" double emab_last_kernel_ms(const emab_ctx_t *c) { return c ? c->last_ms : 0; }
 extern "C" int emab_last_launches(const emab_ctx_t *c) { return c ? c->last_launches : 0; }

@@ -72,6 +72,7 @@ int emab_session_config(emab_session_t *h, const char *rg, const char *bx_index,
 		if (bx_index) h->s->bx_index = bx_index;
 		h->s->apply_opt = apply_opt;
 		h->s->n_threads = n_threads > 0 ? n_threads : 1;
+		emab::session_set_workers(h->s, (int)h->s->workers.size());   // refreshes the workers' wait mode for the new thread budget
 		return EMAB_OK;
 	});
 }

@@ -224,6 +224,14 @@ PinnedBuf &PinnedBuf::operator=(PinnedBuf &&o) noexcept
 // ---------------------------------------------------------------------------------------------
 // session
 // ---------------------------------------------------------------------------------------------
+// Spinning on the stream is the fastest way to wait (a bucket has seven waits) but takes a core per bucket in its device
+// phase; with fewer than two host threads per bucket in flight those cores are needed for parsing and cloud building.
+static void session_wait_modes(Session *s)
+{
+	const int mode = s->n_threads >= 2 * (int)std::max<size_t>(1, std::min<size_t>(s->workers.size(), 3 * s->replicas.size())) + 2 ? 1 : 0;
+	for (Worker &w : s->workers) emab_ctx_set_wait(w.ctx, mode);
+}
+
 int session_set_workers(Session *s, int n_workers)
 {
 	const int n_dev = (int)s->replicas.size();
@@ -244,6 +252,7 @@ int session_set_workers(Session *s, int n_workers)
 			if (rc) { s->err = emab_last_error(); emab_ctx_free(s->workers.back().ctx); s->workers.pop_back(); return rc; }
 		}
 	}
+	session_wait_modes(s);
 	return EMAB_OK;
 }
 

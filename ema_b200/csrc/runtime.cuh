@@ -69,6 +69,7 @@ struct emab_ctx {
 	cudaEvent_t stage_ev[16] = {};
 	cudaEvent_t ev_wait = nullptr;   // cudaEventBlockingSync: see ctx_wait()
 	int wait_mode = 0;               // 0: poll briefly, then sleep between polls; 1: spin (cudaStreamSynchronize); 2: blocking-sync event
+	bool wait_fixed = false;         // EMAB_SYNC was given: emab_ctx_set_wait leaves the mode alone
 	int spin_us = 150;               // how long mode 0 polls before it starts sleeping (EMAB_SPIN_US)
 	double last_ms = 0;
 	int last_launches = 0;

@@ -69,6 +69,9 @@ void emab_ctx_free(emab_ctx_t *ctx);
 /* Makes the ctx's device current on the calling thread.  Every entry point that takes a ctx does this itself; a
  * thread that allocates pinned memory before its first ctx call uses it to stay off device 0. */
 int emab_ctx_make_current(emab_ctx_t *ctx);
+/* how the calling thread waits for the ctx's stream: 0 = poll briefly, then sleep between polls (frees the core: for hosts with
+ * few cores per GPU), 1 = spin (lowest latency, the default of a bare ctx), 2 = blocking-sync event.  EMAB_SYNC=spin|block|nap overrides. */
+int emab_ctx_set_wait(emab_ctx_t *ctx, int mode);
 /* device time (ms, CUDA events on the ctx stream) of the kernels launched by the last call, and
  * the number of kernel launches it made */
 double emab_last_kernel_ms(const emab_ctx_t *ctx);
