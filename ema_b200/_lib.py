@@ -233,6 +233,22 @@ CAND_DTYPE = np.dtype([("pos", "<i8"), ("em_score", "<f8"), ("rid", "<i4"), ("NM
 assert CAND_DTYPE.itemsize == 56
 
 
+PAIR_TEXT_DTYPE = np.dtype([("id_off", "<u4", 2), ("id_len", "<u4", 2), ("read_off", "<u4", 2), ("read_len", "<u4", 2),
+                            ("qual_off", "<u4", 2), ("qual_len", "<u4", 2)])
+
+
+def parse_bucket(ctx: Context, data: bytes, bc_len: int = 16, haplotag: bool = False):
+    """emab_parse_bucket: the bucket reader on the device.  Returns (pair table as a structured array, barcode codes)."""
+    n = C.c_int()
+    pt, bc = C.c_void_p(), C.c_void_p()
+    _check(lib().emab_parse_bucket(ctx._h, data, C.c_uint64(len(data)), bc_len, int(haplotag), C.byref(n), C.byref(pt), C.byref(bc)))
+    if n.value == 0:
+        return np.zeros(0, PAIR_TEXT_DTYPE), np.zeros(0, np.uint64)
+    tab = np.frombuffer(C.string_at(pt, n.value * PAIR_TEXT_DTYPE.itemsize), dtype=PAIR_TEXT_DTYPE).copy()
+    bcs = np.frombuffer(C.string_at(bc, n.value * 8), dtype=np.uint64).copy()
+    return tab, bcs
+
+
 class Stats(C.Structure):
     _fields_ = [("extend_cells", C.c_int64), ("global_cells", C.c_int64), ("local_cells", C.c_int64), ("occ_touches", C.c_int64),
                 ("n_occ", C.c_int64), ("n_regs", C.c_int64), ("kernel_ms", C.c_double), ("ms_seed", C.c_double), ("ms_chain", C.c_double),

@@ -864,7 +864,8 @@ static const uint8_t *nt4_table()
 // The text a batch's pairs point into: one block (a bucket's contents) or two (-1 and -2 files).
 struct TextSrc { const char *base[2] = {nullptr, nullptr}; size_t len[2] = {0, 0}; };
 
-static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector<Pair> &pairs, const TextSrc &src, char **out_buf, size_t *out_len, emab_run_stats_t &st)
+static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector<Pair> &pairs, const TextSrc &src, char **out_buf, size_t *out_len, emab_run_stats_t &st,
+                         const emab_pair_text_t *resident_ptab = nullptr)   // non-null: emab_parse_bucket left text and pair table on wk.ctx's device
 {
 	const int ticket = gp.ticket;
 	const double t0 = now_ms();
@@ -886,10 +887,11 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	// record per pair saying where names, bases and qualities are; the device derives the nt4 reads from it
 	const size_t text_len = src.len[0] + src.len[1];
 	if (text_len >= 0xffffffffull) { wk.err = "batch text larger than 4 GB"; s->take_cloud_base(ticket, 0); return EMAB_ERR_ARG; }
-	if (wk.seq.ensure(text_len + 16) || wk.ptab.ensure(np * sizeof(emab_pair_text_t) + 16)) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
+	if (!resident_ptab && (wk.seq.ensure(text_len + 16) || wk.ptab.ensure(np * sizeof(emab_pair_text_t) + 16))) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
 	char *text = (char *)wk.seq.p;
-	emab_pair_text_t *ptab = (emab_pair_text_t *)wk.ptab.p;
+	const emab_pair_text_t *ptab = resident_ptab ? resident_ptab : (const emab_pair_text_t *)wk.ptab.p;
 	int bad_view = 0;
+	if (!resident_ptab)
 	#pragma omp parallel num_threads(nthr)
 	{
 	HostProf hp(HP_ENCODE);
@@ -911,7 +913,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 			else if (src.base[1] && p >= src.base[1] && p + v.size() <= src.base[1] + src.len[1]) *o = (uint32_t)(src.len[0] + (size_t)(p - src.base[1]));
 			else { *o = 0; *l = 0; if (v.size()) bad_view = 1; }
 		};
-		emab_pair_text_t &t = ptab[i];
+		emab_pair_text_t &t = ((emab_pair_text_t *)wk.ptab.p)[i];
 		where(pairs[i].id1, &t.id_off[0], &t.id_len[0]); where(pairs[i].id2, &t.id_off[1], &t.id_len[1]);
 		for (int m = 0; m < 2; ++m) { where(pairs[i].read[m], &t.read_off[m], &t.read_len[m]); where(pairs[i].qual[m], &t.qual_off[m], &t.qual_len[m]); }
 	}
@@ -923,7 +925,8 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	gp.to(PH_DEVICE);
 	const double t1b = now_ms();
 	{
-		int rc = emab_align_pairs_text(wk.ctx, (int)np, text, text_len, ptab, off, &res, &ds);
+		int rc = resident_ptab ? emab_align_pairs_resident(wk.ctx, (int)np, off, &res, &ds)
+		                       : emab_align_pairs_text(wk.ctx, (int)np, text, text_len, ptab, off, &res, &ds);
 		if (rc) { wk.err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
 	}
 	const int32_t *n_regs = res.n_regs;
@@ -1336,13 +1339,39 @@ static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size
 	const double tw = now_ms();
 	gp.to(PH_PARSE);
 	const double t0 = now_ms();
-	std::vector<Pair> pairs;
-	int rc = parse_bucket(s, wk.n_threads, data, len, pairs, err);
-	if (rc) { s->take_cloud_base(ticket, 0); return rc; }
+	// the bucket's text goes to the device once (through a page-locked copy) and is parsed there: line split, stable barcode
+	// sort, tokens, barcode codes (csrc/parse.cu).  What comes back is one record per pair saying where its fields are.
+	if (len >= 0xfffffff0ull) { *err = "bucket larger than 4 GB"; s->take_cloud_base(ticket, 0); return EMAB_ERR_ARG; }
+	if (wk.seq.ensure(len + 16)) { *err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
+	{
+		char *text = (char *)wk.seq.p;
+		const long long n_blk = (long long)((len + (1u << 20) - 1) >> 20);
+		#pragma omp parallel for num_threads(wk.n_threads) schedule(static)
+		for (long long blk = 0; blk < n_blk; ++blk) {
+			HostProf hp(HP_SPLIT);
+			const size_t a0 = (size_t)blk << 20, a1 = std::min(len, a0 + (1u << 20));
+			memcpy(text + a0, data + a0, a1 - a0);
+		}
+	}
+	int n = 0;
+	const emab_pair_text_t *pt = nullptr;
+	const uint64_t *bcs = nullptr;
+	int rc = emab_parse_bucket(wk.ctx, (const char *)wk.seq.p, (uint64_t)len, s->bc_len, s->is_haplotag ? 1 : 0, &n, &pt, &bcs);
+	if (rc) { *err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
+	std::vector<Pair> pairs((size_t)n);
+	#pragma omp parallel for num_threads(wk.n_threads) schedule(static)
+	for (int i = 0; i < n; ++i) {
+		HostProf hp(HP_TOKENS);
+		Pair &P = pairs[(size_t)i];
+		const emab_pair_text_t &t = pt[i];
+		P.bc = bcs[i];
+		P.id1 = P.id2 = std::string_view(data + t.id_off[0], t.id_len[0]);
+		for (int m = 0; m < 2; ++m) { P.read[m] = std::string_view(data + t.read_off[m], t.read_len[m]); P.qual[m] = std::string_view(data + t.qual_off[m], t.qual_len[m]); }
+	}
 	const double t1 = now_ms();
 	TextSrc src;
 	src.base[0] = data; src.len[0] = len;
-	rc = process_pairs(s, wk, gp, pairs, src, out, out_len, st);
+	rc = process_pairs(s, wk, gp, pairs, src, out, out_len, st, n > 0 ? pt : nullptr);
 	if (rc) *err = wk.err;
 	st.parse_ms = t1 - t0;
 	st.total_ms += t1 - t0;

@@ -524,6 +524,29 @@ extern "C" int emab_align_pairs_text(emab_ctx_t *c, int n_pairs, const char *tex
 	                        3, 0, res, stats, false);
 }
 
+// The pipeline on a batch whose text and pair table emab_parse_bucket left on the device.
+extern "C" int emab_align_pairs_resident(emab_ctx_t *c, int n_pairs, const int64_t *off, emab_pairs_result_t *res, emab_stats_t *stats)
+{
+	CTX_ENTER(c);
+	if (!c || !c->ix || !res || n_pairs < 0 || !off) return EMAB_ERR_ARG;
+	if (!c->text_ready || c->text_pairs != n_pairs) { snprintf(emab_errbuf, sizeof emab_errbuf, "emab_align_pairs_resident: no parsed batch of %d pairs on the device", n_pairs); return EMAB_ERR_ARG; }
+	const int R = 2 * n_pairs;
+	memset(res, 0, sizeof *res);
+	if (stats) memset(stats, 0, sizeof *stats);
+	if (R == 0) return EMAB_OK;
+	int max_len = 1;
+	for (int i = 0; i < R; ++i) {
+		const int64_t l = off[i + 1] - off[i];
+		if (l < 0 || l > EMAB_MAX_READ_LEN) { snprintf(emab_errbuf, sizeof emab_errbuf, "read %d: bad length %lld", i, (long long)l); return EMAB_ERR_ARG; }
+		if (l > max_len) max_len = (int)l;
+	}
+	cudaStream_t st = c->stream;
+	TRY(upload(c, c->b[1], off, (size_t)(R + 1) * 8));
+	TRY(c->b[0].ensure((size_t)off[R] + 16));
+	k_encode_reads<<<(R * 32 + 255) / 256, 256, 0, st>>>(c->b[31].as<char>(), c->b[27].as<emab_pair_text_t>(), R, c->b[1].as<int64_t>(), c->b[0].as<uint8_t>());
+	return align_pairs_core(c, n_pairs, max_len, off[R], (int64_t)c->text_len + (int64_t)(R + 1) * 8, 3, 0, res, stats, false);
+}
+
 static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t total_len, int64_t h2d_bytes, int stage, int want_regs,
                             emab_pairs_result_t *res, emab_stats_t *stats, bool want_cigars)
 {

@@ -86,7 +86,9 @@ struct emab_ctx {
 	bool glob_plan = true;   // ksw_global2 calls of mem_reg2aln likewise (glob_wave.cuh)
 	bool consts_ready = false;
 	bool em_log_ready = false; // emab_em_batch's ln(n) table is resident (slot 30)
-	bool text_ready = false;   // the batch's text + pair table are resident (slots 31, 27: emab_align_pairs_text)
+	bool text_ready = false;   // the batch's text + pair table are resident (slots 31, 27: emab_align_pairs_text / emab_parse_bucket)
+	unsigned text_len = 0;
+	int text_pairs = 0;
 	bool sam_tables_ready = false;  // contig names + rid -> name map resident (slot 45: emab_sam_tables)
 	size_t sam_chrom_off = 0, sam_rid_off = 0;
 };

@@ -216,6 +216,13 @@ typedef struct {
 } emab_sam_job_t;
 int emab_align_pairs_text(emab_ctx_t *ctx, int n_pairs, const char *text, uint64_t text_len, const emab_pair_text_t *pairs,
                           const int64_t *off, emab_pairs_result_t *result, emab_stats_t *stats);
+/* emab_parse_bucket = read_special_fastq (src/align.c:759-806) on the device: uploads one preprocessed bucket's text, splits it
+ * into lines, sorts them stably by their first bc_len bytes, tokenises them and encodes the barcodes.  Returns one
+ * emab_pair_text_t and one barcode code per pair in sorted order (page-locked memory owned by the ctx) and leaves text and
+ * table resident; emab_align_pairs_resident then runs the pipeline on them (off = prefix sums of the read lengths). */
+int emab_parse_bucket(emab_ctx_t *ctx, const char *text, uint64_t text_len, int bc_len, int is_haplotag, int *n_pairs,
+                      const emab_pair_text_t **pairs, const uint64_t **bcs);
+int emab_align_pairs_resident(emab_ctx_t *ctx, int n_pairs, const int64_t *off, emab_pairs_result_t *result, emab_stats_t *stats);
 int emab_sam_tables(emab_ctx_t *ctx, int n_chrom, const char *const *names, int n_rid, const int32_t *rid2chrom);
 int emab_sam_format(emab_ctx_t *ctx, const emab_sam_job_t *job, char *out, uint64_t out_cap, uint64_t *out_len);
 /* pinned host memory for callers that want their input buffers to take the fast H2D path */

@@ -136,3 +136,44 @@ def test_smem_golden_and_oracle(emab, tiny, port_lib):
     # edge cases: empty read, all-N read, read shorter than a seed
     ivs, _ = emab.smem_batch(c, [np.zeros(0, np.uint8), np.full(50, 4, np.uint8), reads[0][:10]])
     assert [len(x) for x in ivs] == [0, 0, 0]
+
+
+def test_bucket_parser_on_the_device(emab):
+    """emab_parse_bucket (read_special_fastq, src/align.c:759-806) against a plain restatement: lines sorted stably by their first
+    BC_LEN bytes, fields split at single whitespace characters, '@' dropped from the id, barcodes 2-bit encoded (src/util.c:41-60);
+    with and without a final newline, with barcode ties (file order must be kept), tabs as separators, and the error cases."""
+    import random
+    rnd = random.Random(5)
+    ctx = emab.Context(None)
+    bcs = ["".join(rnd.choice("ACGT") for _ in range(16)) for _ in range(40)]
+    lines = []
+    for i in range(3000):
+        bc = rnd.choice(bcs)
+        r1 = "".join(rnd.choice("ACGTN") for _ in range(rnd.randint(30, 151)))
+        r2 = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(30, 151)))
+        sep = "\t" if i % 97 == 0 else " "
+        lines.append(sep.join([bc, "@read%d" % i, r1, "I" * len(r1), r2, "J" * len(r2)]))
+    for tail in ("\n", ""):
+        data = ("\n".join(lines) + tail).encode()
+        tab, codes = emab.parse_bucket(ctx, data)
+        order = sorted(range(len(lines)), key=lambda k: lines[k][:16])     # Python's sort is stable
+        assert len(tab) == len(lines)
+        for k, li in enumerate(order):
+            f = lines[li].replace("\t", " ").split(" ")
+            t = tab[k]
+            get = lambda o, l: data[int(o):int(o) + int(l)].decode()
+            assert get(t["id_off"][0], t["id_len"][0]) == f[1][1:] and get(t["id_off"][1], t["id_len"][1]) == f[1][1:]
+            assert get(t["read_off"][0], t["read_len"][0]) == f[2] and get(t["qual_off"][0], t["qual_len"][0]) == f[3]
+            assert get(t["read_off"][1], t["read_len"][1]) == f[4] and get(t["qual_off"][1], t["qual_len"][1]) == f[5]
+            code = 0
+            for ch in reversed(f[0][:16]):
+                code = code << 2 | "ACGT".index(ch)
+            assert int(codes[k]) == code
+    with pytest.raises(emab.EmabError, match="malformed barcode"):
+        emab.parse_bucket(ctx, b"ACGTNACGTACGTACG @x ACGT IIII ACGT IIII\n")
+    with pytest.raises(emab.EmabError, match="malformed barcode"):
+        emab.parse_bucket(ctx, ("\n".join(lines[:5]) + "\n\n" + lines[6] + "\n").encode())   # an empty line
+    with pytest.raises(emab.EmabError, match="MAX_READ_LEN"):
+        emab.parse_bucket(ctx, (bcs[0] + " @x " + "A" * 201 + " " + "I" * 201 + " ACGT IIII\n").encode())
+    tab, _ = emab.parse_bucket(ctx, b"")
+    assert len(tab) == 0
