@@ -91,11 +91,19 @@ struct RefLaneFetch {  // target base i of an ExtTask, straight from the packed 
 
 enum { A_FETCH = 0, A_CHAIN, A_SEED, A_LEFT, A_RIGHT_BEGIN, A_RIGHT, A_IDLE };
 
-// One warp: 32 reads in flight.  `next` is the global read counter, eh this lane's DP column 0.
-template <class Pools_>
+// What a planned extension looks like to the thread-per-read walk: answered without touching the DP (ext_wave.cuh
+// provides the implementation; a null cache answers nothing).
+struct NoExtCache {
+	__device__ __forceinline__ void set_read(int, int) {}
+	__device__ __forceinline__ bool find(const ExtTask &, ExtResult *, unsigned long long *) const { return false; }
+};
+
+// One warp: 32 reads in flight.  `next` is the global read counter, eh this lane's DP column 0.  `cache` answers the
+// ksw_extend2 calls that were computed ahead (the bucket-wide waves); the others are gathered and run by the warp.
+template <class Pools_, class Cache>
 __device__ void align1_warp(const DevIndex &ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, const Pools_ &p,
                             int rescue_room, uint32_t *eh, unsigned long long *next, int *err, unsigned long long *cells_ext,
-                            unsigned long long *cells_glo)
+                            unsigned long long *cells_glo, Cache cache, unsigned long long *n_inline)
 {
 	int st = A_FETCH;
 	// read
@@ -116,11 +124,30 @@ __device__ void align1_warp(const DevIndex &ix, int n_reads, const uint8_t *seq,
 	int t_try = 0;
 	ExtTask x{};
 	ExtResult res{};
-	unsigned long long visited = 0;
+	unsigned long long visited = 0, cached_cells = 0, inline_calls = 0;
+	// what happens once the result of the pending extension (state A_LEFT / A_RIGHT, task x) is known
+	auto consume = [&](const ExtResult &rr) {
+		if (st == A_LEFT) {
+			if (left_try_done(e, rr, t_try)) { ++t_try; x = left_task(s, cw, t_try); }   // again, with the band doubled
+			else { left_finish(s, e, rr); st = A_RIGHT_BEGIN; }
+		} else {  // A_RIGHT
+			if (right_try_done(e, rr, t_try)) { ++t_try; x = right_task(l_query, s, cw, e, t_try); }
+			else {
+				right_finish(l_query, s, cw, e, rr);
+				seed_finish(chains[ci], seeds, s, e, regs, &n_av);
+				--k; st = A_SEED;
+			}
+		}
+	};
 	for (;;) {
 		bool req = false;
 		while (!req && st != A_IDLE) {
-			if (st == A_LEFT || st == A_RIGHT) { req = true; break; }  // a band retry: x is already set
+			if (st == A_LEFT || st == A_RIGHT) {  // an extension is pending: planned ahead, or for the warp to run
+				unsigned long long cc = 0;
+				if (cache.find(x, &res, &cc)) { cached_cells += cc; consume(res); continue; }
+				req = true;
+				break;
+			}
 			if (st == A_FETCH) {
 				const unsigned long long rr = atomicAdd(next, 1ull);
 				if (rr >= (unsigned long long)n_reads) { st = A_IDLE; break; }
@@ -131,6 +158,7 @@ __device__ void align1_warp(const DevIndex &ix, int n_reads, const uint8_t *seq,
 				chains = p.chains + o; seeds_all = p.seeds + o; srt = p.srt + o;
 				regs = p.regs + (o + (size_t)rescue_room * r);
 				n_chains = p.n_chains[r];
+				cache.set_read(r, n_chains);
 				ci = 0; n_av = 0;
 				st = A_CHAIN;
 			} else if (st == A_CHAIN) {
@@ -154,12 +182,12 @@ __device__ void align1_warp(const DevIndex &ix, int n_reads, const uint8_t *seq,
 				if (!seed_wants_extension(l_query, c, seeds, srt, k, regs, n_av)) { --k; continue; }
 				s = seeds[(uint32_t)srt[k]];
 				seed_begin(c, e);
-				if (s.qbeg) { t_try = 0; x = left_task(s, cw, 0); req = true; st = A_LEFT; }
+				if (s.qbeg) { t_try = 0; x = left_task(s, cw, 0); st = A_LEFT; }
 				else { left_none(s, e); st = A_RIGHT_BEGIN; }
 			} else if (st == A_RIGHT_BEGIN) {
 				if (s.qbeg + s.len != l_query) {
 					e.sc0 = e.a.score;
-					t_try = 0; x = right_task(l_query, s, cw, e, 0); req = true; st = A_RIGHT;
+					t_try = 0; x = right_task(l_query, s, cw, e, 0); st = A_RIGHT;
 				} else {
 					right_none(l_query, s, e);
 					seed_finish(chains[ci], seeds, s, e, regs, &n_av);
@@ -171,22 +199,12 @@ __device__ void align1_warp(const DevIndex &ix, int n_reads, const uint8_t *seq,
 		QueryFetch qf{query, x.q0, x.qstep};
 		RefLaneFetch tf{&ix, x.t0, x.tstep};
 		res = extend(eh, req, x.qlen, x.tlen, x.h0, x.w, x.end_bonus, opt::zdrop, qf, tf, visited);
-		if (req) {
-			if (st == A_LEFT) {
-				if (left_try_done(e, res, t_try)) { ++t_try; x = left_task(s, cw, t_try); }   // again, with the band doubled
-				else { left_finish(s, e, res); st = A_RIGHT_BEGIN; }
-			} else {  // A_RIGHT
-				if (right_try_done(e, res, t_try)) { ++t_try; x = right_task(l_query, s, cw, e, t_try); }
-				else {
-					right_finish(l_query, s, cw, e, res);
-					seed_finish(chains[ci], seeds, s, e, regs, &n_av);
-					--k; st = A_SEED;
-				}
-			}
-		}
+		if (req) { ++inline_calls; consume(res); }
 	}
-	for (int d = 16; d; d >>= 1) visited += __shfl_xor_sync(FULL_MASK, visited, d);
+	visited += cached_cells;
+	for (int d = 16; d; d >>= 1) { visited += __shfl_xor_sync(FULL_MASK, visited, d); inline_calls += __shfl_xor_sync(FULL_MASK, inline_calls, d); }
 	if ((threadIdx.x & 31) == 0 && visited) atomicAdd(cells_ext, visited);
+	if ((threadIdx.x & 31) == 0 && inline_calls && n_inline) atomicAdd(n_inline, inline_calls);
 }
 
 }  // namespace lanes

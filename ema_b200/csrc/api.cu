@@ -207,6 +207,7 @@ extern "C" int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out)
 	if (const char *e = getenv("EMAB_SW_MODE")) c->sw_mode = atoi(e);  // tuning knob, see emab_set_sw_mode
 	if (const char *e = getenv("EMAB_RESCUE_PLAN")) c->rescue_plan = atoi(e) != 0;  // tuning knob: 0 = one warp-per-pair rescue kernel
 	if (const char *e = getenv("EMAB_EXT_PLAN")) c->ext_plan = atoi(e) != 0;        // 0 = every ksw_extend2 inline in the warp-per-read kernel
+	if (const char *e = getenv("EMAB_REPLAY_LANES")) c->replay_lanes = atoi(e) != 0;  // 0 = warp-per-read replay of the extension plans
 	if (const char *e = getenv("EMAB_GLOB_PLAN")) c->glob_plan = atoi(e) != 0;      // 0 = every ksw_global2 inline in the warp-per-pair kernel
 	if (const char *e = getenv("EMAB_PL_BPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->pl_bps = v; }  // persistent SW grids: blocks per SM
 	*out = c;

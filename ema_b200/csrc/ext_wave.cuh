@@ -144,4 +144,20 @@ __device__ __forceinline__ bool ext_plan_lookup(const ExtPlan *plans, int n_plan
 	return false;
 }
 
+// the same lookup as a cache object for the thread-per-read walk (lanes::align1_warp)
+struct PlanCache {
+	const ExtPlan *plans;
+	const int32_t *chain_off;
+	const ExtPlan *mine = nullptr;
+	int n_mine = 0;
+	__device__ __forceinline__ void set_read(int r, int n_chains) { mine = plans + chain_off[r]; n_mine = n_chains; }
+	__device__ __forceinline__ bool find(const ExtTask &x, ExtResult *res, unsigned long long *cells) const
+	{
+		uint32_t c = 0;
+		if (!ext_plan_lookup(mine, n_mine, x.q0, x.qstep, x.qlen, x.t0, x.tlen, x.w, x.h0, res, &c)) return false;
+		*cells = c;
+		return true;
+	}
+};
+
 #endif

@@ -1359,14 +1359,17 @@ static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size
 	int rc = emab_parse_bucket(wk.ctx, (const char *)wk.seq.p, (uint64_t)len, s->bc_len, s->is_haplotag ? 1 : 0, &n, &pt, &bcs);
 	if (rc) { *err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
 	std::vector<Pair> pairs((size_t)n);
-	#pragma omp parallel for num_threads(wk.n_threads) schedule(static)
+	#pragma omp parallel num_threads(wk.n_threads)
+	{
+	HostProf hp(HP_TOKENS);
+	#pragma omp for schedule(static)
 	for (int i = 0; i < n; ++i) {
-		HostProf hp(HP_TOKENS);
 		Pair &P = pairs[(size_t)i];
 		const emab_pair_text_t &t = pt[i];
 		P.bc = bcs[i];
 		P.id1 = P.id2 = std::string_view(data + t.id_off[0], t.id_len[0]);
 		for (int m = 0; m < 2; ++m) { P.read[m] = std::string_view(data + t.read_off[m], t.read_len[m]); P.qual[m] = std::string_view(data + t.qual_off[m], t.qual_len[m]); }
+	}
 	}
 	const double t1 = now_ms();
 	TextSrc src;

@@ -252,7 +252,20 @@ __global__ void __launch_bounds__(32)
 k_align1_lanes(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p, int *err, unsigned long long *counters)
 {
 	extern __shared__ uint32_t lanes_smem[];
-	lanes::align1_warp(ix, n_reads, seq, off, occ_off, p, RESCUE_ROOM, lanes_smem + threadIdx.x, &counters[5], err, &counters[0], &counters[3]);
+	lanes::align1_warp(ix, n_reads, seq, off, occ_off, p, RESCUE_ROOM, lanes_smem + threadIdx.x, &counters[5], err, &counters[0], &counters[3],
+	                   lanes::NoExtCache(), nullptr);
+}
+
+// the replay of the planned extensions with one THREAD per read: the reference's control flow of 32 reads per warp-step
+// instead of one (the warp-per-read replay runs every scalar decision on 32 lanes), extensions answered from the plans;
+// the few that were not planned are gathered and run by the warp (lanes::extend)
+__global__ void __launch_bounds__(32)
+k_align1_replay(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, const int32_t *occ_off, Pools p, int *err, unsigned long long *counters,
+                const ExtPlan *plans, const int32_t *chain_off)
+{
+	extern __shared__ uint32_t lanes_smem[];
+	lanes::align1_warp(ix, n_reads, seq, off, occ_off, p, RESCUE_ROOM, lanes_smem + threadIdx.x, &counters[5], err, &counters[0], &counters[3],
+	                   PlanCache{plans, chain_off}, &counters[13]);
 }
 
 // Mate rescue in three kernels.  bwa_mem_mate_sw's rescue half is sequential per pair (every mem_matesw sees the
@@ -667,6 +680,15 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 				d_plans = plans; d_chain_off = chain_off; ext_waves_ran = true;
 			}
 		}
+		if (d_plans && c->replay_lanes) {
+			const size_t smem = lanes::smem_per_warp(max_len);
+			CUDA_TRY(cudaFuncSetAttribute(k_align1_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+			int per_sm = (int)((227 * 1024) / (smem + 1024));
+			per_sm = per_sm > 32 ? 32 : (per_sm < 1 ? 1 : per_sm);
+			int lgrid = c->n_sm * per_sm;
+			if (lgrid > (R + 31) / 32) lgrid = (R + 31) / 32;
+			k_align1_replay<<<lgrid, 32, smem, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, d_err, c->d_counters, d_plans, d_chain_off);
+		} else
 		k_align1<<<grid, PL_WARPS * 32, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, c->b[16].as<uint8_t>(), z_cap,
 		                                          c->b[17].as<uint32_t>(), d_err, c->d_counters, d_plans, d_chain_off);
 	}

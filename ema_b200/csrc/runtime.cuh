@@ -84,6 +84,7 @@ struct emab_ctx {
 	bool rescue_plan = true; // mate-rescue alignments planned and run as one balanced batch (pipeline.cu, k_rescue_plan)
 	bool ext_plan = true;    // ksw_extend2 calls of every chain's top seed run ahead as two bucket-wide waves (ext_wave.cuh)
 	bool glob_plan = true;   // ksw_global2 calls of mem_reg2aln likewise (glob_wave.cuh)
+	bool replay_lanes = true; // the extension replay walks one read per THREAD (k_align1_replay) instead of per warp
 	bool consts_ready = false;
 	bool em_log_ready = false; // emab_em_batch's ln(n) table is resident (slot 30)
 	bool text_ready = false;   // the batch's text + pair table are resident (slots 31, 27: emab_align_pairs_text / emab_parse_bucket)
