@@ -36,6 +36,17 @@ k_seed_wide(DevIndex ix, SeedBatch b)
 	seed_quads_wide(ix, b, seedq_smem);
 }
 
+// the same with ONE WARP per block: a block leaves the SM as soon as its eight reads' queues are dry, so the kernel's long
+// tail (a few hundred long reads) holds a few warps' registers instead of every block's, and the next bucket's kernels
+// (other streams) move in — what the end-to-end rate of several buckets in flight needs
+template <int MIN_BLOCKS>
+static __global__ void __launch_bounds__(32, MIN_BLOCKS)
+k_seed_wide1(DevIndex ix, SeedBatch b)
+{
+	extern __shared__ uint4 seedq_smem[];
+	seed_quads_wide(ix, b, seedq_smem);
+}
+
 // one lane per read, Occ blocks staged through shared memory by cp.async (seed_quad.cuh: StagedFm)
 template <int MIN_BLOCKS>
 static __global__ void __launch_bounds__(SEED_BLOCK, MIN_BLOCKS)
@@ -73,7 +84,14 @@ static inline int seed_mode()
 	if (!v) { const char *e = getenv("EMAB_SEED_MODE"); v = e ? atoi(e) : 3; if (v < 1 || v > 4) v = 3; }
 	return v;
 }
-// EMAB_SEED_BPS: resident 128-thread blocks per SM of the persistent seeding grid (tuning knob)
+// EMAB_SEED_BLOCK: threads per block of the four-lanes-per-read kernel, 32 (default) or 128
+static inline int seed_block()
+{
+	static int v = 0;
+	if (!v) { const char *e = getenv("EMAB_SEED_BLOCK"); v = e ? atoi(e) : 32; if (v != 128) v = 32; }
+	return v;
+}
+// EMAB_SEED_BPS: resident 128-thread blocks (or groups of four one-warp blocks) per SM of the persistent seeding grid (tuning knob)
 static inline int seed_blocks_per_sm()
 {
 	static int v = 0;
@@ -89,7 +107,10 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
 	cudaStream_t st = c->stream;
 	const bool quad = seed_mode() == 4 || seed_mode() == 3;
 	int grid = c->n_sm * seed_blocks_per_sm();
-	const int per_block = quad ? SEED_BLOCK / 4 : SEED_BLOCK;                // reads in flight per block
+	const bool warp_blocks = seed_mode() == 3 && seed_block() == 32;
+	if (warp_blocks) grid *= 4;
+	const int block = warp_blocks ? 32 : SEED_BLOCK;
+	const int per_block = quad ? block / 4 : block;                          // reads in flight per block
 	const int want = (2 * R + per_block - 1) / per_block;  // never more lanes than (read, role) items
 	if (grid > want) grid = want;
 	if (grid < 1) grid = 1;
@@ -108,7 +129,10 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
 	CUDA_TRY(cudaMemsetAsync(b.queue, 0, 16, st));
 	if (seed_mode() == 3) {
 		if (c->ix->d.seq_len >> 39) { snprintf(emab_errbuf, sizeof emab_errbuf, "reference too long for the packed interval lists (2^39)"); return EMAB_ERR_ARG; }
-		if (seed_blocks_per_sm() >= 6) k_seed_wide<6><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
+		if (warp_blocks) {
+			if (seed_blocks_per_sm() >= 6) k_seed_wide1<24><<<grid, 32, SEEDQ_SMEM / 4, st>>>(c->ix->d, b);
+			else k_seed_wide1<20><<<grid, 32, SEEDQ_SMEM / 4, st>>>(c->ix->d, b);
+		} else if (seed_blocks_per_sm() >= 6) k_seed_wide<6><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
 		else k_seed_wide<5><<<grid, SEED_BLOCK, SEEDQ_SMEM, st>>>(c->ix->d, b);
 	} else if (quad) {
 		if (c->ix->d.seq_len >> 39) { snprintf(emab_errbuf, sizeof emab_errbuf, "reference too long for the packed interval lists (2^39)"); return EMAB_ERR_ARG; }

@@ -195,7 +195,8 @@ __device__ __forceinline__ void seed_quads_wide(const DevIndex &ix, const SeedBa
 	QuadFeeder f12{b, 0, q, qmask};
 	QueueFeeder f3{b, 1};
 	PtrLists none{{nullptr, nullptr}};
-	if (((threadIdx.x >> 5) & 3) == 3) { seed_p3(tfm, f3, none); seed_p12(tfm, f12, lists, coop); }
+	const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // roles by warp whatever the block size: every fourth warp starts on pass 3
+	if ((gwarp & 3) == 3) { seed_p3(tfm, f3, none); seed_p12(tfm, f12, lists, coop); }
 	else { seed_p12(tfm, f12, lists, coop); seed_p3(tfm, f3, none); }
 	unsigned touches = fm.touches;
 	for (int d = 16; d; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
