@@ -153,6 +153,11 @@ def set_sw_mode(ctx: Context, mode: int):
     _check(lib().emab_set_sw_mode(ctx._h, mode))
 
 
+def set_seed_mode(ctx: Context, mode: int):
+    """5 (default) = seed_hot.cuh (x1 not carried); 1-4 = the exact forms; 0 = EMAB_SEED_MODE or the default."""
+    _check(lib().emab_set_seed_mode(ctx._h, mode))
+
+
 def extend_resident_load(ctx: Context, q2d: np.ndarray, t2d: np.ndarray, h0):
     """Upload n fixed-length tasks (q2d[n,qlen], t2d[n,tlen]) once for emab_extend_resident_run."""
     n = q2d.shape[0]

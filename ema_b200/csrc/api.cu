@@ -9,6 +9,7 @@
 #include "runtime.cuh"
 #include "fmindex.cuh"
 #include "seed_launch.cuh"
+#include "seed_hot.cuh"
 #include "ksw_warp.cuh"
 #include "ksw_lanes.cuh"
 
@@ -58,6 +59,30 @@ __global__ void k_build_dense_sa(DevIndex ix, T *dense, uint64_t n_sa)
 		--s;
 		dense[k] = (T)s;
 	}
+}
+
+// the derived structures of the default seeding form (seed_hot.cuh)
+__global__ void k_build_hot(const uint4 *bwt, uint4 *hot, uint64_t n_hot)
+{
+	const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_hot) return;
+	uint4 o[4];
+	hot_build_block(bwt, b, o);
+	for (int c = 0; c < 4; ++c) hot[b * 4 + c] = o[c];
+}
+__global__ void k_build_kmer_level1(DevIndex ix, uint4 *kmer)
+{
+	if (threadIdx.x < 4) kmer[threadIdx.x] = kmer_level1(ix, threadIdx.x);
+}
+__global__ void k_build_kmer_level(DevIndex ix, uint4 *kmer, int t)   // level t + 1 from level t
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 1ull << (2 * t)) return;
+	Fm fm{ix, 0};
+	uint4 o[4];
+	kmer_children(fm, kmer[kmer_level_off(t) + i], o);
+	uint4 *dst = kmer + kmer_level_off(t + 1) + i * 4;
+	for (int b = 0; b < 4; ++b) dst[b] = o[b];
 }
 
 extern "C" int emab_index_load(const char *prefix, int device, emab_index_t **out)
@@ -114,7 +139,7 @@ extern "C" int emab_index_load(const char *prefix, int device, emab_index_t **ou
 	memcpy(sas.data() + 1, sw + 7, (ix->n_sa - 1) * 8);
 	CUDA_TRY(cudaMalloc(&ix->d_sa_sampled, sas_bytes));
 	CUDA_TRY(cudaMemcpy(ix->d_sa_sampled, sas.data(), sas_bytes, cudaMemcpyHostToDevice));
-	CUDA_TRY(cudaMalloc(&ix->d_pac, pac.size() + 16));
+	CUDA_TRY(cudaMalloc(&ix->d_pac, pac.size() + 64));   // 16-byte chunk loads may run past the last base (seed_rq.cuh)
 	CUDA_TRY(cudaMemcpy(ix->d_pac, pac.data(), pac.size(), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMalloc(&ix->d_ann_off, ix->ann_offset.size() * 8));
 	CUDA_TRY(cudaMemcpy(ix->d_ann_off, ix->ann_offset.data(), ix->ann_offset.size() * 8, cudaMemcpyHostToDevice));
@@ -131,7 +156,7 @@ extern "C" int emab_index_load(const char *prefix, int device, emab_index_t **ou
 	const char *force64 = getenv("EMAB_SA64");
 	const bool small = ix->d.seq_len < 0xffffffffull && !(force64 && atoi(force64) == 1);
 	size_t dense_bytes = (ix->d.seq_len + 1) * (small ? 4 : 8);
-	CUDA_TRY(cudaMalloc(&ix->d_sa_dense, dense_bytes));
+	CUDA_TRY(cudaMalloc(&ix->d_sa_dense, dense_bytes + 16));   // read in aligned 16-byte chunks (seed_rq.cuh)
 	cudaEvent_t e0, e1;
 	CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
 	CUDA_TRY(cudaEventRecord(e0));
@@ -148,6 +173,32 @@ extern "C" int emab_index_load(const char *prefix, int device, emab_index_t **ou
 	ix->build_ms = ms;
 	if (small) ix->d.sa32 = (const uint32_t *)ix->d_sa_dense; else ix->d.sa64 = (const uint64_t *)ix->d_sa_dense;
 	ix->hbm_bytes = bwt_bytes + sas_bytes + pac.size() + dense_bytes;
+	{  // one-hot Occ blocks and the k-mer interval table (seed_hot.cuh); EMAB_KMER_K overrides the table depth (0 = none)
+		if (ix->d.seq_len >> 39) { snprintf(emab_errbuf, sizeof emab_errbuf, "reference too long for the packed intervals (2^39)"); emab_index_free(ix); return EMAB_ERR_ARG; }
+		const uint64_t n_hot = (ix->d.seq_len >> 6) + 1;
+		CUDA_TRY(cudaMemset((char *)ix->d_bwt + bwt_bytes, 0, 64));
+		CUDA_TRY(cudaMalloc(&ix->d_hot, n_hot * 64));
+		k_build_hot<<<(unsigned)((n_hot + 255) / 256), 256>>>((const uint4 *)ix->d_bwt, (uint4 *)ix->d_hot, n_hot);
+		ix->d.hot = (const uint4 *)ix->d_hot;
+		int K = kmer_default_k(ix->d.seq_len);
+		if (const char *e = getenv("EMAB_KMER_K")) { K = atoi(e); K = K < 0 ? 0 : (K > EMAB_KMER_MAX ? EMAB_KMER_MAX : K); }
+		ix->d.kmer_k = 0;
+		size_t kmer_bytes = 0;
+		if (K > 0) {
+			kmer_bytes = kmer_total(K) * 16;
+			CUDA_TRY(cudaMalloc(&ix->d_kmer, kmer_bytes));
+			k_build_kmer_level1<<<1, 32>>>(ix->d, (uint4 *)ix->d_kmer);
+			for (int t = 1; t < K; ++t) {
+				const uint64_t n = 1ull << (2 * t);
+				k_build_kmer_level<<<(unsigned)((n + 127) / 128), 128>>>(ix->d, (uint4 *)ix->d_kmer, t);
+			}
+			ix->d.kmer = (const uint4 *)ix->d_kmer;
+			ix->d.kmer_k = K;
+		}
+		CUDA_TRY(cudaDeviceSynchronize());
+		CUDA_TRY(cudaGetLastError());
+		ix->hbm_bytes += n_hot * 64 + kmer_bytes;
+	}
 	*out = ix;
 	return EMAB_OK;
 }
@@ -156,6 +207,7 @@ extern "C" void emab_index_free(emab_index_t *ix)
 {
 	if (!ix) return;
 	cudaSetDevice(ix->device);
+	cudaFree(ix->d_hot); cudaFree(ix->d_kmer);
 	cudaFree(ix->d_bwt); cudaFree(ix->d_sa_dense); cudaFree(ix->d_sa_sampled); cudaFree(ix->d_pac); cudaFree(ix->d_ann_off); cudaFree(ix->d_ann_len);
 	delete ix;
 }
@@ -246,6 +298,14 @@ extern "C" int emab_ctx_set_wait(emab_ctx_t *c, int mode)
 {
 	if (!c || mode < 0 || mode > 2) return EMAB_ERR_ARG;
 	if (!c->wait_fixed) c->wait_mode = mode;
+	return EMAB_OK;
+}
+
+// 0 = EMAB_SEED_MODE or the default (5); 1-4 = the exact forms of seed.cuh / seed_quad.cuh; 5 = seed_hot.cuh
+extern "C" int emab_set_seed_mode(emab_ctx_t *c, int mode)
+{
+	if (!c || mode < 0 || mode > 5) return EMAB_ERR_ARG;
+	c->seed_mode = mode;
 	return EMAB_OK;
 }
 

@@ -72,6 +72,10 @@ struct DevIndex {
 	const int64_t *ann_offset;   // n_seqs
 	const int32_t *ann_len;      // n_seqs
 	int seed_load_both;          // tuning/measurement knob (EMAB_SEED_LOAD_BOTH=1): bwt_2occ4 requests its second block even when it is the first
+	// derived at load for the default seeding form (seed_hot.cuh); null / 0 when not built
+	const uint4 *hot;            // one-hot Occ blocks: per 64 symbols, per base {u64 count before the block, u64 "symbol i is this base"}
+	const uint4 *kmer;           // packed intervals of every k-mer, levels 1..kmer_k back to back (kmer_level_off)
+	int kmer_k;
 };
 
 struct Intv {  // bwtintv_t (bwa/bwt.h:62-64)
@@ -132,8 +136,10 @@ struct Aln {  // what append_alignments keeps of mem_aln_t / SingleReadAlignment
 #define EMAB_HD __host__ __device__ inline
 #ifdef __CUDA_ARCH__
 #define emab_popc(x) __popc(x)
+#define emab_popcll(x) __popcll(x)
 #else
 #define emab_popc(x) __builtin_popcount(x)
+#define emab_popcll(x) __builtin_popcountll(x)
 #endif
 EMAB_HD int imax(int a, int b) { return a > b ? a : b; }
 EMAB_HD int imin(int a, int b) { return a < b ? a : b; }

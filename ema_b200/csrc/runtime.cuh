@@ -52,6 +52,7 @@ struct emab_index {
 	DevIndex d{};            // device pointers + scalars (passed to kernels by value)
 	// owned device allocations
 	void *d_bwt = nullptr, *d_sa_dense = nullptr, *d_sa_sampled = nullptr, *d_pac = nullptr, *d_ann_off = nullptr, *d_ann_len = nullptr;
+	void *d_hot = nullptr, *d_kmer = nullptr;   // seed_hot.cuh
 	// host mirrors
 	std::vector<std::string> names;
 	std::vector<int64_t> ann_offset;
@@ -81,6 +82,7 @@ struct emab_ctx {
 	// resident SW microbench inputs
 	int res_n = 0, res_qcap = 0;
 	int sw_mode = 0;         // see emab_set_sw_mode (include/ema_b200.h)
+	int seed_mode = 0;       // see emab_set_seed_mode; 0 = EMAB_SEED_MODE or the default
 	bool rescue_plan = true; // mate-rescue alignments planned and run as one balanced batch (pipeline.cu, k_rescue_plan)
 	bool ext_plan = true;    // ksw_extend2 calls of every chain's top seed run ahead as two bucket-wide waves (ext_wave.cuh)
 	bool glob_plan = true;   // ksw_global2 calls of mem_reg2aln likewise (glob_wave.cuh)

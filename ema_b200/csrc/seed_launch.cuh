@@ -6,6 +6,8 @@
 #include "runtime.cuh"
 #include "seed.cuh"
 #include "seed_quad.cuh"
+#include "seed_hot.cuh"
+#include "seed_rq.cuh"
 
 #define SEED_BLOCK 128
 
@@ -56,6 +58,25 @@ k_seed_staged(DevIndex ix, SeedBatch b)
 	seed_staged(ix, b, seedq_smem);
 }
 
+// the default: one-hot Occ blocks, k-mer start table, text comparison at a unique locus (seed_hot.cuh); four lanes per
+// read, one warp per block
+template <int MIN_BLOCKS>
+static __global__ void __launch_bounds__(32, MIN_BLOCKS)
+k_seed_hot(DevIndex ix, SeedBatch b)
+{
+	extern __shared__ uint4 seedq_smem[];
+	seed_hot_quads(ix, b, seedq_smem);
+}
+
+// ... arranged as a request loop (seed_rq.cuh): the form the pipeline runs
+template <int MIN_BLOCKS>
+static __global__ void __launch_bounds__(32, MIN_BLOCKS)
+k_seed_rq(DevIndex ix, RqBatch rb)
+{
+	extern __shared__ uint4 seedq_smem[];
+	seed_rq_warp(ix, rb, (uint32_t *)seedq_smem);
+}
+
 static __global__ void __launch_bounds__(128)
 k_seed_finish(SeedBatch b, int32_t *n_intv, int32_t *occ_cnt)
 {
@@ -78,12 +99,17 @@ k_seed_finish(SeedBatch b, int32_t *n_intv, int32_t *occ_cnt)
 // 40 000-pair bucket (profiles/r2e_*): mode 1 5.1 ms, mode 4 6.0-6.5 ms — the quad form moves 16 % less DRAM traffic and
 // keeps its lists in shared memory, but runs the loops' bookkeeping on four lanes per read: 2.5 x the warp instructions,
 // 70 % ALU-pipe utilisation; the kernel's length is set by its longest reads' dependent chains, not by bandwidth.
-static inline int seed_mode()
+//   3 = four lanes per read, one backward-round entry per lane (seed_quads_wide); 5 (default) = seed_hot.cuh
+static inline int seed_mode_env()   // read at every launch: a measurement run can switch forms between buckets
 {
-	static int v = 0;
-	if (!v) { const char *e = getenv("EMAB_SEED_MODE"); v = e ? atoi(e) : 3; if (v < 1 || v > 4) v = 3; }
-	return v;
+	const char *e = getenv("EMAB_SEED_MODE");
+	const int v = e ? atoi(e) : 5;
+	return v < 1 || v > 5 ? 5 : v;
 }
+// EMAB_SEED_HOT_FORM=1: the first device arrangement of seed_hot.cuh (state machine with loads inside the states), kept for A/B runs
+static inline bool seed_hot_first_form() { const char *e = getenv("EMAB_SEED_HOT_FORM"); return e && atoi(e) == 1; }
+static thread_local int seed_mode_now = 0;   // the mode of the launch in progress (ctx override or the environment's)
+static inline int seed_mode() { return seed_mode_now ? seed_mode_now : seed_mode_env(); }
 // EMAB_SEED_BLOCK: threads per block of the four-lanes-per-read kernel, 32 (default) or 128
 static inline int seed_block()
 {
@@ -95,19 +121,22 @@ static inline int seed_block()
 static inline int seed_blocks_per_sm()
 {
 	static int v = 0;
-	if (!v) { const char *e = getenv("EMAB_SEED_BPS"); v = e ? atoi(e) : 0; if (v < 1 || v > 16) v = seed_mode() == 4 ? 8 : (seed_mode() == 3 ? 5 : 6); }
-	return v;
+	if (!v) { const char *e = getenv("EMAB_SEED_BPS"); v = e ? atoi(e) : -1; if (v < 1 || v > 16) v = -1; }
+	if (v > 0) return v;
+	return seed_mode() == 4 ? 8 : (seed_mode() == 3 ? 5 : 6);
 }
 
 // Device buffers: d_intv [R][max_intv], d_n_intv [R], d_occ_cnt [R] or null, *d_err int, *d_touches u64 (zeroed by the caller).
-// Uses ctx slots 4 (lane scratch), 25 (pass-3 lists), 26 (per-pass counts + the two queue counters).
+// Uses ctx slots 4 (lane scratch), 25 (pass-3 lists), 26 (per-pass counts + the two queue counters), 41 (2-bit packed reads).
 static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, const int64_t *d_off, Intv *d_intv, int max_intv,
                        int32_t *d_n_intv, int32_t *d_occ_cnt, int *d_err, unsigned long long *d_touches, int *launches)
 {
 	cudaStream_t st = c->stream;
-	const bool quad = seed_mode() == 4 || seed_mode() == 3;
+	seed_mode_now = c->seed_mode;
+	if (seed_mode() == 5 && !c->ix->d.hot) seed_mode_now = 3;
+	const bool quad = seed_mode() == 4 || seed_mode() == 3 || seed_mode() == 5;
 	int grid = c->n_sm * seed_blocks_per_sm();
-	const bool warp_blocks = seed_mode() == 3 && seed_block() == 32;
+	const bool warp_blocks = (seed_mode() == 3 && seed_block() == 32) || seed_mode() == 5;
 	if (warp_blocks) grid *= 4;
 	const int block = warp_blocks ? 32 : SEED_BLOCK;
 	const int per_block = quad ? block / 4 : block;                          // reads in flight per block
@@ -127,7 +156,20 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
 	b.n12 = (int32_t *)(b.queue + 2); b.n3 = b.n12 + R;
 	b.err = d_err; b.touches = d_touches;
 	CUDA_TRY(cudaMemsetAsync(b.queue, 0, 16, st));
-	if (seed_mode() == 3) {
+	if (seed_mode() == 5 && !seed_hot_first_form()) {
+		if (int rc = c->b[41].ensure((size_t)R * RQ_PACKED_BYTES + 64)) return rc;
+		RqBatch rb{b, c->b[41].as<uint32_t>()};
+		k_pack_reads<<<(R * 24 + 255) / 256, 256, 0, st>>>(d_seq, d_off, R, c->b[41].as<uint32_t>());
+		++*launches;
+		if (seed_blocks_per_sm() >= 7) k_seed_rq<28><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
+		else if (seed_blocks_per_sm() >= 6) k_seed_rq<24><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
+		else if (seed_blocks_per_sm() >= 5) k_seed_rq<20><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
+		else k_seed_rq<16><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
+	} else if (seed_mode() == 5) {
+		if (seed_blocks_per_sm() >= 8) k_seed_hot<32><<<grid, 32, SEEDQ_SMEM / 4, st>>>(c->ix->d, b);
+		else if (seed_blocks_per_sm() >= 6) k_seed_hot<24><<<grid, 32, SEEDQ_SMEM / 4, st>>>(c->ix->d, b);
+		else k_seed_hot<16><<<grid, 32, SEEDQ_SMEM / 4, st>>>(c->ix->d, b);
+	} else if (seed_mode() == 3) {
 		if (c->ix->d.seq_len >> 39) { snprintf(emab_errbuf, sizeof emab_errbuf, "reference too long for the packed interval lists (2^39)"); return EMAB_ERR_ARG; }
 		if (warp_blocks) {
 			if (seed_blocks_per_sm() >= 6) k_seed_wide1<24><<<grid, 32, SEEDQ_SMEM / 4, st>>>(c->ix->d, b);

@@ -112,8 +112,16 @@ int emab_int_peak(emab_ctx_t *ctx, int kind, int iters, double *gops_per_s, doub
 /* ---- FM index --------------------------------------------------------------------------------
  * emab_sa_batch      = bwt_sa (bwa/bwt.c:86) for n SA indices; mode 0 = dense SA, 1 = LF walk
  * emab_smem_batch    = mem_collect_intv (bwa/bwamem.c:140) for n reads: intervals[n*max_intv*4]
- *                      (x0,x1,x2,info), n_intv[n]; *touches = 64-byte Occ-block loads issued
+ *                      (x0,x1,x2,info), n_intv[n]
+ * emab_set_seed_mode   which form of the seeding kernel a ctx runs (pipeline and emab_smem_batch alike):
+ *                      5 (default; 0 = EMAB_SEED_MODE or 5): one-hot Occ blocks + k-mer start table + text comparison at
+ *                        a unique locus (csrc/seed_hot.cuh).  Intervals carry the coordinates mem_chain reads — x0, x2,
+ *                        info (bwa/bwamem.c:163-164,294-309) — and x1 = 0: x[1] is bwt_smem1a's forward working
+ *                        coordinate, read by nothing after the forward sweep.  *touches = 32-byte sectors requested.
+ *                      1-4: exact restatements over bwa's Occ layout (csrc/seed.cuh, seed_quad.cuh): x1 as the
+ *                        reference leaves it; *touches = 64-byte Occ-block loads as the reference issues them.
  */
+int emab_set_seed_mode(emab_ctx_t *ctx, int mode);
 int emab_sa_batch(emab_ctx_t *ctx, int n, const int64_t *k, int64_t *out, int mode);
 int emab_smem_batch(emab_ctx_t *ctx, int n, const uint8_t *seq, const int64_t *off, int64_t *intervals, int32_t *n_intv,
                     int max_intv, int64_t *touches);

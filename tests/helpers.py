@@ -36,6 +36,22 @@ def nt4(seq: bytes | str) -> np.ndarray:
     return tab[np.frombuffer(seq, dtype=np.uint8)]
 
 
+def read_fasta_nt4(path):
+    """contigs of a FASTA file as nt4 arrays, in file order"""
+    out, cur = [], []
+    with open(path, "rb") as f:
+        for ln in f:
+            if ln.startswith(b">"):
+                if cur:
+                    out.append(nt4(b"".join(cur)))
+                cur = []
+            else:
+                cur.append(ln.strip())
+    if cur:
+        out.append(nt4(b"".join(cur)))
+    return out
+
+
 def pack(seqs):
     """list of uint8 arrays -> (concatenated, int64 offsets[n+1])"""
     off = np.zeros(len(seqs) + 1, dtype=np.int64)

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <vector>
 #include "../../ema_b200/csrc/seed.cuh"
+#include "../../ema_b200/csrc/seed_hot.cuh"
 #include "../../ema_b200/csrc/chain.cuh"
 #include "../../ema_b200/csrc/align.cuh"
 #include "../../ema_b200/csrc/align_lanes.cuh"
@@ -27,7 +28,32 @@ struct HostIndex {
 	std::vector<uint4> bwt_aligned;  // uint4 loads need 16-byte alignment; the file image is at +40
 	std::vector<uint32_t> sa32;
 	std::vector<uint64_t> sa64;
+	std::vector<uint4> hot, kmer;   // the derived structures of seed_hot.cuh, built by the same thread-scalar code as on the device
 };
+
+static void build_hot_kmer(HostIndex *h, int K)
+{
+	DevIndex &d = h->d;
+	const uint64_t n_hot = (d.seq_len >> 6) + 1;
+	h->bwt_aligned.resize(h->bwt_aligned.size() + 8);   // the last one-hot block reads a whole 64-byte block
+	d.bwt = h->bwt_aligned.data();
+	h->hot.assign(n_hot * 4, make_uint4(0, 0, 0, 0));
+	for (uint64_t b = 0; b < n_hot; ++b) hot_build_block(d.bwt, b, h->hot.data() + b * 4);
+	d.hot = h->hot.data();
+	if (K < 0) K = kmer_default_k(d.seq_len);
+	if (K > EMAB_KMER_MAX) K = EMAB_KMER_MAX;
+	d.kmer_k = K;
+	d.kmer = nullptr;
+	if (K <= 0) return;
+	h->kmer.assign(kmer_total(K), make_uint4(0, 0, 0, 0));
+	for (int b = 0; b < 4; ++b) h->kmer[b] = kmer_level1(d, b);
+	Fm fm{d, 0};
+	for (int t = 1; t < K; ++t) {
+		const uint64_t n = 1ull << (2 * t), po = kmer_level_off(t), co = kmer_level_off(t + 1);
+		for (uint64_t i = 0; i < n; ++i) kmer_children(fm, h->kmer[po + i], h->kmer.data() + co + i * 4);
+	}
+	d.kmer = h->kmer.data();
+}
 
 static thread_local long long hs_cnt[6];  // DP calls: extend, global, local; cells: extend, global, local (instrumentation for tools)
 
@@ -112,7 +138,25 @@ void *hs_index_load(const char *prefix)
 		}
 	}
 	d.sa32 = h->sa32.data();
+	build_hot_kmer(h, -1);
 	return h;
+}
+
+// rebuild the k-mer table with another K (0 = no table): the tests walk the table logic at several depths
+void hs_set_kmer_k(void *h_, int K) { build_hot_kmer((HostIndex *)h_, K); }
+int hs_kmer_k(void *h_) { return ((HostIndex *)h_)->d.kmer_k; }
+
+// the default seeding form (seed_hot.cuh): intervals as (x0, x1 = 0, x2, info); *sectors = 32-byte sectors requested
+int hs_collect_intv_hot(void *h_, int len, const uint8_t *seq, int64_t *out, int max, int64_t *sectors)
+{
+	HostIndex *h = (HostIndex *)h_;
+	std::vector<Intv> mem(EMAB_MAX_INTV), b0(EMAB_MAX_READ_LEN + 1), b1(EMAB_MAX_READ_LEN + 1);
+	int ovf = 0;
+	unsigned sec = 0;
+	int n = collect_intv_hot(h->d, len, seq, mem.data(), EMAB_MAX_INTV, b0.data(), b1.data(), &ovf, &sec);
+	for (int i = 0; i < n && i < max; ++i) { out[i*4] = mem[i].x0; out[i*4+1] = mem[i].x1; out[i*4+2] = mem[i].x2; out[i*4+3] = mem[i].info; }
+	if (sectors) *sectors = sec;
+	return ovf ? -1 : n;
 }
 
 int hs_collect_intv(void *h_, int len, const uint8_t *seq, int64_t *out, int max)
@@ -124,6 +168,18 @@ int hs_collect_intv(void *h_, int len, const uint8_t *seq, int64_t *out, int max
 	int n = collect_intv(fm, len, seq, mem.data(), EMAB_MAX_INTV, b0.data(), b1.data(), &ovf);
 	for (int i = 0; i < n && i < max; ++i) { out[i*4] = mem[i].x0; out[i*4+1] = mem[i].x1; out[i*4+2] = mem[i].x2; out[i*4+3] = mem[i].info; }
 	return ovf ? -1 : n;
+}
+
+// work profile of the default seeding form for one read: out[10], see HotFm::prof (measurement aid for DESIGN.md)
+int hs_hot_profile(void *h_, int len, const uint8_t *seq, int64_t *out)
+{
+	HostIndex *h = (HostIndex *)h_;
+	std::vector<Intv> mem(4096), b0(EMAB_MAX_READ_LEN + 1), b1(EMAB_MAX_READ_LEN + 1);
+	int ovf = 0;
+	unsigned sec = 0, prof[10];
+	int n = collect_intv_hot(h->d, len, seq, mem.data(), 4096, b0.data(), b1.data(), &ovf, &sec, prof);
+	for (int k = 0; k < 10; ++k) out[k] = prof[k];
+	return n;
 }
 
 // the nested (reference-shaped) form, for cross-checking the flattened one; *touches = Occ-block loads

@@ -118,24 +118,67 @@ def test_index_and_sa(emab, tiny):
 
 
 def test_smem_golden_and_oracle(emab, tiny, port_lib):
+    """the exact seeding forms (EMAB_SEED_MODE 1, 3, 4): golden intervals with all four fields and the oracle's count of
+    64-byte Occ-block loads"""
     ix, c = tiny
     g = np.load(os.path.join(G, "fm_golden.npz"))
     reads = unpack(g["reads"], g["roff"])
-    ivs, touches = emab.smem_batch(c, reads)
-    pos = 0
-    for i, (iv, n) in enumerate(zip(ivs, g["n_intv"])):
-        assert len(iv) == n and np.array_equal(iv, g["intv"][pos:pos + n]), f"read {i}"
-        pos += n
     pix = port_lib.orc_index_load(os.path.join(G, "tiny_rep", "ref.fa").encode())
     port_lib.orc_touches(C.c_void_p(pix), 1)
     for s in reads:
         s = np.ascontiguousarray(s)
         ob = np.zeros((256, 4), np.int64)
         port_lib.orc_collect_intv_flat(C.c_void_p(pix), len(s), _p(s, C.c_uint8), _p(ob, C.c_int64), 256)
-    assert touches == port_lib.orc_touches(C.c_void_p(pix), 1), "64-byte Occ block touches must equal the reference's"
-    # edge cases: empty read, all-N read, read shorter than a seed
+    want_touches = port_lib.orc_touches(C.c_void_p(pix), 1)
+    try:
+        for mode in (1, 3, 4):
+            emab.set_seed_mode(c, mode)
+            ivs, touches = emab.smem_batch(c, reads)
+            pos = 0
+            for i, (iv, n) in enumerate(zip(ivs, g["n_intv"])):
+                assert len(iv) == n and np.array_equal(iv, g["intv"][pos:pos + n]), f"mode {mode} read {i}"
+                pos += n
+            assert touches == want_touches, "64-byte Occ block touches must equal the reference's"
+    finally:
+        emab.set_seed_mode(c, 0)
+
+
+def test_smem_default_form_golden(emab, tiny):
+    """the default seeding form (seed_hot.cuh: one-hot Occ blocks, k-mer start table, text comparison at a unique locus):
+    the reference's intervals on the coordinates mem_chain reads (x0, x2, info), x1 = 0; then the same against the exact
+    form on mutated, N-bearing, truncated and text-end reads"""
+    ix, c = tiny
+    g = np.load(os.path.join(G, "fm_golden.npz"))
+    reads = unpack(g["reads"], g["roff"])
+    ivs, sectors = emab.smem_batch(c, reads)
+    pos = 0
+    for i, (iv, n) in enumerate(zip(ivs, g["n_intv"])):
+        assert len(iv) == n and np.array_equal(iv[:, [0, 2, 3]], g["intv"][pos:pos + n][:, [0, 2, 3]]) and not iv[:, 1].any(), f"read {i}"
+        pos += n
+    assert sectors > 0
     ivs, _ = emab.smem_batch(c, [np.zeros(0, np.uint8), np.full(50, 4, np.uint8), reads[0][:10]])
     assert [len(x) for x in ivs] == [0, 0, 0]
+    rng = np.random.default_rng(21)
+    more = []
+    for s in reads[:300]:
+        t = s.copy(); t[rng.integers(0, len(t), size=int(rng.integers(1, 6)))] = 4; more.append(t)
+        u = s.copy(); u[rng.integers(0, len(u), size=int(rng.integers(1, 4)))] ^= 1; more.append(np.minimum(u, 3).astype(np.uint8))
+        more.append(np.ascontiguousarray(s[:int(rng.integers(1, len(s)))]))
+    ref = helpers.read_fasta_nt4(os.path.join(G, "tiny_rep", "ref.fa"))
+    cat = np.concatenate(ref)
+    both = np.concatenate([cat, (3 - cat)[::-1]])
+    L = len(cat)
+    for a in (0, 1, L - 150, L - 75, L - 10, 2 * L - 151, 2 * L - 100):
+        more.append(np.ascontiguousarray(both[a:a + 151]))
+    more.append(rng.integers(0, 4, 151).astype(np.uint8))
+    got, _ = emab.smem_batch(c, more)
+    try:
+        emab.set_seed_mode(c, 3)
+        want, _ = emab.smem_batch(c, more)
+    finally:
+        emab.set_seed_mode(c, 0)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert len(a) == len(b) and np.array_equal(a[:, [0, 2, 3]], b[:, [0, 2, 3]]), f"read {i}"
 
 
 def test_bucket_parser_on_the_device(emab):

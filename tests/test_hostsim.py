@@ -90,6 +90,76 @@ def test_seeding_flat_equals_nested(hs):
         assert hs.hs_collect_intv_touches(hi, len(s), _p(s, C.c_uint8)) == tb.value
 
 
+def _seed_reads(rng, n_lines=200):
+    lines = helpers.read_bucket(os.path.join(G, "tiny_rep", "ema-bin-000.10x"))
+    reads = []
+    for f in lines[:n_lines]:
+        for s in (helpers.nt4(f[2]), helpers.nt4(f[4])):
+            reads.append(s)
+            t = s.copy()
+            t[rng.integers(0, len(t), size=int(rng.integers(1, 6)))] = 4
+            reads.append(t)
+            reads.append(np.ascontiguousarray(s[:int(rng.integers(1, len(s)))]))
+            u = s.copy()   # substitutions: several SMEMs per read, backward sweeps that die at a mismatch
+            u[rng.integers(0, len(u), size=int(rng.integers(1, 4)))] ^= 1
+            reads.append(np.minimum(u, 3).astype(np.uint8))
+    reads.append(np.full(30, 4, np.uint8))
+    reads.append(np.zeros(150, np.uint8))
+    reads.append(np.tile(np.array([0, 1], np.uint8), 75))
+    reads.append(rng.integers(0, 4, 151).astype(np.uint8))   # matches nothing for long: empty table entries
+    return [np.ascontiguousarray(r) for r in reads]
+
+
+@pytest.mark.parametrize("K", [0, 1, 2, 5, -1, 9, 12])
+def test_seeding_hot_equals_exact(hs, K):
+    """The default device form (seed_hot.cuh: one-hot Occ blocks, k-mer start table, text comparison at a unique locus)
+    against the exact restatement of mem_collect_intv: the same intervals on the coordinates mem_chain reads
+    (x0, x2, info), x1 = 0, for every table depth incl. none, the index's default (-1) and deeper than any unique
+    k-mer of this reference; reads with N, substitutions, all lengths from 1, ends of the text."""
+    hi = C.c_void_p(hs.hs_index_load(os.path.join(G, "tiny_rep", "ref.fa").encode()))
+    hs.hs_set_kmer_k(hi, K)
+    reads = _seed_reads(np.random.default_rng(12))
+    # reads cut from the very ends of the forward-reverse text and across the strand junction
+    ref = helpers.read_fasta_nt4(os.path.join(G, "tiny_rep", "ref.fa"))
+    cat = np.concatenate(ref)
+    both = np.concatenate([cat, (3 - cat)[::-1]])
+    L = len(cat)
+    for a in (0, 1, L - 150, L - 75, L - 10, 2 * L - 151, 2 * L - 100):
+        reads.append(np.ascontiguousarray(both[a:a + 151]))
+    n_sec = 0
+    for s in reads:
+        a, b = np.zeros((256, 4), np.int64), np.zeros((256, 4), np.int64)
+        sec = C.c_int64()
+        na = hs.hs_collect_intv(hi, len(s), _p(s, C.c_uint8), _p(a, C.c_int64), 256)
+        nb = hs.hs_collect_intv_hot(hi, len(s), _p(s, C.c_uint8), _p(b, C.c_int64), 256, C.byref(sec))
+        assert na == nb
+        assert np.array_equal(a[:na, [0, 2, 3]], b[:nb, [0, 2, 3]]) and not b[:nb, 1].any()
+        n_sec += sec.value
+    assert n_sec > 0
+
+
+def test_seeding_hot_equals_exact_c1_rep(hs):
+    """the same on the 5 Mbp reference with planted repeats and indel-bearing reads (BASELINE configs[0] variant), at
+    the index's own table depth: 1400 reads, and the traffic of the two forms side by side"""
+    from tools import synth
+    p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    hi = C.c_void_p(hs.hs_index_load(p["fasta"].encode()))
+    assert hs.hs_kmer_k(hi) >= 8
+    hs.hs_collect_intv_touches.restype = C.c_int64
+    sectors = touches = 0
+    for f in helpers.read_bucket(p["bucket"], 700):
+        for s in (helpers.nt4(f[2]), helpers.nt4(f[4])):
+            a, b = np.zeros((256, 4), np.int64), np.zeros((256, 4), np.int64)
+            sec = C.c_int64()
+            na = hs.hs_collect_intv(hi, len(s), _p(s, C.c_uint8), _p(a, C.c_int64), 256)
+            nb = hs.hs_collect_intv_hot(hi, len(s), _p(s, C.c_uint8), _p(b, C.c_int64), 256, C.byref(sec))
+            assert na == nb and np.array_equal(a[:na, [0, 2, 3]], b[:nb, [0, 2, 3]])
+            sectors += sec.value
+            touches += hs.hs_collect_intv_touches(hi, len(s), _p(s, C.c_uint8))
+    # bytes requested: 32-byte sectors here, 64-byte Occ blocks in the exact form
+    assert sectors * 32 < 0.6 * touches * 64, (sectors, touches)
+
+
 def test_scalar_patch_global_vs_oracle(hs, port_lib):
     """ScalarPatchDP::global (the score-only ksw_global2 the thread-per-read kernel runs inline for
     mem_patch_reg) against the oracle: same score and same visited cells, both strands, assorted bands."""
