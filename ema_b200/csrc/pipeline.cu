@@ -12,6 +12,7 @@
 //   k_finalize  warp   / pair   mem_reg2aln + append_alignments        -> candidate alignments
 #include <cmath>
 #include <cstdio>
+#include <mutex>
 #include <cstring>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -823,6 +824,25 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 		cudaEventElapsedTime(&t, c->stage_ev[6], c->stage_ev[7]); stats->ms_finalize = t;
 		stats->h2d_bytes = h2d_bytes;
 		stats->d2h_bytes = (int64_t)R * 4 + (int64_t)A * (int64_t)sizeof(emab_cand_t) + (want_cigars ? (int64_t)NC * 4 : 0) + 96;
+	}
+	if (const char *tl = getenv("EMAB_TIMELINE")) {
+		// measurement aid: where this bucket's stages lie on the device's clock next to the other buckets in flight — one
+		// line per call: ctx, then the stage events' times (ms since a process-wide base event); 0 for an unused event
+		static cudaEvent_t base = nullptr;
+		static std::mutex mu;
+		std::lock_guard<std::mutex> lk(mu);
+		if (!base) { cudaEventCreate(&base); cudaEventRecord(base, st); cudaEventSynchronize(base); }
+		else if (FILE *f = fopen(tl, "a")) {
+			fprintf(f, "%p", (void *)c);
+			const int order[12] = {0, 1, 2, 3, 8, 9, 4, 5, 6, 10, 11, 7};   // seed | chain | align1 (ext waves inside) | rescue | finalize (glob wave inside)
+			for (int k = 0; k < 12; ++k) {
+				float t = 0;
+				if (cudaEventElapsedTime(&t, base, c->stage_ev[order[k]]) != cudaSuccess) { t = 0; cudaGetLastError(); }
+				fprintf(f, " %.3f", t);
+			}
+			fprintf(f, "\n");
+			fclose(f);
+		}
 	}
 	if (h_err[0]) {
 		snprintf(emab_errbuf, sizeof emab_errbuf, "device pipeline error %d (1: backtrack scratch too small, 2: rescue window too long, 3: too many SA intervals, 4: internal DP dispatch)", h_err[0]);

@@ -166,7 +166,7 @@ typedef struct {            /* arrays are pinned host memory owned by the ctx, v
 
 typedef struct {
 	int64_t extend_cells, global_cells, local_cells;  /* DP cells visited */
-	int64_t occ_touches;                              /* 64-byte Occ block loads */
+	int64_t occ_touches;                              /* seeding form 5 (default): 32-byte sectors requested; forms 1-4: 64-byte Occ block loads as the reference issues them */
 	int64_t n_occ, n_regs;
 	double kernel_ms;                                 /* device time, first kernel to last (CUDA events on the ctx stream) */
 	double ms_seed, ms_chain, ms_align1, ms_rescue, ms_finalize; /* per-kernel device time */
