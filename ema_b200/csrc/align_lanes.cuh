@@ -14,6 +14,7 @@
 #pragma once
 #include "align.cuh"
 #include "ksw_lanes.cuh"
+#include "ksw_warp.cuh"
 
 // Thread-scalar ksw_global2 score (bwa/ksw.c:540-622 without the backtrack), used for mem_patch_reg's
 // score-only bwa_gen_cigar2 call (bwa/bwamem.c:448): rare (two colinear regions of one read), so it runs
@@ -94,6 +95,7 @@ enum { A_FETCH = 0, A_CHAIN, A_SEED, A_LEFT, A_RIGHT_BEGIN, A_RIGHT, A_IDLE };
 // What a planned extension looks like to the thread-per-read walk: answered without touching the DP (ext_wave.cuh
 // provides the implementation; a null cache answers nothing).
 struct NoExtCache {
+	static constexpr bool COOP_MISSES = false;   // every extension is for the warp to run: 32 tasks at a time, one per lane
 	__device__ __forceinline__ void set_read(int, int) {}
 	__device__ __forceinline__ bool find(const ExtTask &, ExtResult *, unsigned long long *) const { return false; }
 };
@@ -195,10 +197,36 @@ __device__ void align1_warp(const DevIndex &ix, int n_reads, const uint8_t *seq,
 				}
 			}
 		}
-		if (!__any_sync(FULL_MASK, req)) break;   // every lane idle: the bucket is done
-		QueryFetch qf{query, x.q0, x.qstep};
-		RefLaneFetch tf{&ix, x.t0, x.tstep};
-		res = extend(eh, req, x.qlen, x.tlen, x.h0, x.w, x.end_bonus, opt::zdrop, qf, tf, visited);
+		unsigned pend = __ballot_sync(FULL_MASK, req);
+		if (!pend) break;   // every lane idle: the bucket is done
+		if (Cache::COOP_MISSES) {
+			// A replay asks for an extension the waves did not compute a few times per bucket.  One lane running it alone
+			// (lanes::extend) is ~0.3 ms of a whole warp waiting; the 32 lanes running it TOGETHER (warp_extend: a row at a
+			// time) are done in a few tens of microseconds.  The warp's shared memory is free between extensions.
+			WarpDP &wsm = *reinterpret_cast<WarpDP *>(eh - (threadIdx.x & 31));
+			const int lane = threadIdx.x & 31;
+			while (pend) {
+				const int src = __ffs(pend) - 1;
+				pend &= pend - 1;
+				const unsigned long long qp = __shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)query, src);
+				const int q0 = __shfl_sync(FULL_MASK, x.q0, src), qstep = __shfl_sync(FULL_MASK, x.qstep, src), qlen = __shfl_sync(FULL_MASK, x.qlen, src);
+				const long long t0 = __shfl_sync(FULL_MASK, (long long)x.t0, src);
+				const int tstep = __shfl_sync(FULL_MASK, x.tstep, src), tlen = __shfl_sync(FULL_MASK, x.tlen, src);
+				const int h0 = __shfl_sync(FULL_MASK, x.h0, src), w = __shfl_sync(FULL_MASK, x.w, src), eb = __shfl_sync(FULL_MASK, x.end_bonus, src);
+				const uint8_t *qsrc = reinterpret_cast<const uint8_t *>((uintptr_t)qp);
+				__syncwarp();
+				for (int jq = lane; jq < qlen; jq += 32) wsm.q[jq] = qsrc[q0 + jq * qstep];
+				__syncwarp();
+				RefFetch rf{&ix, (int64_t)t0, tstep};
+				const ExtResult rr = warp_extend(wsm, qlen, rf, tlen, w, eb, opt::zdrop, h0, cells_ext);
+				if (lane == src) res = rr;
+				__syncwarp();
+			}
+		} else {
+			QueryFetch qf{query, x.q0, x.qstep};
+			RefLaneFetch tf{&ix, x.t0, x.tstep};
+			res = extend(eh, req, x.qlen, x.tlen, x.h0, x.w, x.end_bonus, opt::zdrop, qf, tf, visited);
+		}
 		if (req) { ++inline_calls; consume(res); }
 	}
 	visited += cached_cells;

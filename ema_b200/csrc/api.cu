@@ -281,6 +281,7 @@ extern "C" void emab_ctx_free(emab_ctx_t *c)
 	for (auto &b : c->h) b.release();
 	cudaFree(c->d_counters);
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->ev_wait) cudaEventDestroy(c->ev_wait);
+	if (c->stream2) { cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
 	cudaStreamDestroy(c->stream);
 	delete c;
 }

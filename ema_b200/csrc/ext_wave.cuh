@@ -146,6 +146,7 @@ __device__ __forceinline__ bool ext_plan_lookup(const ExtPlan *plans, int n_plan
 
 // the same lookup as a cache object for the thread-per-read walk (lanes::align1_warp)
 struct PlanCache {
+	static constexpr bool COOP_MISSES = true;    // misses are rare: the warp runs each one together (align_lanes.cuh)
 	const ExtPlan *plans;
 	const int32_t *chain_off;
 	const ExtPlan *mine = nullptr;

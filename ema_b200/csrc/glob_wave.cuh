@@ -30,6 +30,7 @@ struct GlobTask {
 	uint32_t pad;
 };
 #define GLOB_NEG16 (-16384)
+#define GLOB_RING_COLS 32         // bands of up to 31 columns are planned; the DP row of a lane is a ring of this many columns
 #define GLOB_MAX_DIM 1024          // rows + columns the int16 argument above covers; larger calls stay inline
 
 #ifdef __CUDACC__
@@ -100,6 +101,7 @@ __global__ void k_glob_zsize(const GlobTask *tasks, const int32_t *order, const 
 	for (int l = 0; l < 32; ++l) {
 		const int ti = wi * 32 + l;
 		if (ti >= n_tasks || keys_sorted[ti] == 0) break;   // sorted descending: nothing valid follows
+		if ((keys_sorted[ti] >> 8) >= GLOB_RING_COLS) continue;   // wide bands: k_glob_wide, with its own scratch
 		const GlobTask &t = tasks[order[ti]];
 		const int nc = t.qlen < 2 * t.w + 1 ? t.qlen : 2 * t.w + 1;
 		ncol = nc > ncol ? nc : ncol;
@@ -117,15 +119,22 @@ __global__ void k_glob_zsize(const GlobTask *tasks, const int32_t *order, const 
 //     partial-sector writes in L2 per instruction, which is what bounded the first version of this kernel.
 __global__ void __launch_bounds__(32)
 k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, const unsigned long long *zoff_warp, uint8_t *zpool,
-            uint32_t *cigars, unsigned long long *planned_cells, int qcap)
+            uint32_t *cigars, unsigned long long *planned_cells, int qcap, int ring_cols, int ncol_lo, int ncol_hi)
 {
+	// One launch serves the tasks whose band (columns per row, the high byte of the sort key) lies in (ncol_lo, ncol_hi].
+	// ring_cols != 0: the DP row is kept as a RING of that many columns (a power of two > the band): a row only ever
+	// touches columns [beg, end], at most band + 1 of them, so a narrow band — most tasks — needs 4 KB of shared memory
+	// per warp instead of 19 KB and twice as many warps fit an SM.  ring_cols == 0: one word per query column.
 	extern __shared__ uint32_t glob_smem[];
 	const int lane = threadIdx.x, ti = blockIdx.x * 32 + lane;
-	const bool valid = ti < n_tasks && keys_sorted[ti] != 0;
+	const int kcol = ti < n_tasks ? keys_sorted[ti] >> 8 : 0;
+	const bool valid = ti < n_tasks && keys_sorted[ti] != 0 && kcol > ncol_lo && kcol <= ncol_hi;
 	if (!__any_sync(FULL_MASK, valid)) return;
-	uint32_t *he = glob_smem + lane;                          // column j at he[j * 32]: {H(i-1, j-1) : lo16, E(i, j) : hi16}
-	uint32_t *qw = glob_smem + (qcap + 1) * 32 + lane;        // query bases j..j+3 in word (j >> 2)
-	uint32_t *rowbase = glob_smem + (qcap + 1) * 32 + ((qcap + 4) >> 2) * 32;   // [GLOB_MAX_DIM] warp-uniform
+	const int he_cols = ring_cols ? ring_cols : qcap + 1;
+	const unsigned rmask = ring_cols ? (unsigned)ring_cols - 1 : ~0u;
+	uint32_t *he = glob_smem + lane;                          // column j at he[(j & rmask) * 32]: {H(i-1, j-1) : lo16, E(i, j) : hi16}
+	uint32_t *qw = glob_smem + he_cols * 32 + lane;           // query bases j..j+3 in word (j >> 2)
+	uint32_t *rowbase = glob_smem + he_cols * 32 + ((qcap + 4) >> 2) * 32;   // [GLOB_MAX_DIM] warp-uniform
 	uint8_t *zw = zpool + zoff_warp[blockIdx.x] + lane;
 	unsigned long long cells = 0;
 	int slot = 0, qlen = 0, tlen = 0, w = 0, tstep = 1;
@@ -137,9 +146,11 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 		qlen = t.qlen; tlen = t.tlen; w = t.w; tstep = t.tstep; t0 = t.t0;
 		const uint8_t *query = t.query;
 		const int q0 = t.q0, qstep = t.qstep;
-		for (int j = 0; j <= qlen; ++j) {
+		// bwa/ksw.c:558-561.  Column j > w + 1 is written (end of row j - w - 1) before row j - w first reads it
+		const int jinit = qlen < w + 1 ? qlen : w + 1;
+		for (int j = 0; j <= jinit; ++j) {
 			const int h = j == 0 ? 0 : (j <= w ? -(opt::o_ins + e_ins * j) : GLOB_NEG16);
-			he[j * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h & 0xffffu);
+			he[(j & rmask) * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h & 0xffffu);
 		}
 		for (int j = 0; j < qlen; j += 4) {
 			uint32_t v = 0;
@@ -163,11 +174,11 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 		int h1 = beg == 0 ? -(opt::o_del + e_del * (i + 1)) : GLOB_NEG16, f = GLOB_NEG16;
 		cells += width;
 		uint8_t *zr = zw + (size_t)row_base * 32;
-		uint32_t *hp = he + beg * 32;
 		for (int jj = 0; jj < mw; ++jj) {
 			if (jj < width) {
 				const int j = beg + jj;
-				const uint32_t wv = hp[jj * 32];
+				uint32_t *hp = he + ((unsigned)j & rmask) * 32;
+				const uint32_t wv = *hp;
 				const int qb = (int)(qw[(j >> 2) * 32] >> ((j & 3) << 3)) & 0xff;
 				const int M = (int)(short)(wv & 0xffffu) + sc_mat(tb, qb);
 				int e = (int)wv >> 16;
@@ -179,7 +190,7 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 				e -= e_del;
 				d |= e > tt ? 1 << 2 : 0;
 				e = e > tt ? e : tt;
-				hp[jj * 32] = ((uint32_t)e << 16) | ((uint32_t)h1 & 0xffffu);
+				*hp = ((uint32_t)e << 16) | ((uint32_t)h1 & 0xffffu);
 				h1 = h;
 				tt = M - oe_ins;
 				f -= e_ins;
@@ -188,13 +199,13 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 				zr[(size_t)jj * 32] = (uint8_t)d;
 			}
 		}
-		if (act) he[end * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h1 & 0xffffu);
+		if (act) he[((unsigned)end & rmask) * 32] = ((uint32_t)(uint16_t)GLOB_NEG16 << 16) | ((uint32_t)h1 & 0xffffu);
 		row_base += (unsigned)mw;
 	}
 	__syncwarp();
 	if (valid) {
 		GlobTask &t = tasks[slot];
-		t.score = (int)(short)(he[qlen * 32] & 0xffffu);
+		t.score = (int)(short)(he[((unsigned)qlen & rmask) * 32] & 0xffffu);
 		t.cells = (uint32_t)cells;
 		// backtrack: operations are met last to first and written back to front, so the kept ones are in forward order at
 		// the end of the task's EMAB_MAX_CIGAR slots
@@ -225,8 +236,62 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 	if (lane == 0 && cells) atomicAdd(planned_cells, cells);
 }
 
+// The wide bands (GLOB_RING_COLS columns or more: a tenth of the tasks, half of the cells), ONE WARP PER TASK: a wave lasts as
+// long as its longest lane, and one lane walking a 150 x 250 matrix alone is ~1 ms — what the bucket used to wait for.
+// The 32 lanes take a row together (warp_global, ksw_warp.cuh), tens of microseconds per task; tasks are the head of the
+// sorted order and are handed out through a counter.  Runs beside k_glob_wave on the ctx's second stream.  Results in
+// the same places and format as k_glob_wave's.
+__global__ void __launch_bounds__(256)
+k_glob_wide(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, uint32_t *cigars, uint8_t *zbuf, size_t z_cap,
+            uint32_t *tmpbuf, unsigned long long *planned_cells, unsigned long long *queue)
+{
+	__shared__ WarpDP sm_all[8];
+	const int lane = threadIdx.x & 31, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+	WarpDP &sm = sm_all[threadIdx.x >> 5];
+	uint8_t *z = zbuf + (size_t)gw * z_cap;
+	uint32_t *tmp = tmpbuf + (size_t)gw * EMAB_MAX_CIGAR;
+	unsigned long long total = 0;
+	for (;;) {
+		unsigned long long pos = 0;
+		if (lane == 0) pos = atomicAdd(queue, 1ull);
+		pos = __shfl_sync(FULL_MASK, pos, 0);
+		if (pos >= (unsigned long long)n_tasks || (keys_sorted[pos] >> 8) < GLOB_RING_COLS) break;   // sorted descending
+		const int slot = order[pos];
+		GlobTask &t = tasks[slot];
+		const int qlen = t.qlen, tlen = t.tlen, w = t.w;
+		const int ncol = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+		if ((size_t)ncol * tlen > z_cap) { __syncwarp(); if (lane == 0) t.query = nullptr; continue; }   // not planned after all: k_finalize's business
+		const uint8_t *query = t.query;
+		const int q0 = t.q0, qstep = t.qstep;
+		__syncwarp();
+		for (int j = lane; j < qlen; j += 32) sm.q[j] = query[q0 + j * qstep];
+		__syncwarp();
+		RefFetch tf{&ix, t.t0, t.tstep};
+		const int score = warp_global(sm, qlen, tf, tlen, w, z, nullptr);
+		__syncwarp();
+		uint32_t fwd[EMAB_MAX_CIGAR];
+		const int n = global_backtrack(z, qlen, tlen, w, fwd, EMAB_MAX_CIGAR, tmp);
+		const int ns = n < EMAB_MAX_CIGAR ? n : EMAB_MAX_CIGAR;
+		uint32_t *cg = cigars + (size_t)slot * EMAB_MAX_CIGAR + (EMAB_MAX_CIGAR - ns);
+		for (int a = lane; a < ns; a += 32) cg[a] = fwd[a];
+		unsigned cells = 0;   // the cells ksw_global2 visits: the band of every row (bwa/ksw.c:571-573)
+		for (int i = lane; i < tlen; i += 32) {
+			const int beg = i > w ? i - w : 0, end = i + w + 1 < qlen ? i + w + 1 : qlen;
+			cells += end > beg ? (unsigned)(end - beg) : 0u;
+		}
+		cells = __reduce_add_sync(FULL_MASK, cells);
+		if (lane == 0) { t.score = score; t.n_cigar = (int16_t)(n > 32767 ? 32767 : n); t.cells = cells; }
+		total += cells;
+		__syncwarp();
+	}
+	if (lane == 0 && total) atomicAdd(planned_cells, total);
+}
+
 // shared memory of one k_glob_wave warp for queries up to qcap bases
-__host__ __device__ inline size_t glob_smem_bytes(int qcap) { return ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) >> 2) * 32 + GLOB_MAX_DIM) * 4; }
+__host__ __device__ inline size_t glob_smem_bytes(int qcap, int ring_cols = 0)
+{
+	return ((size_t)(ring_cols ? ring_cols : qcap + 1) * 32 + (size_t)((qcap + 4) >> 2) * 32 + GLOB_MAX_DIM) * 4;
+}
 
 // a ksw_global2 call of the replay against the read's tasks; on a hit copies the CIGAR (if wanted) and returns true
 __device__ __forceinline__ bool glob_plan_lookup(const GlobTask *tasks, const uint32_t *cigars, int n_tasks, const uint8_t *query, int q0, int qstep, int qlen,

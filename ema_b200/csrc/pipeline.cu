@@ -672,6 +672,8 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 				// One launch per side.  Launching per query-length class (less shared memory, more resident warps for the
 				// short extensions) was measured and dropped: a wave lasts as long as its longest task's single lane
 				// (~0.3 ms for a 130-column extension), and every extra launch adds such a floor (0.97 -> 2.15 ms).
+				// (Two length classes side by side on a second stream, the short one with a quarter of the shared memory, were
+				// measured too — 0.97 -> 1.02 ms: the waves are bound by their longest lanes, not by resident warps.)
 				const size_t smem = lanes::smem_per_warp(max_len);
 				k_ext_wave<false><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_l, lkey_s, NCH, &c->d_counters[12], 0, 255);
 				k_ext_wave<true><<<(NCH + 31) / 32, 32, smem, st>>>(ix, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), plans, order_r, rkey_s, NCH, &c->d_counters[12], 0, 255);
@@ -682,7 +684,9 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 			}
 		}
 		if (d_plans && c->replay_lanes) {
-			const size_t smem = lanes::smem_per_warp(max_len);
+			// shared memory: only the WarpDP of an unplanned extension (the planned ones are answered from the plans), so the
+			// resident warps are bounded by registers, not by 32 DP rows per warp
+			const size_t smem = (sizeof(WarpDP) + 127) & ~(size_t)127;
 			CUDA_TRY(cudaFuncSetAttribute(k_align1_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 			int per_sm = (int)((227 * 1024) / (smem + 1024));
 			per_sm = per_sm > 32 ? 32 : (per_sm < 1 ? 1 : per_sm);
@@ -732,13 +736,15 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 			TRY(c->b[36].ensure((size_t)A * sizeof(GlobTask)));
 			TRY(c->b[37].ensure((size_t)A * 2 * 2 + (size_t)A * 4 * 2 + 64));      // keys, sorted keys | iota, order
 			const int n_gwarps = (A + 31) / 32;
-			TRY(c->b[38].ensure(((size_t)n_gwarps + 1) * 8 * 2));                   // per-warp z size, z offset
+			TRY(c->b[38].ensure(((size_t)n_gwarps + 1) * 8 * 2 + 16));              // per-warp z size, z offset, k_glob_wide's task counter
 			TRY(c->b[39].ensure((size_t)A * EMAB_MAX_CIGAR * 4));
 			GlobTask *gt = c->b[36].as<GlobTask>();
 			int32_t *g_iota = c->b[37].as<int32_t>(), *g_order = g_iota + A;
 			uint16_t *g_keys = (uint16_t *)(g_order + A), *g_keys_s = g_keys + A;
 			unsigned long long *zsize = c->b[38].as<unsigned long long>(), *zoff = zsize + (n_gwarps + 1);
 			CUDA_TRY(cudaMemsetAsync(zsize + n_gwarps, 0, 8, st));
+			unsigned long long *wide_queue = zoff + (n_gwarps + 1);
+			CUDA_TRY(cudaMemsetAsync(wide_queue, 0, 8, st));
 			k_glob_plan<Pools><<<(R + 127) / 128, 128, 0, st>>>(ix, R, c->b[0].as<uint8_t>(), c->b[1].as<int64_t>(), d_occ_off, p, RESCUE_ROOM, d_aln_off, gt, g_keys);
 			k_iota1<<<(A + 255) / 256, 256, 0, st>>>(A, g_iota);
 			size_t sb = 0;
@@ -753,10 +759,17 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 			CUDA_TRY(cudaMemcpyAsync(&Z, zoff + n_gwarps, 8, cudaMemcpyDeviceToHost, st));
 			CUDA_TRY(ctx_wait(c));
 			TRY(c->b[40].ensure((size_t)Z + 64));
-			const size_t smem = glob_smem_bytes(max_len);
 			CUDA_TRY(cudaFuncSetAttribute(k_glob_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 			CUDA_TRY(cudaEventRecord(c->stage_ev[10], st));
-			k_glob_wave<<<n_gwarps, 32, smem, st>>>(ix, gt, g_order, g_keys_s, A, zoff, c->b[40].as<uint8_t>(), c->b[39].as<uint32_t>(), &c->d_counters[14], max_len);
+			// narrow bands (up to GLOB_RING_COLS - 1 columns): one THREAD per task, the DP row a 32-column ring (13 KB of shared
+			// memory per warp instead of 28); wide bands: one WARP per task, beside it on the ctx's second stream
+			TRY(ctx_fork(c));
+			k_glob_wave<<<n_gwarps, 32, glob_smem_bytes(max_len, GLOB_RING_COLS), st>>>(ix, gt, g_order, g_keys_s, A, zoff, c->b[40].as<uint8_t>(),
+			                                                          c->b[39].as<uint32_t>(), &c->d_counters[14], max_len, GLOB_RING_COLS, 0, GLOB_RING_COLS - 1);
+			k_glob_wide<<<grid, PL_WARPS * 32, 0, c->stream2>>>(ix, gt, g_order, g_keys_s, A, c->b[39].as<uint32_t>(), c->b[16].as<uint8_t>(), z_cap,
+			                                                    c->b[17].as<uint32_t>(), &c->d_counters[14], wide_queue);
+			TRY(ctx_join(c));
+			++launches;
 			CUDA_TRY(cudaEventRecord(c->stage_ev[11], st));
 			launches += 6;
 			d_gtasks = gt; d_gcigars = c->b[39].as<uint32_t>(); glob_waves_ran = true;

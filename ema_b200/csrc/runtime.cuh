@@ -69,6 +69,8 @@ struct emab_ctx {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	cudaEvent_t stage_ev[16] = {};
 	cudaEvent_t ev_wait = nullptr;   // cudaEventBlockingSync: see ctx_wait()
+	cudaStream_t stream2 = nullptr;  // a second stream for kernels that run beside each other inside one bucket (ctx_fork / ctx_join)
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	int wait_mode = 0;               // 0: poll briefly, then sleep between polls; 1: spin (cudaStreamSynchronize); 2: blocking-sync event
 	bool wait_fixed = false;         // EMAB_SYNC was given: emab_ctx_set_wait leaves the mode alone
 	int spin_us = 150;               // how long mode 0 polls before it starts sleeping (EMAB_SPIN_US)
@@ -99,6 +101,25 @@ struct emab_ctx {
 // first statement of every entry point that takes a ctx: a worker thread of the host pipeline (or any caller's
 // thread) starts on device 0, and a stream or buffer of another device is an invalid argument there
 #define CTX_ENTER(c) do { if (c) CUDA_TRY(cudaSetDevice((c)->device)); } while (0)
+
+// stream2 starts where the main stream stands (fork); the main stream continues when stream2 is done (join)
+static inline int ctx_fork(emab_ctx *c)
+{
+	if (!c->stream2) {
+		CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+	}
+	CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+	CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+	return EMAB_OK;
+}
+static inline int ctx_join(emab_ctx *c)
+{
+	CUDA_TRY(cudaEventRecord(c->ev_join, c->stream2));
+	CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+	return EMAB_OK;
+}
 
 // Wait for the ctx's stream.  cudaStreamSynchronize spins on a host core for as long as the kernels run — with several
 // buckets in flight that is several cores taken from parsing and SAM formatting (on the 16-core box a fifth of the CPU
