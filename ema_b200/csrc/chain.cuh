@@ -179,8 +179,10 @@ struct WIdxLess { EMAB_HD bool operator()(const WIdx &a, const WIdx &b) const { 
 
 // mem_chain + mem_chain_flt for one read.  Writes the surviving chains (in mem_chain_flt's output
 // order) to out_chains and their seeds, contiguous per chain, to out_seeds; returns their number.
+// sa_vals (optional): the SA values of this read's occurrences in enumeration order, gathered ahead (k_sa_gather): the
+// dependent DRAM gathers of bwt_sa then become reads of a contiguous array
 EMAB_HD int chain_read(const DevIndex &ix, int len, const Intv *intv, int n_intv, ChainWork wk, int cap,
-                       Chain *out_chains, Seed *out_seeds)
+                       Chain *out_chains, Seed *out_seeds, const int64_t *sa_vals = nullptr)
 {
 	if (len < opt::min_seed_len || n_intv == 0 || cap == 0) return 0;
 	const int64_t l_pac = ix.l_pac;
@@ -195,7 +197,7 @@ EMAB_HD int chain_read(const DevIndex &ix, int len, const Intv *intv, int n_intv
 	l_rep += e - b;
 	const float frac_rep = (float)l_rep / len;
 
-	int n_seeds = 0, n_chains = 0, n_nodes = 1, root = 0;
+	int n_seeds = 0, n_chains = 0, n_nodes = 1, root = 0, occ_idx = 0;
 	wk.nodes[0].n = 0; wk.nodes[0].is_internal = 0;
 	for (int i = 0; i < n_intv; ++i) {
 		const Intv p = intv[i];
@@ -205,7 +207,8 @@ EMAB_HD int chain_read(const DevIndex &ix, int len, const Intv *intv, int n_intv
 		for (int64_t k = 0; k < (int64_t)p.x2 && count < opt::max_occ; k += step, ++count) {
 			int si = n_seeds;  // tentative slot
 			Seed &s = wk.seeds[si];
-			s.rbeg = (int64_t)bwt_sa_dense(ix, p.x0 + (uint64_t)k);
+			s.rbeg = sa_vals ? sa_vals[occ_idx] : (int64_t)bwt_sa_dense(ix, p.x0 + (uint64_t)k);
+			++occ_idx;
 			s.qbeg = (int)(p.info >> 32);
 			s.score = s.len = slen;
 			s.next = -1;

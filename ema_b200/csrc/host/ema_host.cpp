@@ -1483,6 +1483,9 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 	// buckets inside a phase, so the host threads are split between three buckets per CPU phase while up to W
 	// buckets are in flight: bucket i's SAM text is written while i+1 runs on the GPU and i+2 is parsed.
 	int caps[PH_COUNT] = {3, 3, 3};
+	// few host threads (a rank of an 8-GPU node has 4-8): two buckets per CPU phase keep more threads on each
+	// (one B200, 20 buckets of 40 000 pairs: 8 threads 9.1 -> 8.6 ms per bucket, 4 threads 13.7 -> 12.0; profiles/r3g_*)
+	if (s->n_threads <= 8) { caps[PH_PARSE] = 2; caps[PH_POST] = 2; }
 	if (const char *e = getenv("EMAB_GATE_CAPS")) sscanf(e, "%d,%d,%d", &caps[0], &caps[1], &caps[2]);  // tuning knob
 	caps[PH_DEVICE] *= (int)s->replicas.size();   // the cap is per GPU
 	for (int k = 0; k < PH_COUNT; ++k) s->gate[k].cap = W > 1 ? std::max(1, std::min(caps[k], W)) : 1;
