@@ -228,7 +228,8 @@ PinnedBuf &PinnedBuf::operator=(PinnedBuf &&o) noexcept
 // phase; with fewer than two host threads per bucket in flight those cores are needed for parsing and cloud building.
 static void session_wait_modes(Session *s)
 {
-	const int mode = s->n_threads >= 2 * (int)std::max<size_t>(1, std::min<size_t>(s->workers.size(), 3 * s->replicas.size())) + 2 ? 1 : 0;
+	// (8 threads pinned to 8 cores, 3 buckets in the device phase: spinning 10.25 ms per bucket, sleeping 9.85; profiles/r3h_*)
+	const int mode = s->n_threads >= 2 * (int)std::max<size_t>(1, std::min<size_t>(s->workers.size(), 3 * s->replicas.size())) + 6 ? 1 : 0;
 	for (Worker &w : s->workers) emab_ctx_set_wait(w.ctx, mode);
 }
 

@@ -74,7 +74,14 @@ static __global__ void __launch_bounds__(32, MIN_BLOCKS)
 k_seed_rq(DevIndex ix, RqBatch rb)
 {
 	extern __shared__ uint4 seedq_smem[];
-	seed_rq_warp(ix, rb, (uint32_t *)seedq_smem);
+	seed_rq_warp<false>(ix, rb, (uint32_t *)seedq_smem);
+}
+// measurement build: EMAB_SEED_PROF=1 runs it instead and prints the per-state iteration counts of the launch to stderr
+static __global__ void __launch_bounds__(32, 24)
+k_seed_rq_prof(DevIndex ix, RqBatch rb)
+{
+	extern __shared__ uint4 seedq_smem[];
+	seed_rq_warp<true>(ix, rb, (uint32_t *)seedq_smem);
 }
 
 static __global__ void __launch_bounds__(128)
@@ -161,7 +168,23 @@ static int launch_seed(emab_ctx *c, int R, int max_len, const uint8_t *d_seq, co
 		RqBatch rb{b, c->b[41].as<uint32_t>()};
 		k_pack_reads<<<(R * 24 + 255) / 256, 256, 0, st>>>(d_seq, d_off, R, c->b[41].as<uint32_t>());
 		++*launches;
-		if (seed_blocks_per_sm() >= 7) k_seed_rq<28><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
+		static const bool prof = getenv("EMAB_SEED_PROF") && atoi(getenv("EMAB_SEED_PROF")) != 0;
+		if (prof) {   // counts land behind the sector counter: a scratch array of its own
+			if (int rc = c->b[43].ensure(32 * 8)) return rc;
+			unsigned long long *cnt = c->b[43].as<unsigned long long>();
+			CUDA_TRY(cudaMemsetAsync(cnt, 0, 32 * 8, st));
+			rb.b.touches = cnt;
+			k_seed_rq_prof<<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
+			unsigned long long h[32];
+			CUDA_TRY(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
+			static const char *names[] = {"FWD", "P3_FWD", "BWD", "READ", "TAB", "P3_TAB", "SA", "P3_SA", "TEXT", "P3_TEXT"};
+			fprintf(stderr, "[emab seed profile] %d reads; quad-iterations per read:", R);
+			unsigned long long tot = 0;
+			for (int k = 0; k < 10; ++k) { fprintf(stderr, " %s %.1f", names[k], (double)h[1 + k] / R); tot += h[1 + k]; }
+			fprintf(stderr, " | total %.1f, sectors %.1f\n", (double)tot / R, (double)h[0] / R);
+			CUDA_TRY(cudaMemcpyAsync(d_touches, cnt, 8, cudaMemcpyDeviceToDevice, st));
+		} else if (seed_blocks_per_sm() >= 7) k_seed_rq<28><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
 		else if (seed_blocks_per_sm() >= 6) k_seed_rq<24><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
 		else if (seed_blocks_per_sm() >= 5) k_seed_rq<20><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);
 		else k_seed_rq<16><<<grid, 32, RQ_SMEM_BYTES(8), st>>>(c->ix->d, rb);

@@ -213,6 +213,8 @@ static __device__ __noinline__ uint64_t text_word32_slow(const DevIndex &ix, int
 	return r;
 }
 
+// PROF: per-state iteration counts (quads x iterations) into rb.b.touches[1 + state] — a measurement build of the same loop
+template <bool PROF>
 __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &rb, uint32_t *smem)
 {
 	const int lane = threadIdx.x & 31;
@@ -300,13 +302,12 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 				else s.st = s.f_x2 == 1 && s.min_intv <= 1 ? RqQuad::SA : RqQuad::FWD;
 				break;
 			case RqQuad::CLOSE:   // end of the forward sweep: the last interval is recorded (bwa/bwt.c:316-321)
-				if (qi == 0) s.lst_put(s.cur, s.n_curr, s.f_x0, s.f_x2, s.i);
+				s.lst_put(s.cur, s.n_curr, s.f_x0, s.f_x2, s.i);   // all four lanes, the same value
 				++s.n_curr;
 				s.ret = s.i;
 				s.st = RqQuad::START_BWD;
 				break;
-			case RqQuad::START_BWD:
-				__syncwarp(s.qmask);   // list entries were stored by their owner lanes
+			case RqQuad::START_BWD:   // (the list's entries were stored by all four lanes, or before the loop's last __syncwarp)
 				s.cur ^= 1;
 				s.n_prev = s.n_curr; s.n_curr = 0;
 				s.i = s.sx - 1; s.rev = 1;
@@ -340,6 +341,7 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 		// ------------------------------------------------------------------ the request of this iteration
 		const bool req = s.st != RqQuad::DRAINED;
 		const bool is_occ = s.st <= RqQuad::BWD;
+		if (PROF && req && qi == 0) atomicAdd(rb.b.touches + 1 + s.st, 1ull);
 		const uint4 *a0 = nullptr, *a1 = nullptr, *a2 = nullptr, *a3 = nullptr;
 		bool p0 = false, p1 = false, p2 = false, p3 = false, uni = false;   // uni: the quad's lanes ask for the same bytes
 		OccReq oq; oq._k = oq._l = 0; oq.kv = oq.lv = oq.other = false;
@@ -394,20 +396,37 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 			}
 		}
 		if (!__any_sync(0xffffffffu, req)) break;
+		__syncwarp();   // list entries and read words stored in the last iteration are visible to the quad's other lanes from here on
 		// ------------------------------------------------------------------ issue: the one place where DRAM is read
 		uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
 		ldg128_if(p0, a0, r0); ldg128_if(p1, a1, r1); ldg128_if(p2, a2, r2); ldg128_if(p3, a3, r3);
 		if (!uni || qi == 0) s.sectors += (unsigned)p0 + (unsigned)p1 + (unsigned)p2 + (unsigned)p3;
-		if (!req) continue;
 		// ------------------------------------------------------------------ consume
+		// The Occ states' cross-lane traffic, for ALL 32 lanes at this convergent point and with the full mask: a shuffle or
+		// vote over a quad's own mask inside per-state code costs a MATCH/WARPSYNC sequence each (a tenth of the kernel's
+		// instructions and 15 % of its stall samples before this).  Lanes in other states take part with values nobody reads.
+		uint64_t tk, ns;
+		occ_count(oq, r0, r1, tk, ns);
+		const bool bwd = is_occ && s.st == RqQuad::BWD;
+		const bool alive = bwd && s.e_valid && !(ns < s.min_intv);
+		const unsigned aliveb = (__ballot_sync(0xffffffffu, alive) >> s.qshift) & 0xfu;
+		uint64_t prev_x2 = __shfl_up_sync(0xffffffffu, ns, 1, 4);
+		bool prev_alive = qi ? (aliveb >> (qi - 1)) & 1 : s.n_curr > 0;
+		if (qi == 0) prev_x2 = s.last_size;
+		// survivors of a backward round: recorded when the first of the round or different in size from the survivor before
+		// (sizes never decrease along the list: every entry's string is a prefix of the one before it)
+		const bool push = alive && (!prev_alive || ns != prev_x2);
+		const unsigned pushb = (__ballot_sync(0xffffffffu, push) >> s.qshift) & 0xfu;
+		const uint64_t last_x2 = __shfl_sync(0xffffffffu, ns, (int)s.qshift + 3);
+		const int cq = (int)s.qshift + (s.c & 3);
+		const uint64_t tk_c = __shfl_sync(0xffffffffu, tk, cq), ns_c = __shfl_sync(0xffffffffu, ns, cq);
+		uint64_t above = qi > s.c ? ns : 0;
+		above += __shfl_xor_sync(0xffffffffu, above, 1);
+		above += __shfl_xor_sync(0xffffffffu, above, 2);
+		if (!req) continue;
 		if (is_occ) {
-			uint64_t tk, ns;
-			occ_count(oq, r0, r1, tk, ns);
-			if (s.st == RqQuad::BWD) {   // bwa/bwt.c:328-345 for four entries of the round, in list order
+			if (bwd) {   // bwa/bwt.c:328-345 for four entries of the round, in list order
 				const uint64_t ok_x0 = ix.L2[s.c] + 1 + tk, ok_x2 = ns;
-				const bool dead = ok_x2 < s.min_intv;
-				const bool alive = s.e_valid && !dead;
-				const unsigned aliveb = s.qballot(alive);
 				if (s.j == 0 && !(aliveb & 1)) {
 					// the round's first entry did not survive; only it can be emitted: a later one finds either a survivor
 					// before it or last_start already set (bwa/bwt.c:331-338)
@@ -418,34 +437,25 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 						s.last_start = s.i + 1;
 					}
 				}
-				// survivors: recorded when the first of the round or different in size from the survivor before (sizes never
-				// decrease along the list: every entry's string is a prefix of the one before it)
-				uint64_t prev_x2 = __shfl_up_sync(s.qmask, ok_x2, 1, 4);
-				bool prev_alive = qi ? (aliveb >> (qi - 1)) & 1 : false;
-				if (qi == 0) { prev_x2 = s.last_size; prev_alive = s.n_curr > 0; }
-				const bool push = alive && (!prev_alive || ok_x2 != prev_x2);
-				const unsigned pushb = s.qballot(push);
 				if (push) s.lst_put(s.cur, s.n_curr + __popc(pushb & ((1u << qi) - 1)), ok_x0, ok_x2, s.e_end);
 				s.n_curr += __popc(pushb);
 				s.j += 4;
 				if (s.j >= s.n_prev) {   // end of the round (bwa/bwt.c:346-348)
 					if (s.n_curr == 0) { if (!s.in_p2) s.x = s.ret; s.st = RqQuad::NEXT; }
 					else {
-						__syncwarp(s.qmask);
 						s.cur ^= 1;
 						s.n_prev = s.n_curr; s.n_curr = 0;
 						--s.i; s.rev = 0;
 						s.st = RqQuad::ROUND;
 					}
-				} else s.last_size = s.qbcast(ok_x2, 3);
+				} else s.last_size = last_x2;
 			} else {   // bwt_extend forward (bwa/bwt.c:262-275), lane q counted base q
-				const uint64_t tk_c = s.qbcast(tk, s.c), ns_c = s.qbcast(ns, s.c), above = s.qsum(qi > s.c ? ns : 0);
 				const uint64_t ok_x1 = ix.L2[s.c] + 1 + tk_c, ok_x2 = ns_c;
 				const uint64_t ok_x0 = s.f_x0 + (s.f_x1 <= ix.primary && s.f_x1 + s.f_x2 - 1 >= ix.primary) + above;
 				if (s.st == RqQuad::FWD) {   // bwa/bwt.c:307-315
 					bool stop = false;
 					if (ok_x2 != s.f_x2) {
-						if (qi == 0) s.lst_put(s.cur, s.n_curr, s.f_x0, s.f_x2, s.i);
+						s.lst_put(s.cur, s.n_curr, s.f_x0, s.f_x2, s.i);   // all four lanes, the same value: each reads back at least its own
 						++s.n_curr; s.ret = s.i;
 						stop = ok_x2 < s.min_intv;
 					}
@@ -466,8 +476,7 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 			if (qi == 0) { s.rw[16] = 0; s.rw[17] = 0; }
 			if (qi < 2) { uint32_t *nm = s.rw + RQ_READ_WORDS + 4 * qi; nm[0] = r1.x; nm[1] = r1.y; nm[2] = r1.z; nm[3] = r1.w; }
 			s.has_n = s.qballot(qi < 2 && (r1.x | r1.y | r1.z | r1.w)) != 0;
-			__syncwarp(s.qmask);
-			s.st = RqQuad::NEXT;
+			s.st = RqQuad::NEXT;   // the words are read from the next iteration on
 			break;
 		}
 		case RqQuad::TAB: {
