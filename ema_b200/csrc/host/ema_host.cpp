@@ -363,6 +363,7 @@ struct Rec {  // SAMRecord (include/samrecord.h:22-58), fields on the path only
 	int mapq, score_mapq, clip, clip_edit_dist;
 	uint8_t mate, rev, duplicate, unique, active, visited;
 	int pair;                 // index of the pair inside its barcode
+	int name_id;              // equal read names of one barcode share an id: the SAMDict key (name, mate) as two integers
 	const emab_cand_t *aln;
 	int cand;                 // aln's index among the batch's candidates (what the device formatter is told)
 	double gamma;
@@ -454,37 +455,19 @@ struct Barcode {
 	std::vector<Rec> recs;                 // after sort: (chrom&0xff, pos, ident) order
 	std::vector<Cloud> clouds;
 	std::vector<Entry> entries;            // insertion order; the reference walks them newest first
-	std::vector<int32_t> slots;            // SAMDict: open-addressing table of entry indices keyed by (ident, mate)
-	uint32_t slot_mask = 0;
+	std::vector<int32_t> slots;            // SAMDict: entry index of (name id, mate), -1 = none
+	int n_names = 0;                       // distinct read names in this barcode
 	std::vector<int> final_;               // records_final
 	std::vector<std::vector<int>> opt_jobs; // -d: name-sorted records of each bad cloud, in cloud order (see process_pairs)
 	int n_out = 0;                         // pairs this barcode prints (two SAM records each)
 	std::string bc_str;                    // decode_bc(bc), printed in every BX tag of this barcode
 
-	void dict_init(size_t n_keys)
-	{
-		size_t c = 16;
-		while (c < 4 * n_keys) c <<= 1;
-		slots.assign(c, -1);
-		slot_mask = (uint32_t)(c - 1);
-	}
-	static uint32_t key_hash(std::string_view ident, int mate) { return (uint32_t)(std::hash<std::string_view>()(ident) * 2 + (size_t)mate); }
-	int find_key(std::string_view ident, int mate) const
-	{
-		for (uint32_t i = key_hash(ident, mate) & slot_mask;; i = (i + 1) & slot_mask) {
-			const int e = slots[i];
-			if (e < 0) return -1;
-			const Rec &k = recs[entries[e].key];
-			if ((int)k.mate == mate && k.ident == ident) return e;
-		}
-	}
-	void dict_insert(std::string_view ident, int mate, int ei)
-	{
-		uint32_t i = key_hash(ident, mate) & slot_mask;
-		while (slots[i] >= 0) i = (i + 1) & slot_mask;
-		slots[i] = ei;
-	}
-	int find(const Rec &k) const { return find_key(k.ident, (int)k.mate); }
+	// SAMDict (src/samdict.c:40-58,76-147) is keyed by (read name, mate).  Names are turned into small integers once per
+	// pair (name_ids below), so the dictionary is a direct table — no string hashing or comparing per candidate record.
+	void dict_init(size_t n_names) { slots.assign(2 * n_names, -1); }
+	int find_key(int name_id, int mate) const { return slots[2 * (size_t)name_id + mate]; }
+	void dict_insert(int name_id, int mate, int ei) { slots[2 * (size_t)name_id + mate] = ei; }
+	int find(const Rec &k) const { return find_key(k.name_id, (int)k.mate); }
 	int dict_add(int ri, int cloud, bool force, bool many_clouds);
 	void dict_del(int ri) { int e = find(recs[ri]); if (e >= 0) { entries[e].cand_rec.pop_back(); entries[e].cand_cloud.pop_back(); } }
 	void build_clouds(const Session *s, const std::vector<Pair> &pairs);
@@ -523,10 +506,10 @@ int Barcode::dict_add(int ri, int v, bool force, bool many_clouds)
 	e.cand_rec.push_back(ri);
 	e.cand_cloud.push_back(v);
 	ei = (int)entries.size();
-	const int me = find_key(k.ident, 1 - (int)k.mate);  // find_mate_for_key
+	const int me = find_key(k.name_id, 1 - (int)k.mate);  // find_mate_for_key
 	if (me >= 0) { e.mate = me; entries[me].mate = ei; }
 	entries.push_back(std::move(e));
-	dict_insert(recs[ri].ident, (int)recs[ri].mate, ei);
+	dict_insert(recs[ri].name_id, (int)recs[ri].mate, ei);
 	return 0;
 }
 
@@ -551,15 +534,23 @@ void Barcode::build_clouds(const Session *s, const std::vector<Pair> &pairs)
 {
 	(void)pairs;
 	// qsort(records, record_cmp): (bc, chrom & 0xff, pos, ident); glibc's merge sort is stable
-	std::stable_sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) {
-		const uint8_t ca = (uint8_t)a.chrom, cb = (uint8_t)b.chrom;
-		if (ca != cb) return ca < cb;
-		if (a.pos != b.pos) return a.pos < b.pos;
-		return a.ident.compare(b.ident) < 0;
-	});
+	// The order is decided on 12-byte keys (chrom & 0xff, pos | index) and the 88-byte records are moved once: sorting
+	// the records themselves moved each of them ~9 times (cloud building was the largest host stage, profiles/r3h_*).
+	{
+		struct Key { uint64_t k; uint32_t i; };
+		std::vector<Key> keys(recs.size());
+		for (size_t i = 0; i < recs.size(); ++i) keys[i] = Key{(uint64_t)(uint8_t)recs[i].chrom << 32 | recs[i].pos, (uint32_t)i};
+		std::stable_sort(keys.begin(), keys.end(), [&](const Key &a, const Key &b) {
+			if (a.k != b.k) return a.k < b.k;
+			return recs[a.i].ident.compare(recs[b.i].ident) < 0;
+		});
+		std::vector<Rec> sorted(recs.size());
+		for (size_t i = 0; i < recs.size(); ++i) sorted[i] = recs[keys[i].i];
+		recs.swap(sorted);
+	}
 	const bool many = s->tech->many_clouds != 0;
 	const size_t n = recs.size();
-	dict_init(2 * (size_t)n_pairs + 8);
+	dict_init((size_t)n_names);
 	entries.reserve(2 * (size_t)n_pairs);
 	size_t i = 0;
 	while (i < n) {
@@ -637,22 +628,26 @@ void Barcode::choose(const Session *s)
 		if (e.mate >= 0) { entries[e.mate].visited = true; entries[e.mate].mate = -1; }
 	}
 	if (!s->tech->many_clouds) {  // duplicates: dup_cmp (src/align.c:85-123), glibc qsort is stable
-		auto key = [&](int r, uint32_t k[6]) {
-			const Rec &x = recs[r];
-			k[0] = x.mate; k[1] = x.rev; k[2] = x.chrom; k[3] = x.pos;
-			k[4] = x.selected_mate >= 0 ? recs[x.selected_mate].chrom : 0xffffffffu;
-			k[5] = x.selected_mate >= 0 ? recs[x.selected_mate].pos : 0xffffffffu;
-		};
-		auto cmp = [&](int a, int b) {
-			uint32_t ka[6], kb[6];
-			key(a, ka); key(b, kb);
-			for (int i = 0; i < 6; ++i) if (ka[i] != kb[i]) return ka[i] < kb[i] ? -1 : 1;
-			return 0;
-		};
-		std::stable_sort(final_.begin(), final_.end(), [&](int a, int b) { return cmp(a, b) < 0; });
-		for (size_t i = 0; i < final_.size();) {
+		// the six fields of dup_cmp as three words per record, built once (the comparator used to rebuild them, through two
+		// levels of indirection, at every comparison)
+		struct DupKey { uint64_t a, b, c; int r; };
+		std::vector<DupKey> dk(final_.size());
+		for (size_t i = 0; i < final_.size(); ++i) {
+			const Rec &x = recs[final_[i]];
+			const uint32_t mc = x.selected_mate >= 0 ? recs[x.selected_mate].chrom : 0xffffffffu;
+			const uint32_t mp = x.selected_mate >= 0 ? recs[x.selected_mate].pos : 0xffffffffu;
+			dk[i] = DupKey{(uint64_t)x.mate << 33 | (uint64_t)x.rev << 32 | x.chrom, (uint64_t)x.pos << 32 | mc, mp, final_[i]};
+		}
+		auto same = [](const DupKey &p, const DupKey &q) { return p.a == q.a && p.b == q.b && p.c == q.c; };
+		std::stable_sort(dk.begin(), dk.end(), [](const DupKey &p, const DupKey &q) {
+			if (p.a != q.a) return p.a < q.a;
+			if (p.b != q.b) return p.b < q.b;
+			return p.c < q.c;
+		});
+		for (size_t i = 0; i < dk.size(); ++i) final_[i] = dk[i].r;
+		for (size_t i = 0; i < dk.size();) {
 			size_t j = i + 1;
-			while (j < final_.size() && cmp(final_[i], final_[j]) == 0) { recs[final_[j]].duplicate = 1; ++j; }
+			while (j < dk.size() && same(dk[i], dk[j])) { recs[dk[j].r].duplicate = 1; ++j; }
 			i = j;
 		}
 	}
@@ -963,8 +958,23 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 	for (int b = 0; b < nb; ++b) {
 		HostProf hp(HP_RECS);
 		Barcode &B = bcs[b];
+		// read names -> ids (equal names, equal ids): a small open-addressing table over this barcode's names
+		size_t tcap = 16;
+		while (tcap < 4 * (size_t)B.n_pairs) tcap <<= 1;
+		std::vector<int32_t> ntab(tcap, -1);
+		std::vector<std::string_view> names;
+		names.reserve(2 * (size_t)B.n_pairs);
+		auto name_id = [&](std::string_view nm) {
+			for (size_t i = std::hash<std::string_view>()(nm) & (tcap - 1);; i = (i + 1) & (tcap - 1)) {
+				if (ntab[i] < 0) { ntab[i] = (int32_t)names.size(); names.push_back(nm); return ntab[i]; }
+				if (names[(size_t)ntab[i]] == nm) return ntab[i];
+			}
+		};
+		B.recs.reserve((size_t)(aoff[2 * ((size_t)B.first_pair + B.n_pairs)] - aoff[2 * (size_t)B.first_pair]));
 		for (int pi = 0; pi < B.n_pairs; ++pi) {  // append_alignments' bookkeeping (src/align.c:1010-1060)
 			const size_t gp = (size_t)B.first_pair + pi;
+			const int nid1 = name_id(pairs[gp].id1);
+			const int nid[2] = {nid1, pairs[gp].id2.data() == pairs[gp].id1.data() && pairs[gp].id2.size() == pairs[gp].id1.size() ? nid1 : name_id(pairs[gp].id2)};
 			for (int m = 0; m < 2; ++m) {
 				int added = 0;
 				for (int64_t k = aoff[2 * gp + m]; k < aoff[2 * gp + m + 1]; ++k) {
@@ -973,6 +983,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 					Rec r;
 					r.chrom = (uint32_t)s->rid2chrom[a.rid]; r.pos = (uint32_t)(a.pos + 1);
 					r.ident = m == 0 ? pairs[gp].id1 : pairs[gp].id2;
+					r.name_id = nid[m];
 					r.score = a.em_score; r.mapq = a.mapq; r.score_mapq = a.score_mapq; r.clip = a.clip; r.clip_edit_dist = a.clip_edit_dist;
 					r.mate = (uint8_t)m; r.rev = (uint8_t)a.is_rev; r.duplicate = 0; r.unique = 0; r.active = 1; r.visited = 0;
 					r.pair = pi; r.aln = &a; r.cand = (int)k; r.gamma = 0; r.cloud = -1; r.selected_mate = -1; r.alt = -1;
@@ -982,6 +993,7 @@ static int process_pairs(Session *s, Worker &wk, GatePass &gp, const std::vector
 				if (added == 1) B.recs.back().unique = 1;
 			}
 		}
+		B.n_names = (int)names.size();
 		hp.next(HP_CLOUDS);
 		B.build_clouds(s, pairs);
 	}
