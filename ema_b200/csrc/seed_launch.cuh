@@ -130,7 +130,7 @@ static inline int seed_blocks_per_sm()
 	static int v = 0;
 	if (!v) { const char *e = getenv("EMAB_SEED_BPS"); v = e ? atoi(e) : -1; if (v < 1 || v > 16) v = -1; }
 	if (v > 0) return v;
-	return seed_mode() == 4 ? 8 : (seed_mode() == 3 ? 5 : 6);
+	return seed_mode() == 4 ? 8 : (seed_mode() == 3 || seed_mode() == 5 ? 5 : 6);   // form 5: 20 warps per SM at 95 registers = 24 at 80 with spills
 }
 
 // Device buffers: d_intv [R][max_intv], d_n_intv [R], d_occ_cnt [R] or null, *d_err int, *d_touches u64 (zeroed by the caller).

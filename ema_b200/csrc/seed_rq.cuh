@@ -76,7 +76,7 @@ struct RqQuad {   // everything one lane keeps about its quad's read; fields are
 	unsigned qmask, qshift;
 	unsigned sectors;
 	// job
-	int st, rid, len, has_n, n12, n3, ovf, cap12;
+	int st, rid, job_p3, len, has_n, n12, n3, ovf, cap12;
 	Intv *out12, *out3;
 	// passes
 	int pass, x, old_n, k2;
@@ -224,7 +224,7 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 	uint32_t *qs = smem + quad * RQ_QUAD_U32;
 	RqQuad s{ix, rb, (uint4 *)qs, qs + 2 * RQ_CAP * 4, (uint4 *)(b.scratch + gquad * 2 * b.scratch_len), 2 * b.scratch_len, qi,
 	         0xfu << (lane & ~3), (unsigned)(lane & ~3), 0};
-	s.st = RqQuad::JOB; s.rid = -1; s.len = 0; s.has_n = 0; s.n12 = s.n3 = s.ovf = 0; s.cap12 = 0; s.out12 = s.out3 = nullptr;
+	s.st = RqQuad::JOB; s.rid = -1; s.job_p3 = 0; s.len = 0; s.has_n = 0; s.n12 = s.n3 = s.ovf = 0; s.cap12 = 0; s.out12 = s.out3 = nullptr;
 	s.pass = 1; s.x = 0; s.old_n = 0; s.k2 = 0; s.q2.clear();
 	s.sx = s.i = s.ret = 0; s.last_start = 0x7fffffff; s.n_prev = s.n_curr = s.j = 0; s.cur = 1; s.rev = 0; s.c = 0; s.in_p2 = 0; s.m = 0;
 	s.min_intv = 1; s.last_size = 0; s.f_x0 = s.f_x1 = s.f_x2 = 0; s.text_p = 0; s.e_x0 = s.e_x2 = 0; s.e_end = 0; s.e_valid = 0;
@@ -234,11 +234,16 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 		while (s.st >= RqQuad::JOB && s.st != RqQuad::DRAINED) {
 			switch (s.st) {
 			case RqQuad::JOB: {
-				if (s.rid >= 0 && qi == 0) { b.n12[s.rid] = s.n12; b.n3[s.rid] = s.n3; if (s.ovf) *b.err = 3; }
+				// A read is TWO jobs: passes 1+2 (~165 iterations) and pass 3 (~40).  The queue hands out all the long jobs
+				// first, then the short ones: the kernel's tail — quads running their last job while the others are dry —
+				// is as long as a short job instead of a whole read (~0.9 ms).
+				if (s.rid >= 0 && qi == 0) { if (s.job_p3) b.n3[s.rid] = s.n3; else b.n12[s.rid] = s.n12; if (s.ovf) *b.err = 3; }
 				unsigned long long r = 0;
 				if (qi == 0) r = atomicAdd(&b.queue[0], 1ull);
 				r = __shfl_sync(s.qmask, r, (int)s.qshift);
-				if (r >= (unsigned long long)b.n_reads) { s.rid = -1; s.st = RqQuad::DRAINED; break; }
+				if (r >= 2ull * (unsigned long long)b.n_reads) { s.rid = -1; s.st = RqQuad::DRAINED; break; }
+				s.job_p3 = r >= (unsigned long long)b.n_reads;
+				if (s.job_p3) r -= (unsigned long long)b.n_reads;
 				s.rid = (int)r;
 				s.len = (int)(b.off[r + 1] - b.off[r]);
 				s.out12 = b.intv + (size_t)r * b.max_intv; s.cap12 = b.max_intv;
@@ -264,13 +269,13 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 							if (end - start >= opt::split_len && p.x2 <= (uint64_t)opt::split_width) break;
 							++s.k2;
 						}
-						if (s.k2 >= s.old_n) { s.pass = 3; s.x = 0; s.st = RqQuad::P3_NEXT; }
+						if (s.k2 >= s.old_n) s.st = RqQuad::JOB;
 						else {
 							const Intv p = s.out12[s.k2++];
 							s.sx = ((int)(p.info >> 32) + (int)(uint32_t)p.info) >> 1;
 							s.min_intv = p.x2 + 1; s.in_p2 = 1; start_call = true;
 						}
-					} else { s.pass = 3; s.x = 0; s.st = RqQuad::P3_NEXT; }
+					} else s.st = RqQuad::JOB;
 				}
 				if (start_call) {   // bwt_smem1a(sx, min_intv): bwa/bwt.c:289-302
 					s.n_curr = 0; s.last_start = 0x7fffffff;
@@ -476,7 +481,7 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 			if (qi == 0) { s.rw[16] = 0; s.rw[17] = 0; }
 			if (qi < 2) { uint32_t *nm = s.rw + RQ_READ_WORDS + 4 * qi; nm[0] = r1.x; nm[1] = r1.y; nm[2] = r1.z; nm[3] = r1.w; }
 			s.has_n = s.qballot(qi < 2 && (r1.x | r1.y | r1.z | r1.w)) != 0;
-			s.st = RqQuad::NEXT;   // the words are read from the next iteration on
+			s.st = s.job_p3 ? RqQuad::P3_NEXT : RqQuad::NEXT;   // the words are read from the next iteration on
 			break;
 		}
 		case RqQuad::TAB: {
