@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <mutex>
 #include <cstring>
+#include <vector>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include "../../include/ema_b200.h"
@@ -698,6 +699,16 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 				cub::DeviceRadixSort::SortPairsDescending(c->b[6].p, sb, rkey, rkey_s, iota_r, order_r, NCH, 0, 8, st);
 				CUDA_TRY(cudaFuncSetAttribute(k_ext_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 				CUDA_TRY(cudaFuncSetAttribute(k_ext_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+				if (getenv("EMAB_EXT_HIST")) {   // measurement aid: how long the planned extensions are (query bases), both sides
+					std::vector<uint8_t> hk(2 * (size_t)NCH);
+					CUDA_TRY(cudaMemcpyAsync(hk.data(), lkey, 2 * (size_t)NCH, cudaMemcpyDeviceToHost, st));
+					CUDA_TRY(cudaStreamSynchronize(st));
+					long long h[2][9] = {};
+					for (int sd = 0; sd < 2; ++sd) for (int k = 0; k < NCH; ++k) { const int v = hk[(size_t)sd * NCH + k]; ++h[sd][v == 0 ? 0 : 1 + (v - 1) / 20 > 8 ? 8 : 1 + (v - 1) / 20]; }
+					fprintf(stderr, "[emab ext hist] %d chains; query length 0 | 1-20 | 21-40 | ... | 141+ :", NCH);
+					for (int sd = 0; sd < 2; ++sd) { fprintf(stderr, sd ? "  right" : "  left"); for (int k = 0; k < 9; ++k) fprintf(stderr, " %lld", h[sd][k]); }
+					fprintf(stderr, "\n");
+				}
 				CUDA_TRY(cudaEventRecord(c->stage_ev[8], st));
 				// One launch per side.  Launching per query-length class (less shared memory, more resident warps for the
 				// short extensions) was measured and dropped: a wave lasts as long as its longest task's single lane
