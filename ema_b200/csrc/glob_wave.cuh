@@ -31,6 +31,7 @@ struct GlobTask {
 };
 #define GLOB_NEG16 (-16384)
 #define GLOB_RING_COLS 32         // bands of up to 31 columns are planned; the DP row of a lane is a ring of this many columns
+#define GLOB_WIDE_COLS 28         // bands of this many columns or more: one warp per task (k_glob_wide)
 #define GLOB_MAX_DIM 1024          // rows + columns the int16 argument above covers; larger calls stay inline
 
 #ifdef __CUDACC__
@@ -93,7 +94,7 @@ k_glob_plan(DevIndex ix, int n_reads, const uint8_t *seq, const int64_t *off, co
 
 // Upper bound of a warp's backtrack matrix: its 32 tasks (in sorted order) advance row by row together and a row is
 // as wide as its widest lane, so 32 * max(ncol) * max(tlen) bytes always suffice.
-__global__ void k_glob_zsize(const GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, unsigned long long *zsize_warp, int n_warps)
+__global__ void k_glob_zsize(const GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, unsigned long long *zsize_warp, int n_warps, int wide_cols)
 {
 	const int wi = blockIdx.x * blockDim.x + threadIdx.x;
 	if (wi >= n_warps) return;
@@ -101,7 +102,7 @@ __global__ void k_glob_zsize(const GlobTask *tasks, const int32_t *order, const 
 	for (int l = 0; l < 32; ++l) {
 		const int ti = wi * 32 + l;
 		if (ti >= n_tasks || keys_sorted[ti] == 0) break;   // sorted descending: nothing valid follows
-		if ((keys_sorted[ti] >> 8) >= GLOB_RING_COLS) continue;   // wide bands: k_glob_wide, with its own scratch
+		if ((keys_sorted[ti] >> 8) >= wide_cols) continue;   // wide bands: k_glob_wide, with its own scratch
 		const GlobTask &t = tasks[order[ti]];
 		const int nc = t.qlen < 2 * t.w + 1 ? t.qlen : 2 * t.w + 1;
 		ncol = nc > ncol ? nc : ncol;
@@ -243,7 +244,7 @@ k_glob_wave(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 // the same places and format as k_glob_wave's.
 __global__ void __launch_bounds__(256)
 k_glob_wide(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *keys_sorted, int n_tasks, uint32_t *cigars, uint8_t *zbuf, size_t z_cap,
-            uint32_t *tmpbuf, unsigned long long *planned_cells, unsigned long long *queue)
+            uint32_t *tmpbuf, unsigned long long *planned_cells, unsigned long long *queue, int wide_cols)
 {
 	__shared__ WarpDP sm_all[8];
 	const int lane = threadIdx.x & 31, gw = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -255,7 +256,7 @@ k_glob_wide(DevIndex ix, GlobTask *tasks, const int32_t *order, const uint16_t *
 		unsigned long long pos = 0;
 		if (lane == 0) pos = atomicAdd(queue, 1ull);
 		pos = __shfl_sync(FULL_MASK, pos, 0);
-		if (pos >= (unsigned long long)n_tasks || (keys_sorted[pos] >> 8) < GLOB_RING_COLS) break;   // sorted descending
+		if (pos >= (unsigned long long)n_tasks || (keys_sorted[pos] >> 8) < wide_cols) break;   // sorted descending
 		const int slot = order[pos];
 		GlobTask &t = tasks[slot];
 		const int qlen = t.qlen, tlen = t.tlen, w = t.w;

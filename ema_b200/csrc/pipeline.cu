@@ -792,7 +792,9 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 			cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, g_keys, g_keys_s, g_iota, g_order, A, 0, 16, st);
 			TRY(c->b[6].ensure(sb + 16));
 			cub::DeviceRadixSort::SortPairsDescending(c->b[6].p, sb, g_keys, g_keys_s, g_iota, g_order, A, 0, 16, st);
-			k_glob_zsize<<<(n_gwarps + 127) / 128, 128, 0, st>>>(gt, g_order, g_keys_s, A, zsize, n_gwarps);
+			// bands of wide_cols columns or more go to the warp-per-task kernel (at most the ring: EMAB_GLOB_WIDE_COLS is a tuning knob)
+			static const int wide_cols = [] { const char *e = getenv("EMAB_GLOB_WIDE_COLS"); int v = e ? atoi(e) : GLOB_WIDE_COLS; return v < 2 ? 2 : (v > GLOB_RING_COLS ? GLOB_RING_COLS : v); }();
+			k_glob_zsize<<<(n_gwarps + 127) / 128, 128, 0, st>>>(gt, g_order, g_keys_s, A, zsize, n_gwarps, wide_cols);
 			cub::DeviceScan::ExclusiveSum(nullptr, sb, zsize, zoff, n_gwarps + 1, st);
 			TRY(c->b[6].ensure(sb + 16));
 			cub::DeviceScan::ExclusiveSum(c->b[6].p, sb, zsize, zoff, n_gwarps + 1, st);
@@ -806,9 +808,9 @@ static int align_pairs_core(emab_ctx_t *c, int n_pairs, int max_len, int64_t tot
 			// memory per warp instead of 28); wide bands: one WARP per task, beside it on the ctx's second stream
 			TRY(ctx_fork(c));
 			k_glob_wave<<<n_gwarps, 32, glob_smem_bytes(max_len, GLOB_RING_COLS), st>>>(ix, gt, g_order, g_keys_s, A, zoff, c->b[40].as<uint8_t>(),
-			                                                          c->b[39].as<uint32_t>(), &c->d_counters[14], max_len, GLOB_RING_COLS, 0, GLOB_RING_COLS - 1);
+			                                                          c->b[39].as<uint32_t>(), &c->d_counters[14], max_len, GLOB_RING_COLS, 0, wide_cols - 1);
 			k_glob_wide<<<grid, PL_WARPS * 32, 0, c->stream2>>>(ix, gt, g_order, g_keys_s, A, c->b[39].as<uint32_t>(), c->b[16].as<uint8_t>(), z_cap,
-			                                                    c->b[17].as<uint32_t>(), &c->d_counters[14], wide_queue);
+			                                                    c->b[17].as<uint32_t>(), &c->d_counters[14], wide_queue, wide_cols);
 			TRY(ctx_join(c));
 			++launches;
 			CUDA_TRY(cudaEventRecord(c->stage_ev[11], st));
