@@ -78,6 +78,43 @@ def test_read_with_many_sa_intervals(tmp_path):
     assert any(l.startswith(b"engineered\t") for l in body)
 
 
+def test_seeding_long_interval_lists(tmp_path):
+    """A staircase of planted prefixes (S[0:k] for k = 25..70, each once, each followed by a wrong base) makes the forward
+    sweep over S change its interval size 46 times: bwt_smem1a's prev/curr lists outgrow the 24 entries the seeding kernel
+    keeps in shared memory and continue in its global slab.  The default form must still equal the exact one."""
+    import ema_b200
+    from tools import synth
+    rng = np.random.default_rng(123)
+    contigs = synth.make_reference(1, 80_000, 7, 0)
+    S = rng.integers(0, 4, 70, dtype=np.uint8)
+    c = contigs[0]
+    for n, k in enumerate(range(25, 71)):
+        pos = 1000 + 1500 * n
+        c[pos:pos + k] = S[:k]
+        c[pos - 1] = (S[0] + 1 + (n & 1)) & 3           # nothing extends the copies to the left in step
+        if k < 70:
+            c[pos + k] = (S[k] + 1) & 3
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, contigs)
+    ema_b200.index_build(fa)
+    ctx = ema_b200.Context(ema_b200.Index(fa))
+    reads = []
+    for cut in (70, 60, 45):
+        for lead in (0, 7, 30):
+            reads.append(np.concatenate([rng.integers(0, 4, lead, dtype=np.uint8), S[:cut], rng.integers(0, 4, 100 - cut, dtype=np.uint8)]))
+            reads.append(np.ascontiguousarray((3 - reads[-1])[::-1]))
+    got, _ = ema_b200.smem_batch(ctx, reads, max_intv=512)
+    ema_b200.set_seed_mode(ctx, 3)
+    want, _ = ema_b200.smem_batch(ctx, reads, max_intv=512)
+    ema_b200.set_seed_mode(ctx, 0)
+    assert max(len(w) for w in want) >= 3
+    sizes = set()
+    for a, b in zip(got, want):
+        assert len(a) == len(b) and np.array_equal(a[:, [0, 2, 3]], b[:, [0, 2, 3]])
+        sizes |= set(int(v) for v in b[:, 2])
+    assert len(sizes) >= 3
+
+
 @pytest.mark.parametrize("platform", ["tru", "10x"])
 def test_fastq_stream_small_batches(platform, tmp_path):
     """-1 cut into ~20 device batches: same bytes as the reference (whose cloud ids run through the whole file)."""

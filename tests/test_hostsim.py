@@ -160,6 +160,42 @@ def test_seeding_hot_equals_exact_c1_rep(hs):
     assert sectors * 32 < 0.6 * touches * 64, (sectors, touches)
 
 
+def test_seeding_hot_staircase(hs, tmp_path):
+    """forward sweeps whose interval size changes 46 times (a staircase of planted prefixes): long prev/curr lists, every
+    k-mer table level and several FM steps recorded, multi-step backward rounds — default form against the exact one"""
+    import subprocess
+    from tools import synth
+    if not os.path.exists(helpers.ref_bin("bwa")):
+        pytest.skip("oracle/_ref/bwa not built")
+    rng = np.random.default_rng(123)
+    contigs = synth.make_reference(1, 80_000, 7, 0)
+    S = rng.integers(0, 4, 70, dtype=np.uint8)
+    c = contigs[0]
+    for n, k in enumerate(range(25, 71)):
+        pos = 1000 + 1500 * n
+        c[pos:pos + k] = S[:k]
+        c[pos - 1] = (S[0] + 1 + (n & 1)) & 3
+        if k < 70:
+            c[pos + k] = (S[k] + 1) & 3
+    fa = str(tmp_path / "ref.fa")
+    synth.write_fasta(fa, contigs)
+    subprocess.run([helpers.ref_bin("bwa"), "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    hi = C.c_void_p(hs.hs_index_load(fa.encode()))
+    n_long = 0
+    for K in (-1, 0, 3):
+        hs.hs_set_kmer_k(hi, K)
+        for cut in (70, 60, 45):
+            for lead in (0, 7, 30):
+                r = np.concatenate([rng.integers(0, 4, lead, dtype=np.uint8), S[:cut], rng.integers(0, 4, 100 - cut, dtype=np.uint8)])
+                for s in (np.ascontiguousarray(r), np.ascontiguousarray((3 - r)[::-1])):
+                    a, b = np.zeros((512, 4), np.int64), np.zeros((512, 4), np.int64)
+                    na = hs.hs_collect_intv(hi, len(s), _p(s, C.c_uint8), _p(a, C.c_int64), 512)
+                    nb = hs.hs_collect_intv_hot(hi, len(s), _p(s, C.c_uint8), _p(b, C.c_int64), 512, None)
+                    assert na == nb and na >= 1 and np.array_equal(a[:na, [0, 2, 3]], b[:nb, [0, 2, 3]])
+                    n_long += int((a[:na, 2] > 5).any())
+    assert n_long > 10, "the staircase should yield multi-copy intervals"
+
+
 def test_scalar_patch_global_vs_oracle(hs, port_lib):
     """ScalarPatchDP::global (the score-only ksw_global2 the thread-per-read kernel runs inline for
     mem_patch_reg) against the oracle: same score and same visited cells, both strands, assorted bands."""
