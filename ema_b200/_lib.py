@@ -35,7 +35,10 @@ def lib():
         L.emab_ctx_free.argtypes = [C.c_void_p]
         L.emab_session_close.argtypes = [C.c_void_p]
         L.emab_free.argtypes = [C.c_void_p]
-        L.emab_align_bucket.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.emab_align_bucket.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.emab_pinned_alloc.restype = C.c_void_p
+        L.emab_pinned_alloc.argtypes = [C.c_uint64]
+        L.emab_pinned_free.argtypes = [C.c_void_p]
         L.emab_align_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
@@ -303,6 +306,37 @@ class RunStats(C.Structure):
                [("ms_ext_wave", C.c_double), ("ms_glob_wave", C.c_double), ("format_kernel_ms", C.c_double)]
 
 
+class PinnedText:
+    """A host buffer in page-locked memory (emab_pinned_alloc) holding `data`: what a caller that reads its bucket files into
+    pinned buffers hands to emab_align_bucket[s] — the library copies it to the device without a staging copy."""
+
+    def __init__(self, data: bytes):
+        self.n = len(data)
+        self.ptr = lib().emab_pinned_alloc(max(self.n, 1))
+        if not self.ptr:
+            raise EmabError("emab_pinned_alloc failed")
+        C.memmove(self.ptr, data, self.n)
+
+    def __len__(self):
+        return self.n
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().emab_pinned_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def _host_ptr(d):
+    """(address, keep-alive object) of a bytes object or a PinnedText"""
+    if isinstance(d, PinnedText):
+        return d.ptr, d
+    b = C.c_char_p(d)
+    return C.cast(b, C.c_void_p).value, b
+
+
 class Session:
     """The operator the reference's main() calls (find_clouds_and_align and friends) on one GPU:
     emab_session_open / emab_sam_header / emab_align_bucket / emab_align_fastq."""
@@ -327,9 +361,11 @@ class Session:
         lib().emab_free(text)
         return out
 
-    def align_bucket(self, data: bytes) -> bytes:
+    def align_bucket(self, data) -> bytes:
         text, n = C.c_void_p(), C.c_uint64()
-        _check(lib().emab_align_bucket(self._h, data, len(data), C.byref(text), C.byref(n)))
+        addr, keep = _host_ptr(data)
+        _check(lib().emab_align_bucket(self._h, addr, len(data), C.byref(text), C.byref(n)))
+        del keep
         return self._take(text, n)
 
     def set_workers(self, n: int):
@@ -343,7 +379,8 @@ class Session:
         """emab_align_buckets (-x mode): up to `workers` buckets in flight; returns the SAM texts in input
         order (or only their lengths when keep_text is False, which skips the copy into Python objects)."""
         n = len(datas)
-        arr = (C.c_char_p * n)(*datas)
+        ptrs = [_host_ptr(d) for d in datas]
+        arr = (C.c_void_p * n)(*[a for a, _ in ptrs])
         lens = (C.c_uint64 * n)(*[len(d) for d in datas])
         outs = (C.c_void_p * n)()
         olens = (C.c_uint64 * n)()

@@ -293,6 +293,13 @@ extern "C" void *emab_pinned_alloc(uint64_t bytes)
 	return p;
 }
 extern "C" void emab_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+// is p inside a page-locked host allocation (one the device can copy from asynchronously, without a staging copy)?
+extern "C" int emab_is_pinned_host(const void *p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return a.type == cudaMemoryTypeHost;
+}
 
 // mode 0: poll ~150 us then sleep between polls, 1: spin, 2: blocking-sync event.  EMAB_SYNC overrides.
 extern "C" int emab_ctx_set_wait(emab_ctx_t *c, int mode)

@@ -1355,8 +1355,11 @@ static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size
 	// the bucket's text goes to the device once (through a page-locked copy) and is parsed there: line split, stable barcode
 	// sort, tokens, barcode codes (csrc/parse.cu).  What comes back is one record per pair saying where its fields are.
 	if (len >= 0xfffffff0ull) { *err = "bucket larger than 4 GB"; s->take_cloud_base(ticket, 0); return EMAB_ERR_ARG; }
-	if (wk.seq.ensure(len + 16)) { *err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
-	{
+	// a caller's buffer that is already page-locked (emab_pinned_alloc, cudaHostAlloc, cudaHostRegister) is copied to the
+	// device as it is; anything else goes through this worker's page-locked staging copy first
+	const char *h2d_src = data;
+	if (!emab_is_pinned_host(data)) {
+		if (wk.seq.ensure(len + 16)) { *err = emab_last_error(); s->take_cloud_base(ticket, 0); return EMAB_ERR_NOMEM; }
 		char *text = (char *)wk.seq.p;
 		const long long n_blk = (long long)((len + (1u << 20) - 1) >> 20);
 		#pragma omp parallel for num_threads(wk.n_threads) schedule(static)
@@ -1365,11 +1368,12 @@ static int run_bucket(Session *s, Worker &wk, int ticket, const char *data, size
 			const size_t a0 = (size_t)blk << 20, a1 = std::min(len, a0 + (1u << 20));
 			memcpy(text + a0, data + a0, a1 - a0);
 		}
+		h2d_src = text;
 	}
 	int n = 0;
 	const emab_pair_text_t *pt = nullptr;
 	const uint64_t *bcs = nullptr;
-	int rc = emab_parse_bucket(wk.ctx, (const char *)wk.seq.p, (uint64_t)len, s->bc_len, s->is_haplotag ? 1 : 0, &n, &pt, &bcs);
+	int rc = emab_parse_bucket(wk.ctx, h2d_src, (uint64_t)len, s->bc_len, s->is_haplotag ? 1 : 0, &n, &pt, &bcs);
 	if (rc) { *err = emab_last_error(); s->take_cloud_base(ticket, 0); return rc; }
 	std::vector<Pair> pairs((size_t)n);
 	#pragma omp parallel num_threads(wk.n_threads)

@@ -236,6 +236,7 @@ int emab_sam_format(emab_ctx_t *ctx, const emab_sam_job_t *job, char *out, uint6
 /* pinned host memory for callers that want their input buffers to take the fast H2D path */
 void *emab_pinned_alloc(uint64_t bytes);
 void emab_pinned_free(void *p);
+int emab_is_pinned_host(const void *p);   /* 1 if p lies in page-locked host memory: such buffers are copied to the device without a staging copy */
 
 /* ---- the barcode-cloud EM (src/align.c:410-543) ------------------------------------------------
  * The host groups candidates into clouds and links mates (the SAMDict bookkeeping of

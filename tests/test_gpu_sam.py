@@ -124,6 +124,12 @@ def test_multi_bucket_pipeline_matches_serial(tmp_path):
     multi = s2.align_buckets(parts)
     assert multi == serial
     assert sum(len(x) for x in multi) > 1_000_000
+    # the same buckets handed over in page-locked buffers (copied to the device without the staging copy), mixed with plain ones
+    s3 = ema_b200.Session(p["fasta"], "10x", threads=8)
+    s3.set_workers(3)
+    mixed = [ema_b200.PinnedText(d) if i % 2 == 0 else d for i, d in enumerate(parts)]
+    assert s3.align_buckets(mixed) == serial
+    assert s3.align_bucket(ema_b200.PinnedText(parts[1])) is not None
     files = []
     for i, d in enumerate(parts[:4]):
         f = tmp_path / f"b{i}"
