@@ -1507,7 +1507,8 @@ int align_special_fastq_multi(Session *s, int n, const char *const *data, const 
 	caps[PH_DEVICE] *= (int)s->replicas.size();   // the cap is per GPU
 	for (int k = 0; k < PH_COUNT; ++k) s->gate[k].cap = W > 1 ? std::max(1, std::min(caps[k], W)) : 1;
 	const int cap = W > 1 ? std::max(s->gate[PH_PARSE].cap, s->gate[PH_POST].cap) : 1;
-	const int per = std::max(1, s->n_threads / cap);
+	int per = std::max(1, s->n_threads / cap);
+	if (const char *e = getenv("EMAB_PHASE_THREADS")) per = std::max(1, atoi(e));   // tuning knob: OpenMP threads of one bucket's CPU phase
 	std::vector<int> tickets(n);
 	for (int i = 0; i < n; ++i) { tickets[i] = s->new_ticket(); out[i] = nullptr; out_len[i] = 0; }
 	std::atomic<int> next(0), first_err(0);
