@@ -1,5 +1,7 @@
-// Host-side launcher of the seeding stage (seed.cuh) shared by emab_align_pairs and emab_smem_batch:
-//   k_seed         persistent warps, pass-1/2 and pass-3 roles fed from two atomic read queues
+// Host-side launcher of the seeding stage shared by emab_align_pairs and emab_smem_batch:
+//   k_pack_reads + k_seed_rq   the default: 2-bit packed reads, then the request loop of seed_rq.cuh (four lanes per read,
+//                              persistent warps fed from one atomic job queue: passes 1+2 of every read, then pass 3)
+//   k_seed / k_seed_quad / k_seed_wide / k_seed_staged   the exact forms over bwa's Occ layout (seed.cuh, seed_quad.cuh)
 //   k_seed_finish  thread / read: merge + sort by info (bwa/bwamem.c:187), SA-occurrence count
 #pragma once
 #include <cstdlib>
@@ -101,12 +103,13 @@ k_seed_finish(SeedBatch b, int32_t *n_intv, int32_t *occ_cnt)
 	}
 }
 
-// EMAB_SEED_MODE: 1 (default) = one lane per read, Occ blocks in registers (seed.cuh); 2 = one lane per read, Occ blocks
+// EMAB_SEED_MODE: 1 = one lane per read, Occ blocks in registers (seed.cuh); 2 = one lane per read, Occ blocks
 // staged in shared memory by cp.async; 4 = four lanes per read (seed_quad.cuh).  Measured on the 3.1 Gbp index, one
 // 40 000-pair bucket (profiles/r2e_*): mode 1 5.1 ms, mode 4 6.0-6.5 ms — the quad form moves 16 % less DRAM traffic and
 // keeps its lists in shared memory, but runs the loops' bookkeeping on four lanes per read: 2.5 x the warp instructions,
 // 70 % ALU-pipe utilisation; the kernel's length is set by its longest reads' dependent chains, not by bandwidth.
-//   3 = four lanes per read, one backward-round entry per lane (seed_quads_wide); 5 (default) = seed_hot.cuh
+//   3 = four lanes per read, one backward-round entry per lane (seed_quads_wide: 4.75 ms, the best of the exact forms);
+//   5 (default) = the algorithm of seed_hot.cuh run as the request loop of seed_rq.cuh (2.2 ms)
 static inline int seed_mode_env()   // read at every launch: a measurement run can switch forms between buckets
 {
 	const char *e = getenv("EMAB_SEED_MODE");
