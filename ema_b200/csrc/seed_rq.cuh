@@ -230,6 +230,9 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 	s.min_intv = 1; s.last_size = 0; s.f_x0 = s.f_x1 = s.f_x2 = 0; s.text_p = 0; s.e_x0 = s.e_x2 = 0; s.e_end = 0; s.e_valid = 0;
 	const int K = ix.kmer_k;
 	for (;;) {
+		// what the quad's lanes stored in the last iteration's consume (list entries, read words) is ordered before what any
+		// of them reads from here on; all 32 lanes pass here every iteration
+		__syncwarp();
 		// ------------------------------------------------------------------ latency-free transitions, each written once
 		while (s.st >= RqQuad::JOB && s.st != RqQuad::DRAINED) {
 			switch (s.st) {
@@ -401,7 +404,7 @@ __device__ __forceinline__ void seed_rq_warp(const DevIndex &ix, const RqBatch &
 			}
 		}
 		if (!__any_sync(0xffffffffu, req)) break;
-		__syncwarp();   // list entries and read words stored in the last iteration are visible to the quad's other lanes from here on
+		__syncwarp();   // ... and what the transitions above stored (all four lanes the same value) before the consume below reads it
 		// ------------------------------------------------------------------ issue: the one place where DRAM is read
 		uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0;
 		ldg128_if(p0, a0, r0); ldg128_if(p1, a1, r1); ldg128_if(p2, a2, r2); ldg128_if(p3, a3, r3);
