@@ -17,6 +17,7 @@
 #ifndef EMA_B200_H
 #define EMA_B200_H
 #include <stdint.h>
+#include <stdio.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -63,6 +64,14 @@ typedef struct {
 int emab_index_build(const char *fasta_path, const char *prefix, int device, emab_index_build_stats_t *stats);
 /* the host half on its own (= `bwa fa2pac -f`): <prefix>.pac/.ann/.amb only; needs no GPU */
 int emab_index_pack_fasta(const char *fasta_path, const char *prefix);
+
+/* ---- the producers of the bucket format (host code; need no GPU) ----------------------------
+ * emab_count   = count()   (cpp/count.h, cpp/count.cc:38-182):   interleaved FASTQ (in: NULL = stdin) -> <prefix>.ema-ncnt, .ema-fcnt
+ * emab_preproc = correct() (cpp/correct.h, cpp/correct.cc:271-633): the count files + the same FASTQ -> <dir>/ema-bin-NNN, ema-nobc
+ * Files are byte-identical to the reference's (tests/test_preproc.py).  10x barcodes only: is_haplotag != 0 is refused. */
+int emab_count(const char *whitelist_path, const char *output_prefix, uint64_t max_map_bytes, int is_haplotag, FILE *in);
+int emab_preproc(const char *whitelist_path, const char *const *count_files, int n_count_files, const char *output_dir,
+                 int do_h2, uint64_t buffer_size, int do_bx_format, int n_threads, int n_buckets, int is_haplotag, FILE *in);
 
 int emab_ctx_create(emab_index_t *ix, emab_ctx_t **out);  /* ix may be NULL for the sequence-only SW calls */
 void emab_ctx_free(emab_ctx_t *ctx);

@@ -193,3 +193,38 @@ def test_single_bucket_split_over_replicas():
     split = s2.align_bucket(data)
     assert split == serial
     assert s2.align_bucket(data).count(b"\n") == serial.count(b"\n")
+
+
+def test_raw_fastq_through_count_preproc_align(tmp_path):
+    """From RAW 10x reads: `count` -> `preproc` -> `align` with this build against the same three steps of the reference —
+    identical bucket files (host/preproc.cpp), identical SAM (the buckets carry corrected barcodes, trimmed read 1)."""
+    import filecmp
+    from tools import synth
+    if not os.path.exists(helpers.ref_bin("bwa")):
+        pytest.skip("oracle/_ref/bwa missing")
+    p = synth.build_config("c1_rep", helpers.DATA_ROOT, helpers.ref_bin("bwa"))
+    n_contigs, clen, rseed, dup, nbc, ppb, indel = synth.CONFIGS["c1_rep"]
+    contigs = synth.make_reference(n_contigs, clen, rseed, dup)
+    sim = synth.simulate_pairs(contigs, 40, 60, rseed + 4242, indel=indel)
+    fq, wl = str(tmp_path / "raw.fq"), str(tmp_path / "wl.txt")
+    synth.write_raw_10x_fastq(fq, wl, sim)
+    outs = {}
+    for tag, exe in (("ref", helpers.ref_bin("ema")), ("our", CLI)):
+        with open(fq, "rb") as f:
+            subprocess.run([exe, "count", "-w", wl, "-o", str(tmp_path / tag)], stdin=f, check=True, stderr=subprocess.DEVNULL)
+        with open(fq, "rb") as f:
+            subprocess.run([exe, "preproc", "-w", wl, "-n", "3", "-t", "2", "-o", str(tmp_path / (tag + "_b")), str(tmp_path / tag) + ".ema-ncnt"],
+                           stdin=f, check=True, stderr=subprocess.DEVNULL)
+        outs[tag] = tmp_path / (tag + "_b")
+    names = sorted(os.listdir(outs["ref"]))
+    assert names == sorted(os.listdir(outs["our"])) == ["ema-bin-000", "ema-bin-001", "ema-bin-002", "ema-nobc"]
+    for n in names:
+        assert filecmp.cmp(outs["ref"] / n, outs["our"] / n, shallow=False), n
+    bucket = str(outs["our"] / "ema-bin-001")
+    ref_sam, our_sam = tmp_path / "ref.sam", tmp_path / "our.sam"
+    subprocess.run([helpers.ref_bin("ema"), "align", "-s", bucket, "-r", p["fasta"], "-p", "10x", "-t", "1", "-o", str(ref_sam)], check=True, stderr=subprocess.DEVNULL)
+    subprocess.run([CLI, "align", "-s", bucket, "-r", p["fasta"], "-p", "10x", "-t", "8", "-o", str(our_sam)], check=True, stderr=subprocess.DEVNULL)
+    _, b1 = split_sam(ref_sam.read_bytes())
+    _, b2 = split_sam(our_sam.read_bytes())
+    assert b1 == b2, diff_msg(b1, b2)
+    assert len(b1) > 1000

@@ -1,0 +1,140 @@
+"""CPU tests (-m "not gpu"): `ema-b200 count` / `preproc` (host/preproc.cpp) against the reference binary (oracle/_ref/ema) on a
+synthetic raw 10x FASTQ — whitelisted barcodes, one- and two-base errors with matching low qualities, N bases, barcodes not
+on the list, short reads, a quality character below '!'.  Every output file must be byte-identical: the census (.ema-ncnt in
+the reference's hash-map order, .ema-fcnt incl. block dumps), every ema-bin-NNN and ema-nobc, with and without -h / -b."""
+import filecmp
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+
+CLI = os.path.join(helpers.ROOT, "ema_b200", "ema-b200")
+REF = helpers.ref_bin("ema")
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def make_raw_fastq(path, wl_path, n_pairs=6000, n_wl=400, n_used=60, seed=7):
+    rng = np.random.default_rng(seed)
+    wl = set()
+    while len(wl) < n_wl:
+        bc = rng.integers(0, 4, 16)
+        if bc.any():
+            wl.add(bytes(ACGT[bc]))
+    wl = sorted(wl)
+    order = rng.permutation(len(wl))
+    with open(wl_path, "wb") as f:
+        for i in order:
+            f.write(wl[i] + b"\n")
+    used = [wl[i] for i in order[:n_used]]
+    with open(path, "wb") as f:
+        for i in range(n_pairs):
+            bc = bytearray(used[int(rng.integers(0, n_used))])
+            qual = bytearray(b"I" * 16)
+            kind = rng.random()
+            if kind < 0.10:      # one substitution, low quality there
+                k = int(rng.integers(0, 16)); bc[k] = b"ACGT"[(b"ACGT".index(bc[k]) + int(rng.integers(1, 4))) % 4]; qual[k] = ord("#") + int(rng.integers(0, 8))
+            elif kind < 0.14:    # two substitutions
+                for k in rng.choice(16, 2, replace=False):
+                    bc[k] = b"ACGT"[(b"ACGT".index(bc[k]) + int(rng.integers(1, 4))) % 4]; qual[k] = ord("#") + int(rng.integers(0, 5))
+            elif kind < 0.18:    # an N
+                k = int(rng.integers(0, 16)); bc[k] = ord("N"); qual[k] = ord("#")
+            elif kind < 0.20:    # two Ns
+                for k in rng.choice(16, 2, replace=False):
+                    bc[k] = ord("N"); qual[k] = ord("#")
+            elif kind < 0.25:    # not on the list
+                bc = bytearray(ACGT[rng.integers(0, 4, 16)].tobytes())
+            elif kind < 0.27:    # substitution with HIGH quality (should not be corrected confidently when ambiguous)
+                k = int(rng.integers(0, 16)); bc[k] = b"ACGT"[(b"ACGT".index(bc[k]) + 1) % 4]
+            l1 = 16 + 7 + int(rng.integers(90, 128)) if rng.random() > 0.02 else int(rng.integers(5, 31))   # some reads too short
+            r1 = bytes(bc) + ACGT[rng.integers(0, 4, max(0, l1 - 16))].tobytes()
+            r1 = r1[:l1]
+            q1 = (bytes(qual) + bytes(rng.integers(35, 75, max(0, l1 - 16)).astype(np.uint8)))[:l1]
+            if rng.random() < 0.003 and l1 > 20:
+                q1 = q1[:3] + b" " + q1[4:]      # a quality character below '!': the read is ignored
+            if rng.random() < 0.01 and l1 > 20:
+                q1 = q1[:5] + b"~" + q1[6:]      # above the cap: trimmed to 'B'
+            l2 = int(rng.integers(100, 151))
+            r2 = ACGT[rng.integers(0, 4, l2)].tobytes()
+            q2 = bytes(rng.integers(35, 75, l2).astype(np.uint8))
+            extra = b" 1:N:0:1" if i % 3 == 0 else b""
+            f.write(b"@read%d%s\n%s\n+\n%s\n@read%d%s\n%s\n+\n%s\n" % (i, extra, r1, q1, i, extra.replace(b"1:N", b"2:N"), r2, q2))
+    return wl_path
+
+
+def run(cmd, stdin_path, cwd=None):
+    with open(stdin_path, "rb") as fin:
+        subprocess.run(cmd, stdin=fin, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=cwd)
+
+
+@pytest.fixture(scope="module")
+def raw(tmp_path_factory):
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/ema not built")
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-s", "-C", os.path.join(helpers.ROOT, "ema_b200", "csrc")], check=True)
+    d = tmp_path_factory.mktemp("raw")
+    fq, wl = str(d / "reads.fq"), str(d / "wl.txt")
+    make_raw_fastq(fq, wl)
+    return d, fq, wl
+
+
+def same_dir(a, b):
+    names = sorted(os.listdir(a))
+    assert names == sorted(os.listdir(b)) and names
+    for n in names:
+        assert filecmp.cmp(os.path.join(a, n), os.path.join(b, n), shallow=False), n
+    return names
+
+
+def test_count_files_identical(raw):
+    d, fq, wl = raw
+    run([REF, "count", "-w", wl, "-o", str(d / "ref")], fq)
+    run([CLI, "count", "-w", wl, "-o", str(d / "our")], fq)
+    for ext in (".ema-ncnt", ".ema-fcnt"):
+        assert filecmp.cmp(str(d / "ref") + ext, str(d / "our") + ext, shallow=False), ext
+    assert os.path.getsize(str(d / "our") + ".ema-ncnt") > 8 + 12 * 30
+
+
+@pytest.mark.parametrize("flags", [[], ["-h"], ["-b"], ["-h", "-t", "3", "-n", "5"]])
+def test_preproc_buckets_identical(raw, flags, tmp_path):
+    d, fq, wl = raw
+    if not os.path.exists(str(d / "ref.ema-ncnt")):
+        run([REF, "count", "-w", wl, "-o", str(d / "ref")], fq)
+    n = ["-n", "7"] if "-n" not in flags else []
+    run([REF, "preproc", "-w", wl, "-o", str(tmp_path / "ref_out")] + n + flags + [str(d / "ref.ema-ncnt")], fq)
+    run([CLI, "preproc", "-w", wl, "-o", str(tmp_path / "our_out")] + n + flags + [str(d / "ref.ema-ncnt")], fq)
+    names = same_dir(str(tmp_path / "ref_out"), str(tmp_path / "our_out"))
+    assert "ema-nobc" in names and "ema-bin-000" in names
+    assert sum(os.path.getsize(str(tmp_path / "our_out" / x)) for x in names if x.startswith("ema-bin")) > 500_000
+
+
+def test_count_block_dumps(raw):
+    """the full census written in several blocks (a small map budget), through the C ABI"""
+    import ctypes as C
+    d, fq, wl = raw
+    lib = C.CDLL(os.path.join(helpers.ROOT, "ema_b200", "libema_b200.so"))
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    lib.emab_count.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p]
+    f = libc.fopen(fq.encode(), b"rb")
+    assert lib.emab_count(wl.encode(), str(d / "blk").encode(), 72 * 400, 0, f) == 0
+    libc.fclose(f)
+    data = open(str(d / "blk.ema-fcnt"), "rb").read()
+    blocks, pos, total = 0, 0, 0
+    while pos < len(data):
+        n = int.from_bytes(data[pos:pos + 8], "little"); pos += 8
+        keys = [data[pos + 24 * i:pos + 24 * i + 16] for i in range(n)]
+        assert keys == sorted(keys)
+        total += sum(int.from_bytes(data[pos + 24 * i + 16:pos + 24 * i + 24], "little") for i in range(n))
+        pos += 24 * n; blocks += 1
+    assert blocks >= 3 and pos == len(data)
+    ref = open(str(d / "ref.ema-fcnt"), "rb").read() if os.path.exists(str(d / "ref.ema-fcnt")) else None
+    if ref:
+        n = int.from_bytes(ref[:8], "little")
+        assert total == sum(int.from_bytes(ref[8 + 24 * i + 16:8 + 24 * i + 24], "little") for i in range(n))
+    assert lib.emab_count(wl.encode(), str(d / "x").encode(), 1 << 30, 1, None) != 0   # haplotag: refused

@@ -224,6 +224,43 @@ def write_bucket(path: str, sim, *, platform="10x", shuffle=True):
     return bcs
 
 
+def write_raw_10x_fastq(path: str, whitelist_path: str, sim, *, n_whitelist=2000, err=0.03):
+    """RAW 10x reads as `ema count` / `ema preproc` take them (interleaved FASTQ, pairs in random order): read 1 = the
+    16-base barcode + 7 bases that preproc trims + the insert's first mate.  A fraction `err` of the pairs carries one
+    substitution in the barcode (low quality there), a few an N or a barcode that is not on the list.  Also writes the
+    whitelist (the used barcodes among `n_whitelist` random ones, shuffled)."""
+    rng = np.random.default_rng(sim["seed"] + 15485863)
+    nb = sim["n_barcodes"]
+    bcs = random_barcodes(nb, 16, rng)
+    wl = set(bcs)
+    while len(wl) < max(n_whitelist, nb):
+        wl.add(ACGT[rng.integers(0, 4, 16)].tobytes())
+    wl = sorted(wl)
+    with open(whitelist_path, "wb") as f:
+        for i in rng.permutation(len(wl)):
+            f.write(wl[i] + b"\n")
+    order, s1, s2, q1, q2 = _lines(sim, None, bcs, rng)
+    bc_idx = sim["bc_idx"]
+    with open(path, "wb") as f:
+        out = []
+        for i in order:
+            bc = bytearray(bcs[bc_idx[i]])
+            qb = bytearray(b"I" * 16)
+            u = rng.random()
+            if u < err:
+                k = int(rng.integers(0, 16)); bc[k] = b"ACGT"[(b"ACGT".index(bc[k]) + int(rng.integers(1, 4))) % 4]; qb[k] = ord("%")
+            elif u < err + 0.005:
+                k = int(rng.integers(0, 16)); bc[k] = ord("N"); qb[k] = ord("#")
+            elif u < err + 0.01:
+                bc = bytearray(ACGT[rng.integers(0, 4, 16)].tobytes())
+            trim = ACGT[rng.integers(0, 4, 7)].tobytes()
+            rid = b"@r" + str(int(i)).encode()
+            out.append(rid + b" 1:N:0\n" + bytes(bc) + trim + s1[i] + b"\n+\n" + bytes(qb) + b"IIIIIII" + q1 + b"\n" +
+                       rid + b" 2:N:0\n" + s2[i] + b"\n+\n" + q2 + b"\n")
+        f.write(b"".join(out))
+    return bcs
+
+
 def write_interleaved_fastq(path: str, sim, *, platform="tru"):
     """Barcode-sorted interleaved FASTQ for `-1` mode.
     tru:     id ``@<int>_<name>`` (barcode = atoi, src/techs.c:57-61)
