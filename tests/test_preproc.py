@@ -138,3 +138,35 @@ def test_count_block_dumps(raw):
         n = int.from_bytes(ref[:8], "little")
         assert total == sum(int.from_bytes(ref[8 + 24 * i + 16:8 + 24 * i + 24], "little") for i in range(n))
     assert lib.emab_count(wl.encode(), str(d / "x").encode(), 1 << 30, 1, None) != 0   # haplotag: refused
+
+
+@pytest.mark.parametrize("case", ["empty", "no_final_newline", "one_pair"])
+def test_preproc_edge_inputs(raw, case, tmp_path):
+    """an empty stream, a last line without its newline, a single pair: same files as the reference"""
+    d, fq, wl = raw
+    text = open(fq, "rb").read()
+    lines = text.split(b"\n")
+    small = {"empty": b"", "no_final_newline": b"\n".join(lines[:8 * 50]), "one_pair": b"\n".join(lines[:8]) + b"\n"}[case]
+    sfq = str(tmp_path / "s.fq")
+    open(sfq, "wb").write(small)
+    for tag, exe in (("ref", REF), ("our", CLI)):
+        run([exe, "count", "-w", wl, "-o", str(tmp_path / tag)], sfq)
+        run([exe, "preproc", "-w", wl, "-n", "4", "-o", str(tmp_path / (tag + "_out")), str(tmp_path / tag) + ".ema-ncnt"], sfq)
+    for ext in (".ema-ncnt", ".ema-fcnt"):
+        assert filecmp.cmp(str(tmp_path / "ref") + ext, str(tmp_path / "our") + ext, shallow=False), ext
+    same_dir(str(tmp_path / "ref_out"), str(tmp_path / "our_out"))
+
+
+def test_preproc_several_count_files(raw, tmp_path):
+    """the census of two FASTQ halves counted separately and corrected together (`preproc ... a.ema-ncnt b.ema-ncnt`)"""
+    d, fq, wl = raw
+    lines = open(fq, "rb").read().split(b"\n")
+    half = (len(lines) // 16) * 8
+    parts = [b"\n".join(lines[:half]) + b"\n", b"\n".join(lines[half:])]
+    for i, p in enumerate(parts):
+        open(str(tmp_path / f"p{i}.fq"), "wb").write(p)
+    for tag, exe in (("ref", REF), ("our", CLI)):
+        for i in range(2):
+            run([exe, "count", "-w", wl, "-o", str(tmp_path / f"{tag}{i}")], str(tmp_path / f"p{i}.fq"))
+        run([exe, "preproc", "-w", wl, "-n", "6", "-t", "2", "-o", str(tmp_path / (tag + "_out")), str(tmp_path / f"{tag}0.ema-ncnt"), str(tmp_path / f"{tag}1.ema-ncnt")], fq)
+    same_dir(str(tmp_path / "ref_out"), str(tmp_path / "our_out"))
