@@ -10,7 +10,8 @@
 // std::unordered_map<uint32_t, .> (cpp/count.cc:151-165, cpp/correct.cc:406-411).  The same container filled by the same
 // sequence of insertions reproduces it; everything order-independent here is laid out differently from the reference
 // (one pass over a block-buffered input, packed 16-byte observation keys, a flat sorted census instead of a node map).
-// 10x barcodes (16 bases + 7 trimmed bases in front of read 1); the haplotag variant (-p) is not part of this build.
+// 10x barcodes (16 bases + 7 trimmed bases in front of read 1) and, with is_haplotag, haplotag barcodes (a BX:Z:AxxCxxBxxDxx
+// tag on the name line, every one of the 96^4 combinations whitelisted, no correction, reads untrimmed).
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -95,6 +96,28 @@ bool observe(const std::string &r, std::string &q, ObsKey &key, uint32_t &code, 
 	return true;
 }
 
+// haplotag: "BX:Z:AxxCxxBxxDxx" after the first blank of the name line -> (A << 24 | C << 16 | B << 8 | D), two decimal
+// digits each taken as they are (cpp/common.h:69-75); `bound` is the length the reference compares the tag's end with
+// (cpp/count.cc:93, cpp/correct.cc:441: the name line in count, a stale line in correct)
+bool haplotag_code(const std::string &name, size_t bound, uint32_t &code, std::string &tag)
+{
+	size_t at = name.find_first_of(" \t");
+	if (at == std::string::npos) return false;
+	at = name.find("BX:Z:", at);
+	if (at == std::string::npos || !(at + 16 < bound)) return false;
+	tag = name.substr(at + 5, 12);
+	auto two = [&](size_t k) { return 10 * ((k < tag.size() ? tag[k] : 0) - '0') + ((k + 1 < tag.size() ? tag[k + 1] : 0) - '0'); };
+	code = (uint32_t)two(1) << 24 | (uint32_t)two(4) << 16 | (uint32_t)two(7) << 8 | (uint32_t)two(10);
+	return true;
+}
+// all 96^4 haplotag barcodes in the order the reference inserts them (cpp/common.h:76-77: a, b, c, d nested, key a|c|b|d)
+template <class Map, class Init>
+void all_haplotags(Map &m, Init init)
+{
+	for (uint32_t a = 1; a <= 96; ++a) for (uint32_t b = 1; b <= 96; ++b) for (uint32_t c = 1; c <= 96; ++c) for (uint32_t d = 1; d <= 96; ++d)
+		init(m[a << 24 | c << 16 | b << 8 | d]);
+}
+
 int load_whitelist(const char *path, std::vector<uint32_t> &codes)
 {
 	FILE *f = fopen(path, "r");
@@ -133,18 +156,20 @@ struct KeyHash {
 
 extern "C" int emab_count(const char *whitelist_path, const char *output_prefix, uint64_t max_map_bytes, int is_haplotag, FILE *in_stream)
 {
-	if (is_haplotag) return fail(EMAB_ERR_ARG, "count -p (haplotag barcodes) is not part of this build");
-	if (!whitelist_path || !output_prefix) return fail(EMAB_ERR_ARG, "count: whitelist and output prefix are required");
-	std::vector<uint32_t> wl;
-	if (int rc = load_whitelist(whitelist_path, wl)) return rc;
+	if ((!whitelist_path && !is_haplotag) || !output_prefix) return fail(EMAB_ERR_ARG, "count: whitelist and output prefix are required");
 	// the reference's container, filled in the reference's order: the census file is written in its iteration order
 	std::unordered_map<uint32_t, int64_t> seen;
-	for (uint32_t c : wl) seen[c] = 0;
+	if (is_haplotag) all_haplotags(seen, [](int64_t &v) { v = 0; });
+	else {
+		std::vector<uint32_t> wl;
+		if (int rc = load_whitelist(whitelist_path, wl)) return rc;
+		for (uint32_t c : wl) seen[c] = 0;
+	}
 	const std::string pre(output_prefix);
-	FILE *ff = fopen((pre + ".ema-fcnt").c_str(), "wb");
-	if (!ff) return fail(EMAB_ERR_IO, "Cannot open file " + pre + ".ema-fcnt");
+	FILE *ff = is_haplotag ? nullptr : fopen((pre + ".ema-fcnt").c_str(), "wb");   // haplotag: no full census (nothing is corrected)
+	if (!ff && !is_haplotag) return fail(EMAB_ERR_IO, "Cannot open file " + pre + ".ema-fcnt");
 	FILE *fn = fopen((pre + ".ema-ncnt").c_str(), "wb");
-	if (!fn) { fclose(ff); return fail(EMAB_ERR_IO, "Cannot open file " + pre + ".ema-ncnt"); }
+	if (!fn) { if (ff) fclose(ff); return fail(EMAB_ERR_IO, "Cannot open file " + pre + ".ema-ncnt"); }
 	// the full census of the current block: the reference dumps its std::map when (sizeof(key) + sizeof(count) + 32) * size
 	// reaches max_map_size (cpp/common.h:120-125, cpp/count.cc:140-143), i.e. at a fixed number of distinct keys
 	const size_t dump_at = (size_t)((max_map_bytes + 71) / 72);
@@ -156,23 +181,25 @@ extern "C" int emab_count(const char *whitelist_path, const char *output_prefix,
 		return write_block(ff, block);
 	};
 	Lines in(in_stream ? in_stream : stdin);
-	std::string name, r, q, skip;
+	std::string name, r, q, skip, tag;
 	ObsKey key;
 	int64_t total = 0, nice = 0, ignored = 0;
 	bool ok = true;
 	while (ok && in.next(name)) {
 		in.next(r); in.next(q); in.next(q);
-		bool process = r.size() >= MIN_READ;
 		uint32_t code = 0;
 		bool has_n = false;
-		if (process) process = observe(r, q, key, code, has_n);
+		bool process = (!is_haplotag || haplotag_code(name, name.size(), code, tag)) && r.size() >= MIN_READ;
+		if (process && !is_haplotag) process = observe(r, q, key, code, has_n);
 		if (process) {
 			if (!has_n) {
 				auto it = seen.find(code);
 				if (it != seen.end()) { ++it->second; ++nice; }
 			}
-			const bool fresh = ++census[key] == 1;
-			if (fresh && census.size() >= dump_at) ok = dump();
+			if (!is_haplotag) {
+				const bool fresh = ++census[key] == 1;
+				if (fresh && census.size() >= dump_at) ok = dump();
+			}
 			++total;
 		} else ++ignored;
 		for (int k = 0; k < 4; ++k) in.next(skip);
@@ -183,8 +210,7 @@ extern "C" int emab_count(const char *whitelist_path, const char *output_prefix,
 	for (const auto &e : seen)
 		if (e.second) ok = ok && put(fn, &e.first, 4) && put(fn, &e.second, 8);
 	fclose(fn);
-	ok = ok && dump();
-	fclose(ff);
+	if (ff) { ok = ok && dump(); fclose(ff); }
 	fprintf(stderr, ":: Reads with OK barcode: %lld out of %lld\n:: Ignored %lld reads\n", (long long)nice, (long long)total, (long long)ignored);
 	return ok ? EMAB_OK : fail(EMAB_ERR_IO, "fwrite failed");
 }
@@ -257,23 +283,26 @@ uint32_t assign(const ObsKey &q, const KnownMap &known, const double *perr, bool
 extern "C" int emab_preproc(const char *whitelist_path, const char *const *count_files, int n_count_files, const char *output_dir,
                             int do_h2, uint64_t buffer_size, int do_bx_format, int n_threads, int n_buckets, int is_haplotag, FILE *in_stream)
 {
-	if (is_haplotag) return fail(EMAB_ERR_ARG, "preproc -p (haplotag barcodes) is not part of this build");
-	if (!whitelist_path || !output_dir || n_buckets < 1 || n_count_files < 0) return fail(EMAB_ERR_ARG, "preproc: bad arguments");
+	if ((!whitelist_path && !is_haplotag) || !output_dir || n_buckets < 1 || n_count_files < 0) return fail(EMAB_ERR_ARG, "preproc: bad arguments");
 	if (n_threads < 1) n_threads = 1;
 	double perr[128];
 	for (int i = 0; i < 128; ++i) perr[i] = pow(10.0, -std::min(QBASE - 1, i) / 10.0);
 	// ---- whitelist and priors (cpp/correct.cc:291-336); the same container and insertion order as the reference: the
 	// barcodes are dealt to the bucket files in its iteration order
-	std::vector<uint32_t> wl;
-	if (int rc = load_whitelist(whitelist_path, wl)) return rc;
 	KnownMap known;
-	for (uint32_t c : wl) known[c].prior = 0;
+	if (is_haplotag) all_haplotags(known, [](Known &k) { k.prior = 0; });
+	else {
+		std::vector<uint32_t> wl;
+		if (int rc = load_whitelist(whitelist_path, wl)) return rc;
+		for (uint32_t c : wl) known[c].prior = 0;
+	}
 	std::vector<std::string> full_paths;
 	for (int i = 0; i < n_count_files; ++i) {
 		std::string s(count_files[i]);
 		struct stat sb;
 		if (stat(s.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) return fail(EMAB_ERR_IO, s + " is not a file");
 		if (s.size() < 9 || s.compare(s.size() - 9, 9, ".ema-ncnt") != 0) return fail(EMAB_ERR_ARG, s + " is not an ema-ncnt file");
+		if (is_haplotag) continue;   // no full census to correct from
 		std::string f = s;
 		f[f.size() - 4] = 'f';
 		if (stat(f.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) return fail(EMAB_ERR_IO, f + " is not a file");
@@ -287,12 +316,12 @@ extern "C" int emab_preproc(const char *whitelist_path, const char *const *count
 		while (ok && n-- > 0) {
 			uint32_t code; int64_t cnt;
 			ok = fread(&code, 4, 1, f) == 1 && fread(&cnt, 8, 1, f) == 1;
-			if (ok) known[code].prior += (double)cnt;
+			if (ok) { if (is_haplotag) known[code].n_reads += cnt; else known[code].prior += (double)cnt; }
 		}
 		fclose(f);
 		if (!ok) return fail(EMAB_ERR_IO, "fread failed (corrupted input?)");
 	}
-	{
+	if (!is_haplotag) {
 		double sum = 0;
 		for (const auto &e : known) sum += e.second.prior + 1;
 		for (auto &e : known) e.second.prior = (e.second.prior + 1) / sum;
@@ -332,7 +361,7 @@ extern "C" int emab_preproc(const char *whitelist_path, const char *const *count
 		}
 		fclose(f);
 	}
-	fprintf(stderr, ":: Stats: no change: %lld \n         no barcode: %lld \n       H1-corrected: %lld \n       H2-corrected: %lld \n",
+	if (!is_haplotag) fprintf(stderr, ":: Stats: no change: %lld \n         no barcode: %lld \n       H1-corrected: %lld \n       H2-corrected: %lld \n",
 	        (long long)stats[0], (long long)stats[3], (long long)stats[1], (long long)stats[2]);
 	// ---- output files; barcodes to the emptiest bucket so far, ties to the lower index (cpp/correct.cc:372-411)
 	{
@@ -364,27 +393,33 @@ extern "C" int emab_preproc(const char *whitelist_path, const char *const *count
 	}
 	// ---- the FASTQ, pair by pair (cpp/correct.cc:413-620)
 	Lines in(in_stream ? in_stream : stdin);
-	std::string name, r, q, l;
+	std::string name, r, q, l, tag;
 	ObsKey key;
 	char bc_text[BCL + 1];
 	bc_text[BCL] = 0;
 	bool ok = true;
+	size_t stale_len = 0;   // haplotag: the reference bounds the tag by the length of the LAST line it read into another
+	                        // variable (the previous pair's last line; empty before the first pair): cpp/correct.cc:441
 	auto word = [](const std::string &s) { size_t k = 0; while (k < s.size() && !isspace((unsigned char)s[k])) ++k; return std::string_view(s.data(), k); };
 	while (ok && in.next(name)) {
 		in.next(r); in.next(q); in.next(q);
 		bool process = r.size() >= MIN_READ;
 		uint32_t code = 0;
 		bool has_n = false;
-		if (process) process = observe(r, q, key, code, has_n);
-		if (!process) { for (int k = 0; k < 4; ++k) in.next(l); continue; }
-		auto fx = fixed.find(key);
-		if (fx != fixed.end()) { code = fx->second; has_n = false; }
+		if (is_haplotag) process = haplotag_code(name, stale_len, code, tag) && process;
+		else if (process) process = observe(r, q, key, code, has_n);
+		if (!process) { for (int k = 0; k < 4; ++k) in.next(l); stale_len = l.size(); continue; }
+		if (!is_haplotag) {
+			auto fx = fixed.find(key);
+			if (fx != fixed.end()) { code = fx->second; has_n = false; }
+		}
 		int fidx = 0;
 		auto kn = has_n ? known.end() : known.find(code);
 		if (kn != known.end()) fidx = kn->second.bucket; else code = 0;
 		std::string &o = outs[(size_t)fidx].buf;
 		auto put_bc = [&]() {
 			if (!code) return;
+			if (is_haplotag) { o.append(tag, 0, 12); o.resize(o.size() + (12 - std::min<size_t>(12, tag.size())), '\0'); return; }
 			uint32_t c = code;
 			for (int k = 0; k < BCL; ++k) { bc_text[BCL - k - 1] = "ACGT"[c & 3]; c >>= 2; }
 			o.append(bc_text, BCL);
@@ -394,9 +429,9 @@ extern "C" int emab_preproc(const char *whitelist_path, const char *const *count
 		o.append(word(name));
 		if (fidx) {
 			o.push_back(' ');
-			if (do_bx_format) { o.append("BX:Z:"); put_bc(); o.append("-1\n"); }
+			if (do_bx_format) { o.append("BX:Z:"); put_bc(); o.append(is_haplotag ? "\n" : "-1\n"); }
 		} else o.push_back('\n');
-		const size_t cut = BCL + TRIM, keep = r.size() - cut;
+		const size_t cut = is_haplotag ? 0 : BCL + TRIM, keep = r.size() - cut;   // haplotag reads are not trimmed
 		o.append(r, cut, keep);
 		if (flat) o.push_back(' '); else o.append("\n+\n");
 		{   // the quality is copied for its own length but the cursor moves by the READ's (cpp/correct.cc:556-557)
@@ -408,13 +443,14 @@ extern "C" int emab_preproc(const char *whitelist_path, const char *const *count
 		in.next(l);
 		if (!flat) {
 			o.append(word(l));
-			if (do_bx_format) { o.append(" BX:Z:"); put_bc(); o.append("-1"); }
+			if (do_bx_format) { o.append(" BX:Z:"); put_bc(); if (!is_haplotag) o.append("-1"); }
 			o.push_back('\n');
 		}
 		in.next(l);
 		o.append(l);
 		if (flat) o.push_back(' '); else o.append("\n+\n");
 		in.next(l); in.next(l);
+		stale_len = l.size();
 		o.append(l);
 		o.push_back('\n');
 		if (o.size() >= buffer_size) { ok = put(outs[(size_t)fidx].f, o.data(), o.size()); o.clear(); }

@@ -68,7 +68,7 @@ int emab_index_pack_fasta(const char *fasta_path, const char *prefix);
 /* ---- the producers of the bucket format (host code; need no GPU) ----------------------------
  * emab_count   = count()   (cpp/count.h, cpp/count.cc:38-182):   interleaved FASTQ (in: NULL = stdin) -> <prefix>.ema-ncnt, .ema-fcnt
  * emab_preproc = correct() (cpp/correct.h, cpp/correct.cc:271-633): the count files + the same FASTQ -> <dir>/ema-bin-NNN, ema-nobc
- * Files are byte-identical to the reference's (tests/test_preproc.py).  10x barcodes only: is_haplotag != 0 is refused. */
+ * Files are byte-identical to the reference's (tests/test_preproc.py); is_haplotag as the reference's -p (whitelist_path may be NULL). */
 int emab_count(const char *whitelist_path, const char *output_prefix, uint64_t max_map_bytes, int is_haplotag, FILE *in);
 int emab_preproc(const char *whitelist_path, const char *const *count_files, int n_count_files, const char *output_dir,
                  int do_h2, uint64_t buffer_size, int do_bx_format, int n_threads, int n_buckets, int is_haplotag, FILE *in);

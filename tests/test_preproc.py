@@ -137,7 +137,6 @@ def test_count_block_dumps(raw):
     if ref:
         n = int.from_bytes(ref[:8], "little")
         assert total == sum(int.from_bytes(ref[8 + 24 * i + 16:8 + 24 * i + 24], "little") for i in range(n))
-    assert lib.emab_count(wl.encode(), str(d / "x").encode(), 1 << 30, 1, None) != 0   # haplotag: refused
 
 
 @pytest.mark.parametrize("case", ["empty", "no_final_newline", "one_pair"])
@@ -170,3 +169,43 @@ def test_preproc_several_count_files(raw, tmp_path):
             run([exe, "count", "-w", wl, "-o", str(tmp_path / f"{tag}{i}")], str(tmp_path / f"p{i}.fq"))
         run([exe, "preproc", "-w", wl, "-n", "6", "-t", "2", "-o", str(tmp_path / (tag + "_out")), str(tmp_path / f"{tag}0.ema-ncnt"), str(tmp_path / f"{tag}1.ema-ncnt")], fq)
     same_dir(str(tmp_path / "ref_out"), str(tmp_path / "our_out"))
+
+
+def make_haplotag_fastq(path, n_pairs=3000, seed=3):
+    rng = np.random.default_rng(seed)
+    tags = ["A%02dC%02dB%02dD%02d" % tuple(int(v) for v in rng.integers(1, 97, 4)) for _ in range(40)]
+    with open(path, "wb") as f:
+        for i in range(n_pairs):
+            t = tags[int(rng.integers(0, len(tags)))]
+            u = rng.random()
+            if u < 0.03:
+                hdr = b"@h%d" % i                                   # no tag at all
+            elif u < 0.06:
+                hdr = b"@h%d BX:Z:A00C00B00D00" % i                 # the "no barcode" tag: not one of the 96^4
+            elif u < 0.08:
+                hdr = b"@h%d RG:Z:x\tBX:Z:%s\tQX:Z:y" % (i, t.encode())   # other tags around it, tab separated
+            else:
+                hdr = b"@h%d BX:Z:%s" % (i, t.encode())
+            l1 = int(rng.integers(100, 151)) if rng.random() > 0.02 else int(rng.integers(5, 31))
+            l2 = int(rng.integers(100, 151))
+            r1, r2 = ACGT[rng.integers(0, 4, l1)].tobytes(), ACGT[rng.integers(0, 4, l2)].tobytes()
+            q1, q2 = bytes(rng.integers(35, 75, l1).astype(np.uint8)), bytes(rng.integers(35, 75, l2).astype(np.uint8))
+            f.write(hdr + b"\n" + r1 + b"\n+\n" + q1 + b"\n" + hdr + b"\n" + r2 + b"\n+\n" + q2 + b"\n")
+
+
+@pytest.mark.skipif(os.environ.get("EMAB_SLOW_TESTS") != "1", reason="builds the 96^4-entry haplotag maps four times (~2 minutes, ~6 GB); EMAB_SLOW_TESTS=1 runs it")
+@pytest.mark.parametrize("flags", [[], ["-b"]])
+def test_haplotag_count_and_preproc(flags, tmp_path):
+    """-p: barcodes from the BX:Z: tag of the name line, all 96^4 combinations known, no correction, reads untrimmed — and
+    the reference's quirks (the first pair is never bucketed, the tag is bounded by the previous pair's last line)"""
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/ema not built")
+    fq = str(tmp_path / "h.fq")
+    make_haplotag_fastq(fq)
+    for tag, exe in (("ref", REF), ("our", CLI)):
+        run([exe, "count", "-p", "-o", str(tmp_path / tag)], fq)
+        run([exe, "preproc", "-p", "-n", "5", "-o", str(tmp_path / (tag + "_out"))] + flags + [str(tmp_path / tag) + ".ema-ncnt"], fq)
+    assert filecmp.cmp(str(tmp_path / "ref.ema-ncnt"), str(tmp_path / "our.ema-ncnt"), shallow=False)
+    assert not os.path.exists(str(tmp_path / "our.ema-fcnt")) and not os.path.exists(str(tmp_path / "ref.ema-fcnt"))
+    names = same_dir(str(tmp_path / "ref_out"), str(tmp_path / "our_out"))
+    assert sum(os.path.getsize(str(tmp_path / "our_out" / x)) for x in names if x.startswith("ema-bin")) > 300_000
