@@ -55,6 +55,10 @@ static void build_hot_kmer(HostIndex *h, int K)
 	d.kmer = h->kmer.data();
 }
 
+// 1: the data flow of the device pipeline's default forms — intervals from the seed_hot.cuh algorithm (x1 = 0) and the SA
+// values of a read's occurrences gathered ahead of chain_read in k_sa_gather's enumeration order (pipeline.cu)
+static int g_device_like = 0;
+
 static thread_local long long hs_cnt[6];  // DP calls: extend, global, local; cells: extend, global, local (instrumentation for tools)
 
 struct HostDP {  // scalar stand-in for WarpPolicy (pipeline.cu)
@@ -141,6 +145,8 @@ void *hs_index_load(const char *prefix)
 	build_hot_kmer(h, -1);
 	return h;
 }
+
+void hs_set_device_like(int on) { g_device_like = on; }
 
 // rebuild the k-mer table with another K (0 = no table): the tests walk the table logic at several depths
 void hs_set_kmer_k(void *h_, int K) { build_hot_kmer((HostIndex *)h_, K); }
@@ -265,14 +271,24 @@ static int do_chain(HostIndex *h, int len, const uint8_t *seq, ReadWork &w)
 	w.intv.resize(EMAB_MAX_INTV); w.b0.resize(EMAB_MAX_READ_LEN + 1); w.b1.resize(EMAB_MAX_READ_LEN + 1);
 	Fm fm{h->d, 0};
 	int ovf = 0;
-	int n = collect_intv(fm, len, seq, w.intv.data(), EMAB_MAX_INTV, w.b0.data(), w.b1.data(), &ovf);
+	int n = g_device_like ? collect_intv_hot(h->d, len, seq, w.intv.data(), EMAB_MAX_INTV, w.b0.data(), w.b1.data(), &ovf, nullptr)
+	                      : collect_intv(fm, len, seq, w.intv.data(), EMAB_MAX_INTV, w.b0.data(), w.b1.data(), &ovf);
 	int cap = 0;
 	if (len >= opt::min_seed_len) for (int i = 0; i < n; ++i) cap += intv_occ_count(w.intv[i].x2);
 	w.cap = cap;
 	w.w_seeds.resize(cap + 1); w.seeds.resize(cap + 1); w.w_chains.resize(cap + 1); w.chains.resize(cap + 1);
 	w.nodes.resize(cap / 3 + 3); w.ord.resize(3 * cap + 3); w.srt.resize(cap + 1); w.regs.resize(cap + RESCUE_ROOM_HS + 1);
 	ChainWork wk{w.w_seeds.data(), w.w_chains.data(), w.nodes.data(), w.ord.data()};
-	w.n_chains = chain_read(h->d, len, w.intv.data(), n, wk, cap, w.chains.data(), w.seeds.data());
+	std::vector<int64_t> sa_vals;
+	if (g_device_like && len >= opt::min_seed_len) {
+		for (int i = 0; i < n; ++i) {
+			const Intv &p = w.intv[i];
+			const int cnt = intv_occ_count(p.x2);
+			const int64_t step = p.x2 > (uint64_t)opt::max_occ ? (int64_t)(p.x2 / opt::max_occ) : 1;
+			for (int t = 0; t < cnt; ++t) sa_vals.push_back((int64_t)bwt_sa_dense(h->d, p.x0 + (uint64_t)(t * step)));
+		}
+	}
+	w.n_chains = chain_read(h->d, len, w.intv.data(), n, wk, cap, w.chains.data(), w.seeds.data(), g_device_like ? sa_vals.data() : nullptr);
 	return w.n_chains;
 }
 

@@ -249,11 +249,14 @@ def _chains(lib, fn, idx, s, *flt):
     return ch[:n], sd[:ns.value]
 
 
-@pytest.mark.parametrize("cfg,limit", [("tiny_rep", 480), ("c1_rep", 700)])
-def test_stages_vs_reference(hs, ref_lib, cfg, limit):
+@pytest.mark.parametrize("cfg,limit,device_like", [("tiny_rep", 480, 0), ("c1_rep", 700, 0), ("c1_rep", 400, 1)])
+def test_stages_vs_reference(hs, ref_lib, cfg, limit, device_like):
     """chains after mem_chain_flt, regions after mem_chain2aln, after mem_sort_dedup_patch, after
-    mate rescue, and the final candidates: all bit-exact against the compiled reference."""
+    mate rescue, and the final candidates: all bit-exact against the compiled reference.  device_like: with the data flow
+    of the device pipeline's default forms — intervals of the seed_hot.cuh algorithm (x1 = 0) and the occurrences' SA
+    values gathered ahead of the chaining, as k_sa_gather hands them to k_chain."""
     from tools import synth
+    hs.hs_set_device_like(device_like)
     p = synth.build_config(cfg, helpers.DATA_ROOT, helpers.ref_bin("bwa"))
     pre = p["fasta"].encode()
     hi = C.c_void_p(hs.hs_index_load(pre))
@@ -268,3 +271,4 @@ def test_stages_vs_reference(hs, ref_lib, cfg, limit):
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), ("chain", f[1])
             assert np.array_equal(_regs(hs, "hs_align1", hi, s, 0), _regs(ref_lib, "ref_chain2aln", ri, s)), ("chain2aln", f[1])
             assert np.array_equal(_regs(hs, "hs_align1", hi, s, 1), _regs(ref_lib, "ref_align1", ri, s)), ("align1", f[1])
+    hs.hs_set_device_like(0)
